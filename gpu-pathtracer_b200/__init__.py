@@ -1,0 +1,12 @@
+"""b200-pathtracer: B200-native unidirectional path-tracing integrator behind the reference's
+BeginRender / Render / EndRender boundary (brickray/gpu-pathtracer, src/pathtracer.h:10-12).
+
+    layouts   numpy dtypes of the reference's structs
+    scenes    scene JSON / OBJ front-end and the synthetic config scenes
+    _lib      ctypes binding of the C ABI (include/b200pt.h)
+    renderer  PathTracer: Python mirror of BeginRender / Render / EndRender
+"""
+from . import layouts, scenes  # noqa: F401
+from .renderer import PathTracer, begin_render, render, end_render  # noqa: F401
+
+__all__ = ["layouts", "scenes", "PathTracer", "begin_render", "render", "end_render"]

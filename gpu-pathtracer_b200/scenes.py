@@ -1,0 +1,423 @@
+"""Scene front-end: the data formats on the caller side of the hot path.
+
+Reads the reference's scene JSON (src/parsescene.cpp:45-590) and Wavefront OBJ meshes, and generates the
+synthetic benchmark scenes of BASELINE.json (C3 stand-in geometry, C4 random triangles + analytic HDRI).
+Output is a `SceneArrays` holding numpy arrays in the reference's struct layouts (layouts.py) — exactly what
+`b200pt_scene_view` (include/b200pt.h) points at.  BVH, light CDF and camera go through the host-side C ABI
+(`b200pt_bvh_build`, `b200pt_light_distribution`, `b200pt_camera_init`) unless a `prep` override is given
+(the tests pass the reference's own Scene::Init from oracle/_ref to pin them).
+
+Mesh import caveat: the reference imports through Assimp, which is not available; meshes with
+explicit normals and triangle faces (all config geometry) are unambiguous, anything else is rejected loudly.
+"""
+import json
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import layouts as L
+
+F = np.float32
+
+
+@dataclass
+class SceneArrays:
+    width: int
+    height: int
+    epsilon: float
+    integrator_type: int
+    max_depth: int
+    camera: np.ndarray                 # 1 x Camera
+    prims: np.ndarray                  # Primitive[] in BVH leaf order
+    nodes: np.ndarray                  # LinearBVHNode[]
+    materials: np.ndarray
+    mediums: np.ndarray
+    lights: np.ndarray                 # Area[]
+    light_distribution: np.ndarray     # float32 CDF
+    infinite: np.ndarray = None        # 1 x Infinite or None
+    infinite_texels: np.ndarray = None  # (h, w, 3) float32, kept alive for infinite.data
+    root_box: np.ndarray = None
+    name: str = ""
+    meta: dict = field(default_factory=dict)
+
+
+# ------------------------------------------------------------------------------------------------ OBJ / meshes
+def load_obj(path):
+    """Triangles of an OBJ file as (n_tri, 3) records of (v, n, uv). Requires explicit vn; fan-triangulates
+    polygons in file order (Assimp's Triangulate does the same for convex quads)."""
+    vs, vns, vts, faces = [], [], [], []
+    with open(path) as f:
+        for line in f:
+            p = line.split()
+            if not p:
+                continue
+            if p[0] == "v":
+                vs.append([float(x) for x in p[1:4]])
+            elif p[0] == "vn":
+                vns.append([float(x) for x in p[1:4]])
+            elif p[0] == "vt":
+                vts.append([float(x) for x in p[1:3]])
+            elif p[0] == "f":
+                corners = []
+                for c in p[1:]:
+                    idx = c.split("/")
+                    vi = int(idx[0])
+                    ti = int(idx[1]) if len(idx) > 1 and idx[1] else 0
+                    ni = int(idx[2]) if len(idx) > 2 and idx[2] else 0
+                    if ni == 0:
+                        raise ValueError(f"{path}: face without normals; smooth-normal generation (Assimp) is not reproduced")
+                    corners.append((vi, ti, ni))
+                for k in range(1, len(corners) - 1):
+                    faces.append((corners[0], corners[k], corners[k + 1]))
+    vs = np.asarray(vs, F).reshape(-1, 3)
+    vns = np.asarray(vns, F).reshape(-1, 3)
+    vts = np.asarray(vts, F).reshape(-1, 2)
+    tri_v = np.zeros((len(faces), 3, 3), F)
+    tri_n = np.zeros((len(faces), 3, 3), F)
+    tri_uv = np.zeros((len(faces), 3, 2), F)
+    for i, fc in enumerate(faces):
+        for k, (vi, ti, ni) in enumerate(fc):
+            tri_v[i, k] = vs[vi - 1 if vi > 0 else vi]
+            tri_n[i, k] = vns[ni - 1 if ni > 0 else ni]
+            if ti:
+                tri_uv[i, k] = vts[ti - 1 if ti > 0 else ti]
+    return tri_v, tri_n, tri_uv
+
+
+def _trs(scale, translate, rotate_deg):
+    """glm: trs = t * r * s with r = Rx * Ry * Rz (src/parsescene.cpp:349-355), float32."""
+    def rot(axis, deg):
+        a = F(np.radians(F(deg)))
+        c, s = F(np.cos(a)), F(np.sin(a))
+        m = np.eye(4, dtype=F)
+        i, j = [(1, 2), (2, 0), (0, 1)][axis]
+        m[i, i] = c; m[j, j] = c; m[i, j] = -s; m[j, i] = s
+        return m
+    S = np.diag(np.asarray(list(scale) + [1], F))
+    T = np.eye(4, dtype=F); T[:3, 3] = np.asarray(translate, F)
+    R = (rot(0, rotate_deg[0]) @ rot(1, rotate_deg[1]) @ rot(2, rotate_deg[2])).astype(F)
+    return (T @ R @ S).astype(F)
+
+
+def _transform_mesh(tri_v, tri_n, trs):
+    """Mesh::processMesh (src/mesh.cpp:50-62): v' = trs*(v,1); n' = normalize(inverse-transpose * (n,0))."""
+    if np.array_equal(trs, np.eye(4, dtype=F)):
+        v = tri_v.copy()
+        nn = tri_n
+    else:
+        v = (tri_v @ trs[:3, :3].T + trs[:3, 3]).astype(F)
+        invT = np.linalg.inv(trs.astype(np.float64)).T.astype(F)
+        nn = (tri_n @ invT[:3, :3].T).astype(F)
+    # glm::normalize = v * (1 / sqrt(dot(v, v))) in float32, dot = (x*x + y*y) + z*z
+    d = (nn[..., 0] * nn[..., 0] + nn[..., 1] * nn[..., 1]).astype(F) + (nn[..., 2] * nn[..., 2]).astype(F)
+    inv = (F(1.0) / np.sqrt(d.astype(F))).astype(F)
+    return v, (nn * inv[..., None]).astype(F)
+
+
+def triangles_to_prims(tri_v, tri_n, tri_uv, mat_idx, medium_inside=-1, medium_outside=-1, light_base=None):
+    n = tri_v.shape[0]
+    prims = np.zeros(n, L.Primitive)
+    prims["type"] = L.GT_TRIANGLE
+    t = prims["triangle"]
+    for k, name in enumerate(("v1", "v2", "v3")):
+        t[name]["v"] = tri_v[:, k]
+        t[name]["n"] = tri_n[:, k]
+        t[name]["uv"] = tri_uv[:, k]
+    t["matIdx"] = mat_idx
+    t["bssrdfIdx"] = -1
+    t["lightIdx"] = -1 if light_base is None else light_base + np.arange(n, dtype=np.int32)
+    t["mediumInside"] = medium_inside
+    t["mediumOutside"] = medium_outside
+    prims["triangle"] = t
+    return prims
+
+
+def sphere_prim(center, radius, mat_idx, medium_inside=-1, medium_outside=-1):
+    p = np.zeros(1, L.PrimitiveSphere)
+    p["type"] = L.GT_SPHERE
+    s = p["sphere"]
+    s["origin"] = np.asarray(center, F); s["radius"] = F(radius)
+    s["matIdx"] = mat_idx; s["bssrdfIdx"] = -1
+    s["mediumInside"] = medium_inside; s["mediumOutside"] = medium_outside
+    p["sphere"] = s
+    return p.view(L.Primitive)
+
+
+def make_material(bsdf="lambertian", diffuse=(1, 1, 1), specular=(1, 1, 1), alphaU=0.01, alphaV=0.01,
+                  insideIOR=1.0, outsideIOR=1.0, k=(0, 0, 0), eta=(0, 0, 0)):
+    m = np.zeros(1, L.Material)
+    m["type"] = L.MATERIAL_TYPES[bsdf]
+    m["alphaU"] = F(alphaU); m["alphaV"] = F(alphaV)
+    m["insideIOR"] = F(insideIOR); m["outsideIOR"] = F(outsideIOR)
+    m["k"] = np.asarray(k, F); m["eta"] = np.asarray(eta, F)
+    m["diffuse"] = np.asarray(diffuse, F); m["specular"] = np.asarray(specular, F)
+    m["textureIdx"] = -1
+    return m
+
+
+def make_homogeneous_medium(sigmaA, sigmaS, g=0.0, scale=1.0):
+    m = np.zeros(1, L.Medium)
+    a = (np.asarray(sigmaA, F) * F(scale)).astype(F)
+    s = (np.asarray(sigmaS, F) * F(scale)).astype(F)
+    m["type"] = L.MT_HOMOGENEOUS; m["g"] = F(g)
+    m["sigmaA"] = a; m["sigmaS"] = s; m["sigmaT"] = (a + s).astype(F)
+    return m
+
+
+# ------------------------------------------------------------------------------------------------ assembly
+def _default_prep():
+    from . import _lib
+    return _lib.HostPrep()
+
+
+def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials, mediums, prims, lights,
+             infinite=None, infinite_texels=None, prep=None, meta=None):
+    """Scene::Init (src/scene.h:50-82): BVH over all primitives, infinite.Init(root_box), light CDF; plus the
+    camera construction of src/main.cpp:268-270."""
+    prep = prep or _default_prep()
+    prims = np.ascontiguousarray(prims)
+    lights = np.ascontiguousarray(lights) if lights is not None and len(lights) else np.zeros(0, L.Area)
+    prims_o, nodes, lightdist, root_box, infinite = prep.scene_init(prims, lights, infinite, infinite_texels)
+    camera = prep.camera(cam["position"], cam["lookat"], cam["up"], width, height, 0.1, cam["fov"],
+                         cam.get("apertureRadius", 0.0), cam.get("focalDistance", 0.0),
+                         cam.get("filmicTonemap", True), cam.get("environment", False), cam.get("medium", -1))
+    return SceneArrays(width=width, height=height, epsilon=float(epsilon),
+                       integrator_type={"pt": L.IT_PT, "vpt": L.IT_VPT}[integrator], max_depth=int(max_depth),
+                       camera=camera, prims=prims_o, nodes=nodes,
+                       materials=np.ascontiguousarray(materials), mediums=np.ascontiguousarray(mediums),
+                       lights=lights, light_distribution=lightdist, infinite=infinite,
+                       infinite_texels=infinite_texels, root_box=root_box, name=name, meta=meta or {})
+
+
+def load_scene_json(path, prep=None, overrides=None):
+    """The subset of LoadScene (src/parsescene.cpp:45) the hot path's configs use: homogeneous media, constant
+    colour materials, OBJ meshes with TRS, spheres, mesh area lights.  Raises on anything else."""
+    with open(path) as f:
+        doc = json.load(f)
+    if overrides:
+        doc.update(overrides)
+    base = os.path.dirname(os.path.abspath(path))
+    medium_names, mediums = [], []
+    for m in doc.get("medium", []):
+        if m.get("type", "homogeneous") != "homogeneous":
+            raise ValueError("heterogeneous media are outside the hot path (SURVEY §8(f).3)")
+        mediums.append(make_homogeneous_medium(m.get("sigmaA", [1, 1, 1]), m.get("sigmaS", [1, 1, 1]),
+                                               m.get("g", 0.0), m.get("scale", 1.0)))
+        medium_names.append(m["name"])
+    mediums = L.cat(mediums, L.Medium)
+
+    def medium_idx(name):
+        return medium_names.index(name) if name in medium_names else -1
+
+    width = doc.get("screen_width", 512); height = doc.get("screen_height", 512)
+    if not ("screen_width" in doc and "screen_height" in doc):
+        width = height = 512
+    epsilon = doc.get("epsilon", 0.001)
+    c = doc["camera"]
+    cam = {"position": c.get("position", [0, 0, 0]), "lookat": c.get("lookat", [0, 0, -1]), "up": c.get("up", [0, 1, 0]),
+           "fov": c.get("fov", 60.0), "apertureRadius": c.get("apertureRadius", 0.0),
+           "focalDistance": c.get("focalDistance", 0.0), "filmicTonemap": c.get("filmicTonemap", True),
+           "environment": c.get("environment", False), "medium": medium_idx(c.get("medium", ""))}
+    integrator = doc.get("integrator", "pt")
+    if integrator not in ("pt", "vpt"):
+        raise ValueError(f"integrator {integrator!r} is outside the hot path")
+    max_depth = doc.get("maxDepth", 5)
+
+    mat_names, mats = [], []
+    for m in doc.get("material", []):
+        if "bssrdf" in m:
+            raise ValueError("bssrdf materials are unreachable on the device path")
+        if isinstance(m.get("diffuse"), str):
+            raise ValueError("textured materials are a 'next' row (SURVEY §8(f).2)")
+        if m.get("remap", False):
+            raise ValueError("roughness remap not supported by this front-end")
+        if "alpha" in m:
+            au = av = m["alpha"]
+        else:
+            au, av = m.get("alphaU", 0.01), m.get("alphaV", 0.01)
+        mats.append(make_material(m["bsdf"], m.get("diffuse", [1, 1, 1]), m.get("specular", [1, 1, 1]), au, av,
+                                  m.get("insideIOR", 1.0), m.get("outsideIOR", 1.0), m.get("k", [0, 0, 0]),
+                                  m.get("eta", [0, 0, 0])))
+        mat_names.append(m["name"])
+    materials = L.cat(mats, L.Material)
+
+    def mat_idx(name):
+        return mat_names.index(name)   # first match, like the reference's linear search
+
+    prims = []
+    for u in doc.get("scene", []):
+        mi, mo = medium_idx(u.get("inside", "")), medium_idx(u.get("outside", ""))
+        mat_name = u.get("material", "")
+        midx = -1
+        if mat_name != "" or not (mi != -1 or mo != -1):
+            midx = mat_idx(mat_name)
+        if "mesh" in u:
+            tv, tn, tuv = load_obj(os.path.join(base, u["mesh"]))
+            trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
+            tv, tn = _transform_mesh(tv, tn, trs)
+            prims.append(triangles_to_prims(tv, tn, tuv, midx, mi, mo))
+        elif "sphere" in u:
+            prims.append(sphere_prim(u.get("center", [0, 0, 0]), u.get("radius", 1.0), midx, mi, mo))
+        else:
+            raise ValueError("line primitives are a 'next' row (SURVEY §8(f).2)")
+    lights = []
+    n_lights = 0
+    for u in doc.get("light", []):
+        if "mesh" not in u:
+            raise ValueError("infinite lights load from .exr, which is not shipped; use the generators")
+        tv, tn, tuv = load_obj(os.path.join(base, u["mesh"]))
+        trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
+        tv, tn = _transform_mesh(tv, tn, trs)
+        # light triangles: mediumInside/Outside are left untouched by the reference (src/parsescene.cpp:531-541);
+        # we define them as -1
+        p = triangles_to_prims(tv, tn, tuv, mat_idx(u.get("material", "matte")), -1, -1, light_base=n_lights)
+        prims.append(p)
+        a = np.zeros(len(p), L.Area)
+        a["radiance"] = np.asarray(u.get("radiance", [0, 0, 0]), F)
+        a["triangle"] = p["triangle"]
+        a["medium"] = medium_idx(u.get("medium", ""))
+        lights.append(a)
+        n_lights += len(p)
+    prims = L.cat(prims, L.Primitive)
+    lights = L.cat(lights, L.Area)
+    return assemble(os.path.basename(path), width, height, epsilon, integrator, max_depth, cam, materials, mediums,
+                    prims, lights, prep=prep, meta={"json": path})
+
+
+# ------------------------------------------------------------------------------------------------ configs
+def golden_dir():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def cornell_pt(width=256, height=256, max_depth=4, prep=None):
+    """C1/C2: shipped Cornell materials/camera/light as `pt`, with short+tall boxes."""
+    return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "cornell_pt.json"), prep=prep,
+                           overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
+
+
+def cornell_vol_caustic(width=512, height=512, max_depth=17, prep=None):
+    """C5: vol_caustic.json as `vpt` with the regular Cornell emitter."""
+    return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "vol_caustic_vpt.json"), prep=prep,
+                           overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
+
+
+def _box_tris(lo, hi, inward=False):
+    lo = np.asarray(lo, F); hi = np.asarray(hi, F)
+    c = np.array([[lo[0], lo[1], lo[2]], [hi[0], lo[1], lo[2]], [hi[0], hi[1], lo[2]], [lo[0], hi[1], lo[2]],
+                  [lo[0], lo[1], hi[2]], [hi[0], lo[1], hi[2]], [hi[0], hi[1], hi[2]], [lo[0], hi[1], hi[2]]], F)
+    quads = [(0, 3, 2, 1, (0, 0, -1)), (4, 5, 6, 7, (0, 0, 1)), (0, 1, 5, 4, (0, -1, 0)),
+             (3, 7, 6, 2, (0, 1, 0)), (0, 4, 7, 3, (-1, 0, 0)), (1, 2, 6, 5, (1, 0, 0))]
+    tv, tn, tuv = [], [], []
+    uvq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], F)
+    for a, b, cc, d, n in quads:
+        n = np.asarray(n, F) * (F(-1) if inward else F(1))
+        for tri in ((0, 1, 2), (0, 2, 3)):
+            idx = [(a, b, cc, d)[k] for k in tri]
+            tv.append(c[idx]); tn.append(np.tile(n, (3, 1))); tuv.append(uvq[list(tri)])
+    return np.asarray(tv, F), np.asarray(tn, F), np.asarray(tuv, F)
+
+
+def _ellipsoid_tris(center, radii, nu=24, nv=12):
+    center = np.asarray(center, np.float64); radii = np.asarray(radii, np.float64)
+    def pt(i, j):
+        th = np.pi * j / nv; ph = 2 * np.pi * i / nu
+        d = np.array([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)])
+        p = center + radii * d
+        n = d / radii; n /= np.linalg.norm(n)
+        return p, n, np.array([i / nu, j / nv])
+    tv, tn, tuv = [], [], []
+    for j in range(nv):
+        for i in range(nu):
+            q = [pt(i, j), pt(i + 1, j), pt(i + 1, j + 1), pt(i, j + 1)]
+            for tri in ((0, 3, 2), (0, 2, 1)):
+                if j == 0 and tri == (0, 2, 1):
+                    continue
+                if j == nv - 1 and tri == (0, 3, 2):
+                    continue
+                tv.append([q[k][0] for k in tri]); tn.append([q[k][1] for k in tri]); tuv.append([q[k][2] for k in tri])
+    return np.asarray(tv, F), np.asarray(tn, F), np.asarray(tuv, F)
+
+
+def veach_standin(width=768, height=576, max_depth=17, prep=None):
+    """C3: materials / lights / camera of scenes/veach_bidir/scene.json verbatim over a procedural stand-in
+    geometry (the .ply assets are not shipped): room box, table, glass ellipsoid, rough-metal
+    block, a small bright floor-lamp emitter and a wall-spot emitter.  z is up (camera up = +z)."""
+    mats = L.cat([
+        make_material("dielectric", specular=(1, 1, 1), insideIOR=1.5, outsideIOR=1.0),                       # glass
+        make_material("lambertian", diffuse=(0.616, 0.4752, 0.352)),                                           # lamp
+        make_material("roughconduct", alphaU=0.2, alphaV=0.2, eta=(2.865601, 2.119182, 1.940077),
+                      k=(3.032326, 2.056108, 1.616293)),                                                       # lamp1
+        make_material("lambertian", diffuse=(0.5, 0.5, 0.5)),                                                  # matte
+        make_material("lambertian", diffuse=(0.32963, 0.257976, 0.150292)),                                    # wood
+    ], L.Material)
+    GLASS, LAMP, LAMP1, MATTE, WOOD = range(5)
+    prims = []
+    prims.append(triangles_to_prims(*_box_tris((-3.0, -7.5, -1.0), (3.0, 1.5, 2.6), inward=True), MATTE))      # room
+    prims.append(triangles_to_prims(*_box_tris((-1.3, -5.2, -0.32), (0.9, -3.4, -0.25)), WOOD))                # table top
+    for lx, ly in ((-1.2, -5.1), (0.7, -5.1), (-1.2, -3.6), (0.7, -3.6)):
+        prims.append(triangles_to_prims(*_box_tris((lx, ly, -1.0), (lx + 0.1, ly + 0.1, -0.32)), WOOD))        # legs
+    prims.append(triangles_to_prims(*_ellipsoid_tris((-0.45, -4.3, 0.05), (0.22, 0.22, 0.30)), GLASS))         # glass egg
+    prims.append(triangles_to_prims(*_box_tris((0.15, -4.6, -0.25), (0.55, -4.2, 0.15)), LAMP1))               # metal block
+    prims.append(triangles_to_prims(*_box_tris((1.9, -2.2, -1.0), (2.0, -2.1, 1.2)), LAMP1))                   # lamp pole
+    lights = []
+    # floor-lamp emitter: tiny downward quad under a shade (radiance 7000, 5450, 3630)
+    def quad_light(p0, du, dv, n, radiance, base):
+        p0 = np.asarray(p0, F); du = np.asarray(du, F); dv = np.asarray(dv, F)
+        q = [p0, p0 + du, p0 + du + dv, p0 + dv]
+        uvq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], F)
+        tv = np.asarray([[q[0], q[1], q[2]], [q[0], q[2], q[3]]], F)
+        tn = np.tile(np.asarray(n, F), (2, 3, 1))
+        tuv = np.asarray([uvq[[0, 1, 2]], uvq[[0, 2, 3]]], F)
+        p = triangles_to_prims(tv, tn, tuv, LAMP, -1, -1, light_base=base)
+        a = np.zeros(2, L.Area)
+        a["radiance"] = np.asarray(radiance, F); a["triangle"] = p["triangle"]; a["medium"] = -1
+        return p, a
+    p, a = quad_light((1.93, -2.17, 1.19), (0.04, 0, 0), (0, 0.04, 0), (0, 0, -1), (7000.0, 5450.0, 3630.0), 0)
+    prims.append(p); lights.append(a)
+    p, a = quad_light((-2.99, -4.6, 1.4), (0, 0.15, 0), (0, 0, 0.15), (1, 0, 0), (500.0, 500.0, 500.0), 2)
+    prims.append(p); lights.append(a)
+    cam = {"position": [-0.223944, -6.642450, 0.366128], "lookat": [-0.261616, -5.644770, 0.309317],
+           "up": [0.0, 0.0, 1.0], "fov": 34.156548, "medium": -1}
+    return assemble("veach_standin", width, height, 0.001, "pt", max_depth, cam, mats, np.zeros(0, L.Medium),
+                    L.cat(prims, L.Primitive), L.cat(lights, L.Area), prep=prep)
+
+
+def sky_texels(w=512, h=256):
+    """Analytic HDRI for C4: vertical sky gradient + Gaussian sun (no .exr is shipped)."""
+    v = (np.arange(h, dtype=np.float64) + 0.5) / h           # 0 = +v pole (zenith)
+    u = (np.arange(w, dtype=np.float64) + 0.5) / w
+    theta = np.pi * v[:, None]; phi = 2 * np.pi * u[None, :]
+    up = np.cos(theta)
+    sky = np.stack([0.35 + 0.25 * up, 0.5 + 0.3 * up, 0.8 + 0.4 * up], -1) * np.ones((h, w, 1))
+    sky = np.where(up[..., None] < 0, np.array([0.25, 0.22, 0.2]) * (1 + 0.5 * up[..., None]), sky)
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta) * np.ones_like(phi), np.sin(theta) * np.sin(phi)], -1)
+    sun = np.array([0.5, 0.7, 0.5]); sun /= np.linalg.norm(sun)
+    ang = np.arccos(np.clip(d @ sun, -1, 1))
+    sky = sky + np.array([40.0, 36.0, 30.0]) * np.exp(-(ang / 0.08) ** 2)[..., None]
+    return np.ascontiguousarray(sky.astype(F))
+
+
+def random_triangles(n_tris=1_000_000, width=2048, height=2048, max_depth=8, seed=12345, prep=None):
+    """C4: n random triangles (centre uniform in [-1,1]^3, edges uniform in [-0.02,0.02]^3, flat normals,
+    lambertian 0.725) lit only by the analytic infinite light; camera (0,0,6.8)->(0,0,0), fov 19.5."""
+    rs = np.random.RandomState(seed)
+    U = lambda *shape: ((rs.randint(0, 2 ** 32, size=shape, dtype=np.uint32) >> np.uint32(8)).astype(np.float64) / 2 ** 24)
+    c = (U(n_tris, 3) * 2 - 1).astype(F)
+    a = ((U(n_tris, 3) * 2 - 1) * 0.02).astype(F)
+    b = ((U(n_tris, 3) * 2 - 1) * 0.02).astype(F)
+    nrm = np.cross(a.astype(np.float64), b.astype(np.float64))
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    tv = np.stack([c, (c + a).astype(F), (c + b).astype(F)], 1).astype(F)
+    tn = np.repeat(nrm.astype(F)[:, None, :], 3, 1)
+    tuv = np.zeros((n_tris, 3, 2), F)
+    prims = triangles_to_prims(tv, tn, tuv, 0)
+    mats = make_material("lambertian", diffuse=(0.725, 0.725, 0.725))
+    tex = sky_texels()
+    inf = np.zeros(1, L.Infinite)
+    inf["data"] = tex.ctypes.data; inf["width"] = tex.shape[1]; inf["height"] = tex.shape[0]
+    inf["u"] = (1, 0, 0); inf["v"] = (0, 1, 0); inf["w"] = (0, 0, 1); inf["isvalid"] = 1
+    cam = {"position": [0, 0, 6.8], "lookat": [0, 0, 0], "up": [0, 1, 0], "fov": 19.5, "medium": -1}
+    return assemble(f"random_tris_{n_tris}", width, height, 0.001, "pt", max_depth, cam, mats, np.zeros(0, L.Medium),
+                    prims, np.zeros(0, L.Area), infinite=inf, infinite_texels=tex, prep=prep,
+                    meta={"seed": seed, "n_tris": n_tris})

@@ -1,0 +1,150 @@
+/* b200pt.h — C ABI of the B200-native unidirectional path-tracing integrator.
+ *
+ * Drop-in boundary: these entry points are what an FFI / adapter for the reference's
+ *     void BeginRender(Scene&, unsigned w, unsigned h, float ep);                      (src/pathtracer.h:11)
+ *     void Render(Scene&, unsigned w, unsigned h, Camera*, unsigned iter, bool reset,
+ *                 float3* output);                                                     (src/pathtracer.h:10)
+ *     void EndRender();                                                                (src/pathtracer.h:12)
+ * binds.  `gpu-pathtracer_b200/csrc/pathtracer_adapter.cpp` implements exactly those three C++ symbols on
+ * top of this header.
+ *
+ * All scene arrays are passed in the REFERENCE's own struct layouts (byte-for-byte what the reference's
+ * BeginRender cudaMemcpy's, src/pathtracer.cu:2578-2671); the implementation re-lays them out on upload.
+ * Plain pointers and sizes only; no C++ / torch types.  Every function returns 0 on success or a negative
+ * B200PT_E* code; b200pt_last_error() returns a human-readable message for the calling thread's last failure.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- reference struct sizes (verified with sizeof/offsetof on the reference headers) ------------------ */
+#define B200PT_SIZEOF_CAMERA      104  /* src/camera.h:8      */
+#define B200PT_SIZEOF_PRIMITIVE   176  /* src/primitive.h:15  (tag@0, union@8; Triangle 168 B, src/mesh.h:20) */
+#define B200PT_SIZEOF_BVHNODE      40  /* src/bvh.h:19        (bbox@0, second_child_offset@24, is_leaf@28, start@32, end@36) */
+#define B200PT_SIZEOF_MATERIAL     72  /* src/material.h:19   */
+#define B200PT_SIZEOF_MEDIUM      104  /* src/medium.h:186    */
+#define B200PT_SIZEOF_AREA        192  /* src/area.h:7        */
+#define B200PT_SIZEOF_INFINITE     72  /* src/infinite.h:6    */
+
+/* IntegratorType values the hot path implements (src/scene.h:15-24). */
+#define B200PT_IT_PT   1   /* IT_PT  -> Path    (src/pathtracer.cu:880)  */
+#define B200PT_IT_VPT  2   /* IT_VPT -> Volpath (src/pathtracer.cu:1025) */
+
+/* error codes */
+#define B200PT_OK            0
+#define B200PT_EINVAL       -1   /* bad argument / unsupported scene feature */
+#define B200PT_ECUDA        -2   /* CUDA runtime error (message in b200pt_last_error) */
+#define B200PT_ENOMEM       -3
+#define B200PT_EUNSUPPORTED -4   /* integrator / primitive / medium type outside the hot path */
+
+/* One uchar4 texture (src/texture.h:9, uploaded at src/pathtracer.cu:2646-2661). */
+typedef struct b200pt_texture {
+    const void* texels;   /* width*height uchar4, row-major */
+    int32_t width, height;
+} b200pt_texture;
+
+/* Everything BeginRender reads from `Scene&` (src/pathtracer.cu:2578-2671, :2711-2717). Host pointers. */
+typedef struct b200pt_scene_view {
+    const void*  camera;             /* 1 x Camera (104 B) — scene.camera                                   */
+    const void*  prims;              /* n_prims x Primitive (176 B), in BVH leaf order — scene.bvh.prims     */
+    const void*  nodes;              /* n_nodes x LinearBVHNode (40 B) — scene.bvh.linear_root               */
+    const void*  materials;          /* n_materials x Material (72 B)                                        */
+    const void*  mediums;            /* n_mediums x Medium (104 B); heterogeneous density = host pointer     */
+    const void*  lights;             /* n_lights x Area (192 B)                                              */
+    const void*  infinite;           /* 1 x Infinite (72 B; data = host float3 texels) or NULL               */
+    const float* light_distribution; /* n_light_distribution floats — scene.lightDistribution (CDF)          */
+    const b200pt_texture* textures;  /* n_textures entries or NULL                                           */
+    int32_t n_prims, n_nodes, n_materials, n_mediums, n_lights, n_light_distribution, n_textures;
+    int32_t integrator_type;         /* scene.integrator.type  (B200PT_IT_*)                                 */
+    int32_t max_depth;               /* scene.integrator.maxDepth                                            */
+} b200pt_scene_view;
+
+/* Pixel-tile shard of the image this context renders (multi-GPU: rank r of n takes tiles k with k % n == r).
+ * tile_w x tile_h screen tiles in row-major tile order; n_shards == 1 renders everything. */
+typedef struct b200pt_shard {
+    int32_t shard, n_shards;
+    int32_t tile_w, tile_h;
+} b200pt_shard;
+
+typedef struct b200pt_ctx b200pt_ctx;
+
+/* Replaces BeginRender (src/pathtracer.cu:2568): deep-copies + re-lays-out the scene onto `device`.
+ * `shard` may be NULL (whole image).  width % 32 == 0 and height % 4 == 0 as in the reference's launch
+ * (src/pathtracer.cu:2707-2709). */
+int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uint32_t height, float epsilon,
+                  int device, const b200pt_shard* shard, b200pt_ctx** out_ctx);
+
+/* Replaces `spp` consecutive calls Render(scene,w,h,camera,iter,reset&&iter==first_iter,output) for
+ * iter = first_iter .. first_iter+spp-1 (src/pathtracer.cu:2705-2750).  spp == 1 is exactly one Render call.
+ * `camera` (104-B reference Camera, host) is re-read every call like src/pathtracer.cu:2706.
+ * `output` receives the tonemapped w*h float3 image of the LAST iteration (what Output writes,
+ * src/pathtracer.cu:2516-2531); it may be NULL, a device pointer (output_is_device=1; the reference's
+ * contract) or a host pointer (0).  Pixels outside this context's shard are written as 0.
+ * Returns after the results are visible. */
+int b200pt_render(b200pt_ctx* ctx, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
+                  float* output, int output_is_device);
+
+/* Same, asynchronous on the context's stream with everything device-resident (no host copies, no sync):
+ * used for device-timed benchmarking; pair with b200pt_sync. */
+int b200pt_render_async(b200pt_ctx* ctx, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
+                        float* output_device);
+int b200pt_sync(b200pt_ctx* ctx);
+
+/* Linear accumulation buffer kernel_acc_image (src/pathtracer.cu:10,2525): w*h float3, sum over iterations.
+ * dst may be host (dst_is_device=0) or device.  Pixels outside the shard are 0 (so shards sum exactly). */
+int b200pt_get_accum(b200pt_ctx* ctx, float* dst, int dst_is_device);
+/* Device pointer of the same buffer (for an in-place NCCL reduce over NVLink by the caller). */
+int b200pt_accum_device_ptr(b200pt_ctx* ctx, float** out_ptr);
+/* Last per-iteration radiance kernel_color (src/pathtracer.cu:1019-1020), w*h float3, host. */
+int b200pt_get_color(b200pt_ctx* ctx, float* dst_host);
+/* Tonemap an externally reduced accumulation image: out = tonemap(acc / iter) (src/pathtracer.cu:2526-2530). */
+int b200pt_tonemap(b200pt_ctx* ctx, const float* acc_device, uint32_t iter, float* out_device);
+
+/* Primary-visibility debug/parity query: for every pixel of iteration `iter` the closest hit of the camera
+ * ray — t (or -1), primitive index, barycentrics b1,b2 — as computed by the traversal kernel
+ * (parity target: Intersect, src/pathtracer.cu:214).  hits_host: w*h * 4 floats (t, prim as int bits, b1, b2). */
+int b200pt_trace_primary(b200pt_ctx* ctx, const void* camera, uint32_t iter, float* hits_host);
+
+/* Counters of the last render call: [0]=samples, [1]=kernel launches, [2]=rays traced, [3]=wavefront steps,
+ * [4]=device ms (CUDA events around the call's stream work). */
+int b200pt_stats(b200pt_ctx* ctx, double* out5);
+
+/* Tunables (pool = number of path slots in flight; 0 keeps default). */
+int b200pt_set_option(b200pt_ctx* ctx, const char* name, int64_t value);
+
+/* Replaces EndRender (src/pathtracer.cu:2697); frees ALL device memory of the context. */
+int b200pt_destroy(b200pt_ctx* ctx);
+
+const char* b200pt_last_error(void);
+int b200pt_version(void);
+
+/* ---- scene preparation (SURVEY §8(f) "next" rows; host side, C++) ------------------------------------- */
+
+/* Binned-SAH BVH2 build + flatten, same algorithm and output layout as BVH::build/split/flatten
+ * (src/bvh.cpp:16-173): reorders prims into leaf order and emits LinearBVHNode[].
+ * prims_in/out: n x 176-B Primitive; nodes_out capacity must be >= 2*n; returns node count in *n_nodes. */
+int b200pt_bvh_build(const void* prims_in, int32_t n_prims, void* prims_out, void* nodes_out,
+                     int32_t nodes_capacity, int32_t* n_nodes, float* root_box6);
+
+/* Camera constructor arithmetic (src/camera.h:31-47 + Lookat :124-129): fills a 104-B reference Camera. */
+int b200pt_camera_init(void* camera104, const float* position3, const float* lookat3, const float* up3,
+                       float res_x, float res_y, float distance, float fov, float aperture_radius,
+                       float focal_distance, int filmic, int environment, int medium);
+
+/* Light-selection CDF of Scene::Init (src/scene.h:65-82). out has n_lights+1 (+1 if infinite valid) floats. */
+int b200pt_light_distribution(const void* lights, int32_t n_lights, const void* infinite_or_null,
+                              float* out, int32_t* n_out);
+
+/* Infinite::Init (src/infinite.h:61 -> BBox::boundingSphere, src/bbox.h:98): sets center/radius in place. */
+int b200pt_infinite_init(void* infinite72, const float* root_box6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — generates tests/golden/ from the reference (run in the build container, where
+/root/reference exists; the GPU box only sees the committed outputs).
+
+ 1. scene fixtures: the Cornell geometry/material/camera data of scenes/cornell_box (inputs, not source code)
+    copied verbatim + the two derived scene files of SURVEY §8(d) (C1/C2 `cornell_pt.json`, C5
+    `vol_caustic_vpt.json`).
+ 2. golden scene arrays: output of the reference's own Scene::Init (BVH build, light CDF) and Camera ctor,
+    run through oracle/_ref/libref_host.so, for every config scene (cornell, vol_caustic, veach stand-in,
+    20k random triangles).
+ 3. golden function-level vectors and small golden images rendered by the reference's own kernel bodies
+    (host build).  GPU goldens (reference CUDA build on a B200) are added by oracle/make_gpu_goldens.py.
+"""
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("B200PT_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def stage_scene_files():
+    src = os.path.join(REF, "scenes", "cornell_box")
+    dst = os.path.join(GOLD, "scenes", "cornell_box")
+    os.makedirs(os.path.join(dst, "geometry"), exist_ok=True)
+    for f in ["floor", "ceil", "back", "left", "right", "short", "tall", "light",
+              "mesh_0", "mesh_1", "mesh_2", "mesh_3", "mesh_4", "mesh_5", "mesh_6"]:
+        shutil.copy(os.path.join(src, "geometry", f + ".obj"), os.path.join(dst, "geometry", f + ".obj"))
+    with open(os.path.join(src, "scene.json")) as f:
+        doc = json.load(f)
+    # C1/C2: `pt`, no smoke volume, short+tall boxes with material "General", right.obj lower-case (§8(c) hazards)
+    doc["integrator"] = "pt"; doc["maxDepth"] = 4; doc["screen_width"] = 256; doc["screen_height"] = 256
+    doc["medium"] = []
+    doc["scene"] = [u for u in doc["scene"] if "density_render" not in u["mesh"]]
+    for u in doc["scene"]:
+        u["mesh"] = u["mesh"].replace("Right.obj", "right.obj")
+    doc["scene"] += [{"mesh": "geometry/short.obj", "material": "General"}, {"mesh": "geometry/tall.obj", "material": "General"}]
+    with open(os.path.join(dst, "cornell_pt.json"), "w") as f:
+        json.dump(doc, f, indent=1)
+    with open(os.path.join(src, "vol_caustic.json")) as f:
+        doc = json.load(f)
+    # C5: `vpt`, emitter swapped to the regular Cornell light (mesh_6 is 0.005 x 0.004: image mean 2.5e-5)
+    doc["integrator"] = "vpt"
+    doc["light"][0]["mesh"] = "geometry/light.obj"
+    with open(os.path.join(dst, "vol_caustic_vpt.json"), "w") as f:
+        json.dump(doc, f, indent=1)
+
+
+def main():
+    stage_scene_files()
+    from tests.refhost import RefHost, RefPrep
+    import gpu_pathtracer_b200 as pt
+    ref = RefHost()
+    prep = RefPrep(ref)
+    scenes = {
+        "cornell_pt_64": lambda: pt.scenes.cornell_pt(64, 64, 4, prep=prep),
+        "vol_caustic_64": lambda: pt.scenes.cornell_vol_caustic(64, 64, 17, prep=prep),
+        "veach_standin_64x48": lambda: pt.scenes.veach_standin(64, 48, 17, prep=prep),
+        "random_tris_20k_64": lambda: pt.scenes.random_triangles(20000, 64, 64, 8, prep=prep),
+    }
+    for name, mk in scenes.items():
+        s = mk()
+        out = {"camera": s.camera.view(np.uint8), "nodes": s.nodes.view(np.uint8), "prims_order_hash": prim_hash(s.prims),
+               "light_distribution": s.light_distribution, "root_box": s.root_box}
+        if name != "random_tris_20k_64":
+            out["prims"] = s.prims.view(np.uint8)
+        spp = 4
+        acc, tone = ref.render(s, 1, spp)
+        out["ref_host_accum"] = acc
+        out["ref_host_tonemapped"] = tone
+        out["spp"] = np.int32(spp)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+        print(name, "nodes", len(s.nodes), "prims", len(s.prims), "mean", acc.reshape(-1, 3).mean(0) / spp)
+    kat = ref.known_answers(pt.scenes.cornell_pt(64, 64, 4, prep=prep), pt.scenes.veach_standin(64, 48, 17, prep=prep))
+    np.savez_compressed(os.path.join(GOLD, "kat.npz"), **kat)
+    print("kat:", {k: v.shape for k, v in kat.items()})
+
+
+def prim_hash(prims):
+    import zlib
+    return np.uint32(zlib.crc32(prims.tobytes()))
+
+
+if __name__ == "__main__":
+    main()
