@@ -31,27 +31,28 @@ class Shard(C.Structure):
 
 
 EXPORTS = [
-    "b200pt_create", "b200pt_render", "b200pt_render_async", "b200pt_sync", "b200pt_get_accum",
+    "b200pt_create", "b200pt_render", "b200pt_get_accum",
     "b200pt_accum_device_ptr", "b200pt_get_color", "b200pt_tonemap", "b200pt_trace_primary", "b200pt_stats",
     "b200pt_set_option", "b200pt_destroy", "b200pt_last_error", "b200pt_version", "b200pt_bvh_build",
     "b200pt_camera_init", "b200pt_light_distribution", "b200pt_infinite_init",
 ]
 
 
-def load():
+def load(path=None):
+    """Load csrc/libb200pt.so (the only library the package ever loads by itself).  `path` is for the test suite,
+    which binds the same ABI of tests/emu/libb200pt_emu.so explicitly; there is no implicit fallback."""
     global _lib
-    if _lib is not None:
+    if _lib is not None and path is None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                           "The path tracer has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.b200pt_last_error.restype = C.c_char_p
     lib.b200pt_create.argtypes = [C.POINTER(SceneView), C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.POINTER(Shard),
                                   C.POINTER(C.c_void_p)]
     lib.b200pt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_int]
-    lib.b200pt_render_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
-    lib.b200pt_sync.argtypes = [C.c_void_p]
     lib.b200pt_get_accum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.b200pt_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.b200pt_get_color.argtypes = [C.c_void_p, C.c_void_p]

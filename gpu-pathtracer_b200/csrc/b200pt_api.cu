@@ -1,0 +1,512 @@
+// b200pt_api.cu — C ABI (include/b200pt.h) of the wavefront path tracer: context creation (scene upload and
+// re-layout, replaces BeginRender src/pathtracer.cu:2568-2695), the render loop (replaces Render :2705-2750)
+// and teardown (EndRender :2697).  One context = one GPU = one CUDA stream; no global state.
+#include "b200pt.h"
+#include "ref_layouts.h"
+#include "k_shade.cuh"
+#include "k_trace.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pt;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(B200PT_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+struct b200pt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
+    SceneDev sc{};
+    ShardMap map{};
+    Pool pool{};
+    std::vector<void*> allocs;            // everything cudaMalloc'ed (freed in destroy)
+    Counters* counters = nullptr;
+    Counters* h_counters = nullptr;       // pinned, 2 polling slots
+    float4* samples = nullptr; size_t samples_cap = 0;   // in float4
+    float *acc = nullptr, *color = nullptr, *out = nullptr;
+    uint32_t width = 0, height = 0;
+    int num_sms = 148, trace_blocks = 0;
+    uint32_t stage_nodes = 0, stage_prims = 0;
+    size_t max_batch_bytes = (size_t)2 << 30;
+    int steps_per_poll = 8;
+    double stats[5] = {0, 0, 0, 0, 0};
+    double total_ms = 0;
+    bool vol = false;
+    int last_filmic = 1;
+};
+
+template <class T> static int dev_alloc(b200pt_ctx* c, T** p, size_t n, bool zero = false) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc ") + std::to_string(bytes) + " B: " + cudaGetErrorString(e));
+    if (zero) cudaMemsetAsync(q, 0, bytes, c->stream);
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <class T> static int dev_upload(b200pt_ctx* c, T** p, const T* src, size_t n) {
+    int rc = dev_alloc(c, p, n);
+    if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// ---- device-side preparation: per-triangle constants with the SAME device arithmetic the reference uses -----
+// normalize(dpdv) of Triangle::Intersect's epilogue (src/mesh.h:69-83) and Triangle::GetSurfaceArea (:39).
+__global__ void k_prepare_shade(WShade* shade, const WPrim* prims, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    WShade& s = shade[i];
+    if (s.type != 0) return;
+    const WPrim& p = prims[i];
+    f3 e1 = mk3(p.q0.w, p.q1.x, p.q1.y), e2 = mk3(p.q1.z, p.q1.w, p.q2.x);
+    f2 duv1 = mk2(s.uv2[0], s.uv2[1]) - mk2(s.uv1[0], s.uv1[1]);
+    f2 duv2 = mk2(s.uv3[0], s.uv3[1]) - mk2(s.uv1[0], s.uv1[1]);
+    float det = duv1.x * duv2.y - duv1.y * duv2.x;
+    f3 dpdu, dpdv;
+    if (fabs((double)det) < 1e-8) {
+        f3 nn = normalize(cross(e1, e2));
+        make_coordinate(nn, dpdu, dpdv);
+    } else {
+        float invDet = 1 / det;
+        dpdu = (duv2.y * e1 - duv1.y * e2) * invDet;
+        dpdv = (-duv2.x * e1 + duv1.x * e2) * invDet;
+    }
+    f3 nd = normalize(dpdv);
+    s.ndpdv[0] = nd.x; s.ndpdv[1] = nd.y; s.ndpdv[2] = nd.z;
+}
+__global__ void k_prepare_lights(WLight* lights, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    WLight& L = lights[i];
+    f3 e1 = ld3(L.v2) - ld3(L.v1);
+    f3 e2 = ld3(L.v3) - ld3(L.v1);
+    L.area = length(cross(e1, e2)) * 0.5f;
+}
+
+static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
+    if (v->integrator_type != B200PT_IT_PT && v->integrator_type != B200PT_IT_VPT)
+        return fail(B200PT_EUNSUPPORTED, "only the `pt` and `vpt` integrators are on the hot path");
+    if (v->n_prims <= 0 || v->n_nodes <= 0 || !v->prims || !v->nodes || !v->camera || !v->materials || !v->light_distribution)
+        return fail(B200PT_EINVAL, "scene view is missing primitives / nodes / camera / materials / light distribution");
+    if (v->n_textures > 0) return fail(B200PT_EUNSUPPORTED, "textured materials are not implemented yet (SURVEY 8(f).2)");
+    if (v->n_mediums > 254) return fail(B200PT_EINVAL, "too many media");
+    const RefPrimitive* prims = (const RefPrimitive*)v->prims;
+    const RefLinearBVHNode* nodes = (const RefLinearBVHNode*)v->nodes;
+    const RefMaterial* mats = (const RefMaterial*)v->materials;
+    for (int i = 0; i < v->n_materials; ++i)
+        if (mats[i].textureIdx != -1) return fail(B200PT_EUNSUPPORTED, "textured materials are not implemented yet (SURVEY 8(f).2)");
+
+    // -- primitives: intersection records + shading records
+    std::vector<WPrim> wp(v->n_prims);
+    std::vector<WShade> ws(v->n_prims);
+    for (int i = 0; i < v->n_prims; ++i) {
+        const RefPrimitive& p = prims[i];
+        WPrim& q = wp[i]; WShade& s = ws[i];
+        std::memset(&q, 0, sizeof(q)); std::memset(&s, 0, sizeof(s));
+        if (p.type == REF_GT_TRIANGLE) {
+            const RefTriangle& t = p.u.triangle;
+            float e1[3], e2[3];
+            for (int k = 0; k < 3; ++k) { e1[k] = t.v2.v[k] - t.v1.v[k]; e2[k] = t.v3.v[k] - t.v1.v[k]; }
+            q.q0 = make_float4(t.v1.v[0], t.v1.v[1], t.v1.v[2], e1[0]);
+            q.q1 = make_float4(e1[1], e1[2], e2[0], e2[1]);
+            q.q2 = make_float4(e2[2], 0.f, 0.f, 0.f);
+            std::memcpy(s.n1, t.v1.n, 12); std::memcpy(s.n2, t.v2.n, 12); std::memcpy(s.n3, t.v3.n, 12);
+            std::memcpy(s.uv1, t.v1.uv, 8); std::memcpy(s.uv2, t.v2.uv, 8); std::memcpy(s.uv3, t.v3.uv, 8);
+            s.matIdx = t.matIdx; s.lightIdx = t.lightIdx; s.mediumInside = t.mediumInside; s.mediumOutside = t.mediumOutside;
+            s.type = 0;
+            if (t.matIdx >= v->n_materials || (t.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
+                return fail(B200PT_EINVAL, "triangle " + std::to_string(i) + " has material index " + std::to_string(t.matIdx) +
+                                               " (a material-less medium boundary needs the vpt integrator)");
+            if (t.lightIdx >= v->n_lights) return fail(B200PT_EINVAL, "triangle light index out of range");
+        } else if (p.type == REF_GT_SPHERE) {
+            const RefSphere& sp = p.u.sphere;
+            q.q0 = make_float4(sp.origin[0], sp.origin[1], sp.origin[2], sp.radius);
+            int one = 1; float onef; std::memcpy(&onef, &one, 4);
+            q.q2 = make_float4(0.f, onef, 0.f, 0.f);
+            std::memcpy(s.n1, sp.origin, 12); s.n2[0] = sp.radius;
+            s.matIdx = sp.matIdx; s.lightIdx = -1; s.mediumInside = sp.mediumInside; s.mediumOutside = sp.mediumOutside;
+            s.type = 1;
+            if (sp.matIdx >= v->n_materials || (sp.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
+                return fail(B200PT_EINVAL, "sphere material index out of range");
+        } else {
+            return fail(B200PT_EUNSUPPORTED, "line primitives are not implemented yet (SURVEY 8(f).2)");
+        }
+        if (s.mediumInside >= v->n_mediums || s.mediumOutside >= v->n_mediums) return fail(B200PT_EINVAL, "medium index out of range");
+    }
+    // -- nodes: reference DFS layout (left child = i+1, right = second_child_offset) -> two-child records
+    std::vector<int> inner_id(v->n_nodes, -1);
+    int n_inner = 0;
+    for (int i = 0; i < v->n_nodes; ++i) if (!nodes[i].is_leaf) inner_id[i] = n_inner++;
+    auto mark_leaf = [&](const RefLinearBVHNode& n) -> int {
+        if (n.start < 0 || n.end >= v->n_prims || n.end < n.start) return -1;
+        int one = 1; float onef; std::memcpy(&onef, &one, 4);
+        wp[n.end].q2.z = onef;                                   // last-in-leaf flag
+        return 0;
+    };
+    std::vector<WNode> wn(std::max(n_inner, 1));
+    std::memset(wn.data(), 0, wn.size() * sizeof(WNode));
+    for (int i = 0; i < v->n_nodes; ++i) {
+        const RefLinearBVHNode& n = nodes[i];
+        if (n.is_leaf) { if (mark_leaf(n)) return fail(B200PT_EINVAL, "leaf node with an invalid primitive range"); continue; }
+        int l = i + 1, r = n.second_child_offset;
+        if (l >= v->n_nodes || r <= 0 || r >= v->n_nodes) return fail(B200PT_EINVAL, "BVH node child index out of range");
+        const RefLinearBVHNode& L = nodes[l]; const RefLinearBVHNode& R = nodes[r];
+        WNode& w = wn[inner_id[i]];
+        w.q0 = make_float4(L.fmin[0], L.fmin[1], L.fmin[2], L.fmax[0]);
+        w.q1 = make_float4(L.fmax[1], L.fmax[2], R.fmin[0], R.fmin[1]);
+        w.q2 = make_float4(R.fmin[2], R.fmax[0], R.fmax[1], R.fmax[2]);
+        w.link.x = L.is_leaf ? ~L.start : inner_id[l];
+        w.link.y = R.is_leaf ? ~R.start : inner_id[r];
+        w.link.z = 0; w.link.w = 0;
+    }
+    SceneDev& sc = c->sc;
+    std::memcpy(sc.root_min, nodes[0].fmin, 12); std::memcpy(sc.root_max, nodes[0].fmax, 12);
+    sc.root_leaf_count = nodes[0].is_leaf ? (nodes[0].end - nodes[0].start + 1) : 0;
+    sc.n_nodes = n_inner; sc.n_prims = v->n_prims;
+    WNode* d_nodes; WPrim* d_prims; WShade* d_shade;
+    int rc;
+    if ((rc = dev_upload(c, &d_nodes, wn.data(), wn.size()))) return rc;
+    if ((rc = dev_upload(c, &d_prims, wp.data(), wp.size()))) return rc;
+    if ((rc = dev_upload(c, &d_shade, ws.data(), ws.size()))) return rc;
+    sc.nodes = d_nodes; sc.prims = d_prims; sc.shade = d_shade;
+    PT_LAUNCH(k_prepare_shade, (v->n_prims + 255) / 256, 256, 0, c->stream, d_shade, d_prims, v->n_prims);
+
+    // -- lights
+    std::vector<WLight> wl(std::max(v->n_lights, 1));
+    std::memset(wl.data(), 0, wl.size() * sizeof(WLight));
+    const RefArea* areas = (const RefArea*)v->lights;
+    for (int i = 0; i < v->n_lights; ++i) {
+        const RefTriangle& t = areas[i].triangle;
+        std::memcpy(wl[i].v1, t.v1.v, 12); std::memcpy(wl[i].v2, t.v2.v, 12); std::memcpy(wl[i].v3, t.v3.v, 12);
+        std::memcpy(wl[i].n1, t.v1.n, 12); std::memcpy(wl[i].n2, t.v2.n, 12); std::memcpy(wl[i].n3, t.v3.n, 12);
+        std::memcpy(wl[i].radiance, areas[i].radiance, 12);
+    }
+    WLight* d_lights;
+    if ((rc = dev_upload(c, &d_lights, wl.data(), wl.size()))) return rc;
+    if (v->n_lights) PT_LAUNCH(k_prepare_lights, (v->n_lights + 127) / 128, 128, 0, c->stream, d_lights, v->n_lights);
+    sc.lights = d_lights; sc.n_lights = v->n_lights;
+
+    // -- materials (72-B reference records are used as they are), media, light CDF
+    Material* d_mats;
+    if ((rc = dev_upload(c, &d_mats, (const Material*)v->materials, (size_t)v->n_materials))) return rc;
+    sc.mats = d_mats; sc.n_mats = v->n_materials;
+    std::vector<WMedium> wm(std::max(v->n_mediums, 1));
+    std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
+    const RefMedium* med = (const RefMedium*)v->mediums;
+    for (int i = 0; i < v->n_mediums; ++i) {
+        if (med[i].type != REF_MEDIUM_HOMOGENEOUS) return fail(B200PT_EUNSUPPORTED, "heterogeneous media are not implemented yet (SURVEY 8(f).3)");
+        std::memcpy(wm[i].sigmaA, med[i].sigmaA, 12); std::memcpy(wm[i].sigmaS, med[i].sigmaS, 12); std::memcpy(wm[i].sigmaT, med[i].sigmaT, 12);
+        wm[i].g = med[i].g; wm[i].type = 0;
+    }
+    WMedium* d_med;
+    if ((rc = dev_upload(c, &d_med, wm.data(), wm.size()))) return rc;
+    sc.mediums = d_med; sc.n_mediums = v->n_mediums;
+    float* d_cdf;
+    // one trailing pad entry: the reference's scan reads cdf[n] in its last iteration (src/pathtracer.cu:175)
+    std::vector<float> cdf(v->light_distribution, v->light_distribution + v->n_light_distribution);
+    cdf.push_back(cdf.empty() ? 0.f : cdf.back());
+    if ((rc = dev_upload(c, &d_cdf, cdf.data(), cdf.size()))) return rc;
+    sc.cdf = d_cdf; sc.n_cdf = v->n_light_distribution;
+
+    // -- infinite light
+    std::memset(&sc.inf, 0, sizeof(sc.inf));
+    if (v->infinite) {
+        const RefInfinite* inf = (const RefInfinite*)v->infinite;
+        if (inf->isvalid) {
+            if (!inf->data || inf->width <= 0 || inf->height <= 0) return fail(B200PT_EINVAL, "infinite light without texels");
+            float* d_tex;
+            if ((rc = dev_upload(c, &d_tex, inf->data, (size_t)3 * inf->width * inf->height))) return rc;
+            sc.inf.data = d_tex; sc.inf.width = inf->width; sc.inf.height = inf->height;
+            std::memcpy(sc.inf.center, inf->center, 12); sc.inf.radius = inf->radius;
+            std::memcpy(sc.inf.u, inf->u, 12); std::memcpy(sc.inf.v, inf->v, 12); std::memcpy(sc.inf.w, inf->w, 12);
+            sc.inf.isvalid = 1;
+        }
+    }
+    // consistency of the CDF with the light list (idx == n_lights selects the infinite light, :931)
+    int expect = 1 + v->n_lights + (sc.inf.isvalid ? 1 : 0);
+    if (v->n_light_distribution != expect)
+        return fail(B200PT_EINVAL, "light distribution has " + std::to_string(v->n_light_distribution) + " entries, expected " + std::to_string(expect));
+    sc.integrator = v->integrator_type; sc.max_depth = v->max_depth;
+    if (v->max_depth < 0 || v->max_depth > 255) return fail(B200PT_EINVAL, "maxDepth must be in [0, 255]");
+    c->vol = v->integrator_type == B200PT_IT_VPT;
+
+    // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
+    size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
+    if (nb + pb <= 40 * 1024) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; }
+    CK(cudaStreamSynchronize(c->stream));     // host staging vectors go out of scope
+    return 0;
+}
+
+static int alloc_pool(b200pt_ctx* c, int n) {
+    Pool& p = c->pool;
+    float4** arrs[] = {&p.o_rng, &p.d_flags, &p.beta_s, &p.li_t, &p.shd, &p.misd, &p.ldl, &p.misf, &p.beta_old, &p.hit0, &p.hit1, &p.vis, &p.aux};
+    for (auto a : arrs) { int rc = dev_alloc(c, a, (size_t)n, true); if (rc) return rc; }
+    p.n = n;
+    return 0;
+}
+
+extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uint32_t height, float epsilon,
+                             int device, const b200pt_shard* shard, b200pt_ctx** out_ctx) {
+    if (!scene || !out_ctx) return fail(B200PT_EINVAL, "null argument");
+    if (width == 0 || height == 0 || width % 32 || height % 4)
+        return fail(B200PT_EINVAL, "width must be a multiple of 32 and height a multiple of 4 (reference launch grid, src/pathtracer.cu:2707-2709)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(B200PT_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " — this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200PT_EINVAL, "device index out of range");
+    CK(cudaSetDevice(device));
+    b200pt_ctx* c = new b200pt_ctx();
+    c->device = device; c->width = width; c->height = height;
+    auto bail = [&](int rc) { std::string keep = g_err; b200pt_destroy(c); g_err = keep; return rc; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B200PT_ECUDA, "stream create failed"));
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    c->sc.eps = epsilon;
+    int rc = build_scene(c, scene);
+    if (rc) return bail(rc);
+
+    // shard map
+    ShardMap& m = c->map;
+    m.width = (int)width; m.height = (int)height;
+    m.shard = 0; m.n_shards = 1; m.tile_w = 32; m.tile_h = 32;
+    if (shard && shard->n_shards > 1) {
+        if (shard->shard < 0 || shard->shard >= shard->n_shards || shard->tile_w <= 0 || shard->tile_h <= 0 ||
+            width % shard->tile_w || height % shard->tile_h)
+            return bail(fail(B200PT_EINVAL, "bad shard description (tiles must divide the image)"));
+        m.shard = shard->shard; m.n_shards = shard->n_shards; m.tile_w = shard->tile_w; m.tile_h = shard->tile_h;
+    }
+    m.tiles_x = (int)width / m.tile_w; m.tiles_y = (int)height / m.tile_h;
+    int n_tiles = m.tiles_x * m.tiles_y;
+    m.n_local_tiles = m.n_shards == 1 ? n_tiles : (n_tiles - m.shard + m.n_shards - 1) / m.n_shards;
+    m.n_local_pixels = m.n_shards == 1 ? (int)(width * height) : m.n_local_tiles * m.tile_w * m.tile_h;
+
+    size_t npix = (size_t)width * height;
+    if ((rc = dev_alloc(c, &c->acc, 3 * npix, true))) return bail(rc);
+    if ((rc = dev_alloc(c, &c->color, 3 * npix, true))) return bail(rc);
+    if ((rc = dev_alloc(c, &c->out, 3 * npix, true))) return bail(rc);
+    if ((rc = dev_alloc(c, &c->counters, 1, true))) return bail(rc);
+    if (cudaMallocHost((void**)&c->h_counters, 2 * sizeof(Counters)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
+    int pool = 1 << 20;
+    if ((size_t)pool > (size_t)m.n_local_pixels * 4) pool = std::max(1024, m.n_local_pixels * 4);
+    if ((rc = alloc_pool(c, pool))) return bail(rc);
+
+    // persistent traversal grid: resident CTAs per SM x SM count
+    int per_sm = 0;
+    size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+    if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, 256, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, 256, smem);
+    if (per_sm <= 0) per_sm = 1;
+    c->trace_blocks = c->num_sms * per_sm;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));
+    *out_ctx = c;
+    return B200PT_OK;
+}
+
+extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return fail(B200PT_EINVAL, "null argument");
+    std::string n(name);
+    if (n == "pool") {
+        if (value < 256 || value > (1 << 26)) return fail(B200PT_EINVAL, "pool must be in [256, 2^26]");
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        return alloc_pool(c, (int)value);      // the old pool is released with the context
+    }
+    if (n == "steps_per_poll") { if (value < 1 || value > 1024) return fail(B200PT_EINVAL, "steps_per_poll out of range"); c->steps_per_poll = (int)value; return 0; }
+    if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
+    if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; } return 0; }
+    return fail(B200PT_EINVAL, "unknown option " + n);
+}
+
+// One batch = n_iters iterations of every local pixel through the wavefront, then the ordered resolve.
+static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint32_t n_iters, int reset, float* out_dev, int write_out,
+                     double* launches, double* steps) {
+    const size_t need = (size_t)n_iters * c->map.n_local_pixels;
+    if (need > c->samples_cap) {
+        if (c->samples) {
+            CK(cudaStreamSynchronize(c->stream));
+            c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)c->samples), c->allocs.end());
+            cudaFree(c->samples); c->samples = nullptr; c->samples_cap = 0;
+        }
+        int rc = dev_alloc(c, &c->samples, need);
+        if (rc) return rc;
+        c->samples_cap = need;
+    }
+    BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
+    CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 2, c->stream));   // next_sample, done_samples (rays keeps counting)
+    ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.cam = cam; sa.map = c->map; sa.batch = bp;
+    TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.counters = c->counters; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
+    const int shade_blocks = (c->pool.n + 127) / 128;
+    const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+    auto shade = [&]() { if (c->vol) PT_LAUNCH(k_shade<true>, shade_blocks, 128, 0, c->stream, sa); else PT_LAUNCH(k_shade<false>, shade_blocks, 128, 0, c->stream, sa); };
+    auto trace = [&]() { if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, 256, smem, c->stream, ta); else PT_LAUNCH(k_trace<false>, c->trace_blocks, 256, smem, c->stream, ta); };
+    // all slots start dead: the first shade pass only regenerates
+    CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)c->pool.n, c->stream));
+    shade(); *launches += 1;
+    // Launch in chunks and poll the retired-sample counter one chunk behind, so the GPU never waits on the host.
+    int chunk = 0;
+    bool done = false;
+    while (!done) {
+        for (int s = 0; s < c->steps_per_poll; ++s) { trace(); shade(); }
+        *launches += 2.0 * c->steps_per_poll; *steps += c->steps_per_poll;
+        const int slot = chunk & 1;
+        CK(cudaMemcpyAsync(&c->h_counters[slot], c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaEventRecord(c->ev_poll[slot], c->stream));
+        if (chunk >= 1) {
+            const int prev = (chunk - 1) & 1;
+            CK(cudaEventSynchronize(c->ev_poll[prev]));
+            if (c->h_counters[prev].done_samples >= bp.total) done = true;
+        }
+        ++chunk;
+        if (chunk > (1 << 22)) return fail(B200PT_ECUDA, "wavefront did not converge (internal error)");
+    }
+    ResolveArgs ra; ra.samples = c->samples; ra.acc = c->acc; ra.color = c->color; ra.out = out_dev ? out_dev : c->out;
+    ra.map = c->map; ra.batch = bp; ra.reset = reset; ra.filmic = cam.filmic; ra.write_out = write_out;
+    PT_LAUNCH(k_resolve, (c->map.n_local_pixels + 255) / 256, 256, 0, c->stream, ra);
+    *launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
+                             float* output, int output_is_device) {
+    if (!c || !camera) return fail(B200PT_EINVAL, "null argument");
+    if (spp == 0) return fail(B200PT_EINVAL, "spp must be >= 1");
+    if (first_iter == 0) return fail(B200PT_EINVAL, "iter is 1-based (src/main.cpp:178 increments before the first Render)");
+    CK(cudaSetDevice(c->device));
+    Camera cam; std::memcpy(&cam, camera, sizeof(Camera));      // re-read every call, like src/pathtracer.cu:2706
+    if (c->vol && cam.medium >= c->sc.n_mediums) return fail(B200PT_EINVAL, "camera medium index out of range");
+    c->last_filmic = cam.filmic;
+    float* out_dev = (output && output_is_device) ? output : c->out;
+    const size_t npix = (size_t)c->width * c->height;
+    unsigned long long rays0 = 0;
+    CK(cudaMemcpyAsync(&rays0, &c->counters->rays, sizeof(rays0), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (reset && c->map.n_shards > 1) CK(cudaMemsetAsync(c->acc, 0, 3 * npix * sizeof(float), c->stream));
+    if (c->map.n_shards > 1 && out_dev) CK(cudaMemsetAsync(out_dev, 0, 3 * npix * sizeof(float), c->stream));
+    // batch size: as many iterations as fit the sample-plane budget
+    size_t per_iter = (size_t)c->map.n_local_pixels * sizeof(float4);
+    uint32_t max_iters = (uint32_t)std::max<size_t>(1, c->max_batch_bytes / per_iter);
+    double launches = 0, steps = 0;
+    uint32_t done = 0;
+    while (done < spp) {
+        uint32_t n = std::min(max_iters, spp - done);
+        bool last = done + n == spp;
+        int rc = run_batch(c, cam, first_iter + done, n, reset && done == 0, out_dev, last ? 1 : 0, &launches, &steps);
+        if (rc) return rc;
+        done += n;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (output && !output_is_device) CK(cudaMemcpyAsync(output, out_dev, 3 * npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long rays1 = 0;
+    CK(cudaMemcpyAsync(&rays1, &c->counters->rays, sizeof(rays1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats[0] = (double)spp * c->map.n_local_pixels; c->stats[1] = launches; c->stats[2] = (double)(rays1 - rays0);
+    c->stats[3] = steps; c->stats[4] = ms;
+    c->total_ms += ms;
+    return B200PT_OK;
+}
+
+extern "C" int b200pt_get_accum(b200pt_ctx* c, float* dst, int dst_is_device) {
+    if (!c || !dst) return fail(B200PT_EINVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, c->acc, 3 * (size_t)c->width * c->height * sizeof(float),
+                       dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int b200pt_accum_device_ptr(b200pt_ctx* c, float** out_ptr) {
+    if (!c || !out_ptr) return fail(B200PT_EINVAL, "null argument");
+    *out_ptr = c->acc;
+    return 0;
+}
+extern "C" int b200pt_get_color(b200pt_ctx* c, float* dst_host) {
+    if (!c || !dst_host) return fail(B200PT_EINVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst_host, c->color, 3 * (size_t)c->width * c->height * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int b200pt_tonemap(b200pt_ctx* c, const float* acc_device, uint32_t iter, float* out_device) {
+    if (!c || !acc_device || !out_device || iter == 0) return fail(B200PT_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    uint32_t npix = c->width * c->height;
+    PT_LAUNCH(k_tonemap, (npix + 255) / 256, 256, 0, c->stream, acc_device, out_device, npix, iter, c->last_filmic);
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Primary-visibility query through the production traversal kernel: regenerate one iteration, trace once.
+extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t iter, float* hits_host) {
+    if (!c || !camera || !hits_host || iter == 0) return fail(B200PT_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    if (c->map.n_shards != 1) return fail(B200PT_EINVAL, "trace_primary needs an unsharded context");
+    Camera cam; std::memcpy(&cam, camera, sizeof(Camera));
+    const uint32_t npix = c->width * c->height;
+    std::vector<float4> hits(npix);
+    const uint32_t P = (uint32_t)c->pool.n;
+    if (c->samples_cap < npix) { int rc = dev_alloc(c, &c->samples, (size_t)npix); if (rc) return rc; c->samples_cap = npix; }
+    std::vector<float4> tmp(P), bs(P);
+    for (uint32_t base = 0; base < npix; base += P) {
+        // hand out exactly the samples [base, base + P) of this iteration
+        uint32_t cnt = std::min(P, npix - base);
+        BatchParams bp; bp.first_iter = iter; bp.n_iters = 1; bp.total = base + cnt;
+        Counters z; std::memset(&z, 0, sizeof(z)); z.next_sample = base;
+        CK(cudaMemcpyAsync(c->counters, &z, sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)P, c->stream));
+        ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.cam = cam; sa.map = c->map; sa.batch = bp;
+        TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.counters = c->counters; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
+        const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+        if (c->vol) { PT_LAUNCH(k_shade<true>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<true>, c->trace_blocks, 256, smem, c->stream, ta); }
+        else { PT_LAUNCH(k_shade<false>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<false>, c->trace_blocks, 256, smem, c->stream, ta); }
+        CK(cudaMemcpyAsync(tmp.data(), c->pool.hit0, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(bs.data(), c->pool.beta_s, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (uint32_t s = 0; s < P; ++s) {
+            uint32_t sample; std::memcpy(&sample, &bs[s].w, 4);
+            if (sample >= base && sample < base + cnt) hits[sample] = tmp[s];
+        }
+    }
+    CK(cudaGetLastError());
+    std::memcpy(hits_host, hits.data(), sizeof(float4) * npix);
+    return 0;
+}
+
+extern "C" int b200pt_stats(b200pt_ctx* c, double* out5) {
+    if (!c || !out5) return fail(B200PT_EINVAL, "null argument");
+    std::memcpy(out5, c->stats, sizeof(c->stats));
+    return 0;
+}
+
+extern "C" int b200pt_destroy(b200pt_ctx* c) {
+    if (!c) return fail(B200PT_EINVAL, "null context");
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto& e : c->ev_poll) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" const char* b200pt_last_error(void) { return g_err.c_str(); }
+extern "C" int b200pt_version(void) { return 100; }

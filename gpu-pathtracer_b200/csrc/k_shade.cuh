@@ -1,0 +1,493 @@
+// k_shade.cuh — the shading / next-event / regeneration stage of the wavefront (replaces the body of the
+// `Path` and `Volpath` bounce loops, src/pathtracer.cu:904-1017 and :1050-1238, minus the ray traversals).
+//
+// Per slot and step:
+//   A. finish the PREVIOUS bounce: add beta_old * Ld where Ld = light-sampled term (if the shadow ray was
+//      unoccluded) + BSDF-sampled MIS term (needs the MIS ray's hit)                      (:942-995 / :1145-1211)
+//   B. shade the continuation ray's hit: escape / emitter / delta or non-delta BSDF, draw the random numbers in
+//      the reference's order (1 light pick, 2 light uv, 3 MIS-BSDF, 3 continuation-BSDF, +1 Russian roulette
+//      when bounces > 3), emit the shadow, MIS and continuation rays                        (:905-1016)
+//   C. when the sample ends, write its radiance to the sample plane and REGENERATE the slot with the next
+//      (iteration, pixel) pair from the global counter (ray generation, :881-903)
+#pragma once
+#include "wavefront.cuh"
+
+namespace pt {
+
+struct ShadeArgs {
+    SceneDev sc;
+    Pool pool;
+    Counters* counters;
+    float4* samples;          // [n_iters][n_local_pixels] radiance of every finished sample (w = 1)
+    Camera cam;
+    ShardMap map;
+    BatchParams batch;
+};
+
+struct SurfaceHit { f3 pos, nor, dpdu; int matIdx, lightIdx, mediumInside, mediumOutside; };
+
+// Epilogue of Triangle::Intersect (src/mesh.h:68-95) / Sphere::Intersect (src/sphere.h:74-91), evaluated once
+// for the final hit from (t, prim, b1, b2).
+__device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, float t, int prim, float b1, float b2, SurfaceHit& h) {
+    const WShade& s = sc.shade[prim];
+    h.pos = o + t * d;
+    if (s.type == 0) {
+        h.nor = normalize(ld3(s.n1) * (1.f - b1 - b2) + ld3(s.n2) * b1 + ld3(s.n3) * b2);
+        h.dpdu = normalize(cross(h.nor, ld3(s.ndpdv)));
+    } else {
+        h.nor = normalize(h.pos - ld3(s.n1));
+        h.dpdu = normalize(mk3(-kTwoPi * h.pos.y, kTwoPi * h.pos.x, 0));
+    }
+    h.matIdx = s.matIdx; h.lightIdx = s.lightIdx; h.mediumInside = s.mediumInside; h.mediumOutside = s.mediumOutside;
+}
+// shading normal only (MIS hit, :962)
+__device__ __forceinline__ f3 hit_normal(const SceneDev& sc, f3 pos, int prim, float b1, float b2) {
+    const WShade& s = sc.shade[prim];
+    if (s.type == 0) return normalize(ld3(s.n1) * (1.f - b1 - b2) + ld3(s.n2) * b1 + ld3(s.n3) * b2);
+    return normalize(pos - ld3(s.n1));
+}
+
+// Infinite::getTexel / getTexelBilinear (src/infinite.h:66-94)
+__device__ __forceinline__ f3 inf_texel(const WInfinite& I, int x, int y) {
+    int width = I.width, height = I.height;
+    float rx = x - (x / width) * width;
+    float ry = y - (y / height) * height;
+    x = (rx < 0) ? rx + width : rx;
+    y = (ry < 0) ? ry + height : ry;
+    if (x < 0) x = 0;
+    if (x > width - 1) x = width - 1;
+    if (y < 0) y = 0;
+    if (y > height - 1) y = height - 1;
+    const float* c = I.data + 3 * ((size_t)y * width + x);
+    return mk3(c[0], c[1], c[2]);
+}
+__device__ __forceinline__ f3 inf_bilinear(const WInfinite& I, f2 uv) {
+    float xx = I.width * uv.x;
+    float yy = I.height * uv.y;
+    int x = floorf(xx);
+    int y = floorf(yy);
+    float dx = fabsf(xx - x);
+    float dy = fabsf(yy - y);
+    f3 c00 = inf_texel(I, x, y), c10 = inf_texel(I, x + 1, y), c01 = inf_texel(I, x, y + 1), c11 = inf_texel(I, x + 1, y + 1);
+    return (1 - dy) * ((1 - dx) * c00 + dx * c10) + dy * ((1 - dx) * c01 + dx * c11);
+}
+// direction -> lat-long uv, shared by Infinite::Le (:47) and Infinite::SampleLight (:17)
+__device__ __forceinline__ f2 inf_dir_to_uv(const WInfinite& I, f3 dir) {
+    f3 u = ld3(I.u), v = ld3(I.v), w = ld3(I.w);
+    float costheta = dot(dir, v);
+    float theta = acosf(costheta);
+    f3 d = normalize(dir - costheta * v);
+    float cosphi = dot(d, u);
+    float phi = acosf(cosphi);
+    float c = dot(d, w);
+    phi = c > 0 ? kTwoPi - phi : phi;
+    float uu = phi / kTwoPi;
+    float vv = theta / kPi;
+    return mk2(1.f - uu, vv);
+}
+__device__ __forceinline__ f3 inf_le(const WInfinite& I, f3 dir) { return inf_bilinear(I, inf_dir_to_uv(I, dir)); }
+
+// LookUpLightDistribution (src/pathtracer.cu:172): first interval [cdf[i], cdf[i+1]] containing u.
+__device__ __forceinline__ int lookup_light(const SceneDev& sc, float u, float& pdf) {
+    const int n = sc.n_cdf - 1;
+    if (n <= 8) {
+        for (int i = 0; i < n; ++i) {
+            float s = sc.cdf[i], e = sc.cdf[i + 1];
+            if (u >= s && u <= e) { pdf = e - s; return i; }
+        }
+        pdf = 0.f; return -1;
+    }
+    // many emissive triangles: binary search for the first i with cdf[i+1] >= u — the same index the linear
+    // scan returns, because the CDF is non-decreasing (cdf[i] < u for that i, or i == 0)
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (sc.cdf[mid + 1] >= u) hi = mid; else lo = mid + 1; }
+    float s = sc.cdf[lo], e = sc.cdf[lo + 1];
+    if (u >= s && u <= e) { pdf = e - s; return lo; }
+    pdf = 0.f; return -1;
+}
+
+struct LightSample { f3 radiance, dir; float tmax, pdf; };
+// Area::SampleLight (src/area.h:14) -> Triangle::SampleShape (src/mesh.h:100)
+__device__ __forceinline__ void area_sample(const WLight& L, f3 pos, float ux, float uy, float eps, LightSample& ls) {
+    f2 uv = uniform_triangle(ux, uy);
+    f3 p = uv.x * ld3(L.v1) + uv.y * ld3(L.v2) + (1 - uv.x - uv.y) * ld3(L.v3);
+    f3 normal = normalize(uv.x * ld3(L.n1) + uv.y * ld3(L.n2) + (1 - uv.x - uv.y) * ld3(L.n3));
+    f3 dir = p - pos;
+    float pdf = 1.f / (L.area * fabsf(dot(normal, normalize(dir)))) * dot(dir, dir);
+    if (dot(normal, dir) >= 0.f) pdf = 0.f;
+    ls.pdf = pdf;
+    ls.radiance = pdf != 0.f ? ld3(L.radiance) : mk3(0.f, 0.f, 0.f);
+    ls.dir = normalize(dir);
+    ls.tmax = sqrtf(dot(dir, dir) - eps);
+}
+// Infinite::SampleLight (src/infinite.h:17)
+__device__ __forceinline__ void inf_sample(const WInfinite& I, float ux, float uy, float eps, LightSample& ls) {
+    float pdfW;
+    f3 dir = uniform_sphere(ux, uy, pdfW);
+    f2 uv = inf_dir_to_uv(I, dir);
+    ls.dir = dir;
+    ls.tmax = 2.f * I.radius - eps;
+    ls.pdf = pdfW;
+    ls.radiance = inf_bilinear(I, uv);
+}
+
+__device__ __forceinline__ f3 exp3(f3 c) { return mk3(expf(c.x), expf(c.y), expf(c.z)); }
+
+template <bool VOL>
+__global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= (uint32_t)a.pool.n) return;
+    const SceneDev& sc = a.sc;
+
+    float4 df = a.pool.d_flags[slot];
+    uint32_t flags = __float_as_uint(df.w);
+    float4 orng = a.pool.o_rng[slot];
+    uint32_t rng = __float_as_uint(orng.w);
+    f3 o = mk3(orng.x, orng.y, orng.z);
+    f3 d = mk3(df.x, df.y, df.z);
+    f3 beta, Li;
+    uint32_t sample;
+    bool alive = (flags & F_ALIVE) != 0;
+    bool finished = false;
+    if (alive) {
+        float4 bs = a.pool.beta_s[slot];
+        float4 lt = a.pool.li_t[slot];
+        beta = mk3(bs.x, bs.y, bs.z); sample = __float_as_uint(bs.w);
+        Li = mk3(lt.x, lt.y, lt.z);
+    } else {
+        if (a.counters->next_sample >= a.batch.total) return;    // nothing left to regenerate: stay dead
+        beta = mk3(1, 1, 1); Li = mk3(0, 0, 0); sample = 0;
+        finished = true;                                         // take the regeneration path below
+    }
+    int bounces = (int)((flags >> kBounceShift) & 0xffu);
+    int medium = (int)((flags >> kMediumShift) & 0xffu) - 1;      // medium of the continuation ray (vpt)
+
+    // ---------------------------------------------------------------- A. pending direct light of the previous bounce
+    if (alive && (flags & F_PENDING)) {
+        const float4 bo = a.pool.beta_old[slot];
+        const f3 beta_old = mk3(bo.x, bo.y, bo.z);
+        const int medium2 = (int)((flags >> kMedium2Shift) & 0xffu) - 1;
+        if (VOL && (flags & F_MEDSCATTER)) {
+            // Li += tr*beta*phase*radiance / (lightPdf*choicePdf)   (src/pathtracer.cu:1092-1093)
+            if (flags & F_SHADOW) {
+                const float4 v = a.pool.vis[slot]; const float4 l = a.pool.ldl[slot]; const float4 mf = a.pool.misf[slot];
+                f3 tr = mk3(v.x, v.y, v.z), radiance = mk3(l.x, l.y, l.z);
+                Li += tr * beta_old * mf.x * radiance / mf.y;
+            }
+        } else {
+            f3 Ld = mk3(0.f, 0.f, 0.f);
+            if (flags & F_SHADOW) {
+                const float4 v = a.pool.vis[slot]; const float4 l = a.pool.ldl[slot];
+                if (!VOL) {
+                    if (v.x != 0.f) Ld += mk3(l.x, l.y, l.z);                                   // :942-951
+                } else {
+                    // Ld += weight*tr*fr*radiance*|cos| / (lightPdf*choicePdf)                  // :1153-1154
+                    const float4 ax = a.pool.aux[slot];   // radiance xyz, weight
+                    const float4 mf = a.pool.misf[slot];
+                    f3 tr = mk3(v.x, v.y, v.z), fr = mk3(l.x, l.y, l.z), radiance = mk3(ax.x, ax.y, ax.z);
+                    Ld += ax.w * tr * fr * radiance * bo.w / mf.w;
+                }
+            }
+            if (flags & F_MIS) {
+                const float4 md = a.pool.misd[slot]; const float4 mf = a.pool.misf[slot];
+                const float4 h1 = a.pool.hit1[slot];
+                const float absdot = a.pool.ldl[slot].w;
+                const f3 out = mk3(md.x, md.y, md.z), fr = mk3(mf.x, mf.y, mf.z);
+                const float pdf = md.w;
+                if (h1.x >= 0.f) {
+                    const int prim = __float_as_int(h1.y);
+                    const int lightIdx = sc.shade[prim].lightIdx;
+                    f3 p = o + h1.x * out;
+                    f3 n = hit_normal(sc, p, prim, h1.z, h1.w);
+                    f3 radiance = mk3(0.f, 0.f, 0.f);
+                    if (lightIdx != -1) {
+                        const WLight& L = sc.lights[lightIdx];
+                        if (dot(n, -out) > 0.f) radiance = ld3(L.radiance);                     // Area::Le, src/area.h:38
+                        if (!is_black(radiance)) {
+                            float pdfA = 1.f / L.area;                                          // Area::Pdf, src/area.h:28
+                            float choicePdf = sc.cdf[lightIdx + 1] - sc.cdf[lightIdx];
+                            float lenSquare = dot(p - o, p - o);
+                            float costheta = fabsf(dot(n, out));
+                            float lPdf = pdfA * lenSquare / (costheta);
+                            float weight = power_heuristic(1, pdf, 1, lPdf * choicePdf);
+                            if (!VOL) Ld += weight * fr * radiance * absdot / pdf;               // :975
+                            else {
+                                f3 tr = mk3(1.f, 1.f, 1.f);
+                                if (medium2 >= 0) tr = exp3(ld3(sc.mediums[medium2].sigmaT) * (-h1.x));
+                                Ld += weight * tr * fr * radiance * absdot / pdf;                // :1185
+                            }
+                        }
+                    }
+                } else if (sc.inf.isvalid) {
+                    f3 radiance = inf_le(sc.inf, out);
+                    float choicePdf = sc.cdf[sc.n_lights + 1] - sc.cdf[sc.n_lights];
+                    float weight = power_heuristic(1, pdf, 1, kInvFourPi * choicePdf);
+                    if (!VOL) Ld += weight * fr * radiance * absdot / pdf;                       // :989
+                    else {
+                        f3 tr = mk3(1.f, 1.f, 1.f);
+                        if (medium2 >= 0) tr = exp3(ld3(sc.mediums[medium2].sigmaT) * (-INFINITY));
+                        Ld += weight * tr * fr * radiance * absdot / pdf;                        // :1205
+                    }
+                }
+            }
+            Li += beta_old * Ld;                                                                // :994
+        }
+        if (flags & F_TERMINATE) finished = true;
+    }
+
+    // ---------------------------------------------------------------- B. shade the continuation hit
+    uint32_t nf = F_ALIVE;          // flags of the next step
+    f3 new_o = o, new_d = d;
+    bool specular = (flags & F_SPECULAR) != 0;
+    if (alive && !finished) {
+        const float4 h0 = a.pool.hit0[slot];
+        if (h0.x < 0.f) {                                                                       // miss, :905-909
+            if ((bounces == 0 || specular) && sc.inf.isvalid) Li += beta * inf_le(sc.inf, d);
+            finished = true;
+        } else {
+            SurfaceHit h;
+            reconstruct_hit(sc, o, d, h0.x, __float_as_int(h0.y), h0.z, h0.w, h);
+            bool shade_surface = true;
+            if (VOL) {
+                float sampledDist = 0.f; bool sampledMedium = false;
+                if (medium >= 0) {                                                              // Homogeneous::Sample, src/medium.h:19
+                    const WMedium& M = sc.mediums[medium];
+                    f3 sigmaT = ld3(M.sigmaT), sigmaS = ld3(M.sigmaS);
+                    float sigma = dot(sigmaT, mk3(0.212671f, 0.715160f, 0.072169f));
+                    float dist = -logf(rng_next(rng)) / sigma;
+                    f3 Tr = exp3(sigmaT * -dist);
+                    float pdf = sigma * expf(sigma * -dist);
+                    sampledMedium = dist < h0.x;
+                    sampledDist = dist;
+                    beta *= sampledMedium ? (Tr * sigmaS / pdf) : sigmaT * Tr / pdf;
+                }
+                if (is_black(beta)) { finished = true; shade_surface = false; }                 // :1070
+                else if (sampledMedium) {                                                       // :1071-1101
+                    shade_surface = false;
+                    const WMedium& M = sc.mediums[medium];
+                    float u = rng_next(rng);
+                    float choicePdf;
+                    int idx = lookup_light(sc, u, choicePdf);
+                    if (idx < 0) idx = 0;
+                    f3 samplePos = o + sampledDist * d;
+                    float ua = rng_next(rng), ub = rng_next(rng);
+                    LightSample ls;
+                    if (idx != sc.n_lights) area_sample(sc.lights[idx], samplePos, ua, ub, sc.eps, ls);
+                    else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+                    float phase = kInvFourPi;                                                   // Medium::Phase, src/medium.h:222
+                    if (M.g != 0) {
+                        float costheta = dot(-d, ls.dir);
+                        float cubicTerm = (1.f + M.g * M.g - 2.f * M.g * costheta);
+                        phase = kInvFourPi * (1.f - M.g * M.g) / sqrtf(cubicTerm * cubicTerm * cubicTerm);
+                    }
+                    nf |= F_PENDING | F_MEDSCATTER;
+                    a.pool.beta_old[slot] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                    if (!is_black(ls.radiance)) {                                               // Tr() is side-effect free otherwise
+                        nf |= F_SHADOW;
+                        a.pool.shd[slot] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax);
+                        a.pool.ldl[slot] = make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f);
+                        a.pool.misf[slot] = make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f);
+                    }
+                    float pa = rng_next(rng), pb = rng_next(rng);                               // Medium::SamplePhase, src/medium.h:197
+                    f3 dir;
+                    if (M.g == 0) { float pdf_; dir = uniform_sphere(pa, pb, pdf_); }
+                    else {
+                        float costheta;
+                        if (fabsf(M.g) < 1e-3f) costheta = 1.f - 2.f * pa;
+                        else {
+                            float sqrtTerm = (1.f - M.g * M.g) / (1.f - M.g + 2.f * M.g * pa);
+                            costheta = (1.f + M.g * M.g - sqrtTerm * sqrtTerm) / (2.f * M.g);
+                        }
+                        float sintheta = sqrtf(1.f - costheta * costheta);
+                        float phi = kTwoPi * pb;
+                        float sinphi = sinf(phi), cosphi = cosf(phi);
+                        dir = mk3(sintheta * cosphi, costheta, sintheta * sinphi);
+                    }
+                    new_o = samplePos; new_d = dir;
+                    nf |= F_CONT | ((uint32_t)(medium + 1) << kMediumShift) | ((uint32_t)(medium + 1) << kMedium2Shift);
+                    specular = false;
+                    // Russian roulette + depth limit shared with the surface branch below
+                    int b_old = bounces;
+                    bounces = bounces + 1;
+                    if (b_old > 3) {
+                        float illumate = clampf(1.f - luminance(beta), 0.f, 1.f);
+                        if (rng_next(rng) < illumate) nf = (nf | F_TERMINATE) & ~F_CONT;
+                        else beta /= (1 - illumate);
+                    }
+                    if (bounces >= sc.max_depth) nf = (nf | F_TERMINATE) & ~F_CONT;
+                }
+            }
+            if (shade_surface) {
+                bool emitter_hit = (bounces == 0 || specular) && h.lightIdx != -1;
+                if (emitter_hit) {                                                              // :917-922 / :1103-1115
+                    const WLight& L = sc.lights[h.lightIdx];
+                    f3 le = dot(h.nor, -d) > 0.f ? ld3(L.radiance) : mk3(0.f, 0.f, 0.f);
+                    if (!VOL) Li += beta * le;
+                    else {
+                        f3 tr = mk3(1.f, 1.f, 1.f);
+                        if (medium >= 0) tr = exp3(ld3(sc.mediums[medium].sigmaT) * (-h0.x));
+                        Li += tr * beta * le;
+                    }
+                    finished = true;
+                } else if (VOL && h.matIdx == -1) {                                             // medium boundary, :1117-1124
+                    int m = dot(d, h.nor) > 0 ? h.mediumOutside : h.mediumInside;
+                    new_o = h.pos; new_d = d;
+                    nf |= F_CONT | ((uint32_t)(m + 1) << kMediumShift);
+                    // bounces unchanged, no Russian roulette (the reference `continue`s)
+                } else {
+                    const Material mat = sc.mats[h.matIdx];
+                    const f3 albedo = ld3(mat.diffuse);                                         // GetTexel, textureIdx == -1
+                    const f3 wo = -d;
+                    if (!is_delta(mat.type)) {                                                  // :925-995
+                        float u = rng_next(rng);
+                        float choicePdf;
+                        int idx = lookup_light(sc, u, choicePdf);
+                        if (idx < 0) idx = 0;      // u outside every interval (NaN): the reference falls off its loop (UB)
+                        float ua = rng_next(rng), ub = rng_next(rng);
+                        LightSample ls;
+                        if (idx != sc.n_lights) area_sample(sc.lights[idx], h.pos, ua, ub, sc.eps, ls);
+                        else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+                        nf |= F_PENDING;
+                        a.pool.beta_old[slot] = make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir)));
+                        float mis_absdot = 0.f;
+                        f3 ldl = mk3(0, 0, 0);
+                        if (!is_black(ls.radiance)) {
+                            f3 fr; float samplePdf;
+                            eval_bsdf(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
+                            float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
+                            nf |= F_SHADOW;
+                            a.pool.shd[slot] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax);
+                            if (!VOL) ldl = weight * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
+                            else {
+                                ldl = fr;
+                                a.pool.aux[slot] = make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight);
+                            }
+                        }
+                        float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
+                        f3 out, fr; float pdf;
+                        sample_bsdf(mat, albedo, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
+                        float denom = ls.pdf * choicePdf;
+                        if (!(is_black(fr) || pdf == 0)) {
+                            nf |= F_MIS;
+                            mis_absdot = fabsf(dot(out, h.nor));
+                            a.pool.misd[slot] = make_float4(out.x, out.y, out.z, pdf);
+                            a.pool.misf[slot] = make_float4(fr.x, fr.y, fr.z, denom);
+                        } else if (VOL) {
+                            a.pool.misf[slot] = make_float4(0.f, 0.f, 0.f, denom);
+                        }
+                        a.pool.ldl[slot] = make_float4(ldl.x, ldl.y, ldl.z, mis_absdot);
+                        nf |= ((uint32_t)(medium + 1) << kMedium2Shift);
+                    }
+                    float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :997-1003
+                    f3 out, fr; float pdf;
+                    sample_bsdf(mat, albedo, wo, h.nor, h.dpdu, mk3(c0, c1, c2), out, fr, pdf);
+                    if (is_black(fr)) {
+                        nf |= F_TERMINATE;
+                    } else {
+                        beta *= fr * fabsf(dot(h.nor, out)) / pdf;                              // :1005
+                        specular = is_delta(mat.type);
+                        int m = -1;
+                        if (VOL) {                                                              // :1224-1226
+                            m = dot(out, h.nor) > 0 ? h.mediumOutside : h.mediumInside;
+                            m = dot(-d, h.nor) * dot(out, h.nor) > 0 ? medium : m;
+                        }
+                        new_o = h.pos; new_d = out;
+                        nf |= F_CONT | ((uint32_t)(m + 1) << kMediumShift);
+                        int b_old = bounces;
+                        bounces = bounces + 1;
+                        if (b_old > 3) {                                                        // :1010-1016
+                            float illumate = clampf(1.f - luminance(beta), 0.f, 1.f);
+                            if (rng_next(rng) < illumate) nf = (nf | F_TERMINATE) & ~F_CONT;
+                            else beta /= (1 - illumate);
+                        }
+                        if (bounces >= sc.max_depth) nf = (nf | F_TERMINATE) & ~F_CONT;        // loop bound, :904
+                    }
+                    // the shadow/MIS rays of this bounce start at the hit point as well
+                    if (!(nf & F_CONT)) new_o = h.pos;
+                }
+            }
+            // a path that ends with nothing pending retires right away
+            if (!finished && (nf & F_TERMINATE) && !(nf & F_PENDING)) finished = true;
+        }
+    }
+
+    // ---------------------------------------------------------------- C. retire + regenerate
+    if (finished) {
+        if (alive) {
+            a.samples[sample] = make_float4(Li.x, Li.y, Li.z, 1.f);
+            atomicAdd(&a.counters->done_samples, 1ull);
+        }
+        const unsigned long long s = atomicAdd(&a.counters->next_sample, 1ull);
+        if (s >= a.batch.total) {
+            a.pool.d_flags[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));            // dead
+            return;
+        }
+        sample = (uint32_t)s;
+        const uint32_t npix = (uint32_t)a.map.n_local_pixels;
+        const uint32_t it_local = sample / npix, local = sample - it_local * npix;
+        uint32_t x, y;
+        local_to_xy(a.map, local, x, y);
+        const uint32_t pixel = x + y * (uint32_t)a.map.width;                                   // :883
+        rng = rng_seed(pixel, a.batch.first_iter + it_local);                                   // :888
+        float offsetx = rng_next(rng) - 0.5f;                                                   // :892-897
+        float offsety = rng_next(rng) - 0.5f;
+        float a0 = rng_next(rng), a1 = rng_next(rng);
+        f2 aperture = mk2(0.f, 0.f);
+        if (a.cam.apertureRadius > 0.00001f) aperture = uniform_disk(a0, a1);                    // unused otherwise (camera.h:63)
+        camera_ray(a.cam, x + offsetx, y + offsety, aperture, new_o, new_d);
+        beta = mk3(1.f, 1.f, 1.f); Li = mk3(0.f, 0.f, 0.f);
+        bounces = 0; specular = false;
+        int m = VOL ? a.cam.medium : -1;                                                        // :1043
+        nf = F_ALIVE | F_CONT | ((uint32_t)(m + 1) << kMediumShift);
+    }
+    if (specular) nf |= F_SPECULAR;
+    nf |= ((uint32_t)bounces & 0xffu) << kBounceShift;
+    a.pool.o_rng[slot] = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng));
+    a.pool.d_flags[slot] = make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf));
+    a.pool.beta_s[slot] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample));
+    a.pool.li_t[slot] = make_float4(Li.x, Li.y, Li.z, 0.f);
+}
+
+// ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------
+// Per pixel, in iteration order: NaN/Inf samples keep the previous iteration's colour (:1019-1020),
+// acc += colour, and the last iteration's tonemapped acc/iter goes to `out`.
+struct ResolveArgs {
+    const float4* samples; float* acc; float* color; float* out;
+    ShardMap map; BatchParams batch;
+    int reset; int filmic; int write_out;
+};
+__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t npix = (uint32_t)a.map.n_local_pixels;
+    if (local >= npix) return;
+    uint32_t x, y;
+    local_to_xy(a.map, local, x, y);
+    const size_t pixel = (size_t)x + (size_t)y * (size_t)a.map.width;
+    f3 color = mk3(a.color[3 * pixel], a.color[3 * pixel + 1], a.color[3 * pixel + 2]);
+    f3 acc = a.reset ? mk3(0.f, 0.f, 0.f) : mk3(a.acc[3 * pixel], a.acc[3 * pixel + 1], a.acc[3 * pixel + 2]);
+    for (uint32_t k = 0; k < a.batch.n_iters; ++k) {
+        const float4 s = a.samples[(size_t)k * npix + local];
+        const f3 L = mk3(s.x, s.y, s.z);
+        if (!is_inf3(L) && !is_nan3(L)) color = L;
+        acc += color;
+    }
+    a.color[3 * pixel] = color.x; a.color[3 * pixel + 1] = color.y; a.color[3 * pixel + 2] = color.z;
+    a.acc[3 * pixel] = acc.x; a.acc[3 * pixel + 1] = acc.y; a.acc[3 * pixel + 2] = acc.z;
+    if (a.write_out) {
+        const uint32_t iter = a.batch.first_iter + a.batch.n_iters - 1;
+        f3 c = acc / (float)(int)iter;
+        c = a.filmic ? filmic_tonemap(c) : gamma_correct(c);
+        a.out[3 * pixel] = c.x; a.out[3 * pixel + 1] = c.y; a.out[3 * pixel + 2] = c.z;
+    }
+}
+
+// out = tonemap(acc / iter) for an externally reduced accumulation image (multi-GPU, after the NCCL reduce)
+__global__ void k_tonemap(const float* acc, float* out, uint32_t npix, uint32_t iter, int filmic) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    f3 c = mk3(acc[3 * p], acc[3 * p + 1], acc[3 * p + 2]) / (float)(int)iter;
+    c = filmic ? filmic_tonemap(c) : gamma_correct(c);
+    out[3 * p] = c.x; out[3 * p + 1] = c.y; out[3 * p + 2] = c.z;
+}
+
+}  // namespace pt

@@ -1,0 +1,133 @@
+// wavefront.cuh — device-side data layout of the wavefront integrator.
+//
+// The reference keeps one path per thread in registers for its whole life (src/pathtracer.cu:880-1021).
+// Here a path lives in a slot of a structure-of-arrays POOL in HBM/L2 and moves through two kernels per
+// bounce:  k_trace (all rays of all slots: continuation closest-hit, shadow any-hit, MIS closest-hit) and
+// k_shade (finish the previous bounce's direct light, shade the new hit, emit the next three rays, or
+// retire the sample and regenerate the slot from the global sample counter).
+#pragma once
+#include <stdint.h>
+#include "cuda_compat.h"
+#include "pt_math.cuh"
+
+namespace pt {
+
+// ---- re-laid-out scene (built once per context by k_prepare_* from the reference's arrays) ---------------
+// Two-child BVH node, 64 B: both child boxes in one record so one visit = two slab tests + one 64-B fetch
+// (the reference fetches a 40-B node per box test, src/pathtracer.cu:222).
+//   q0 = lmin.xyz, lmax.x   q1 = lmax.yz, rmin.xy   q2 = rmin.z, rmax.xyz   q3 = {left, right, -, -}
+// child >= 0: inner node index; child < 0: leaf whose first primitive is ~child (the run ends at the WPrim
+// flagged last-in-leaf).
+struct WNode { float4 q0, q1, q2; int4 link; };
+static_assert(sizeof(WNode) == 64, "WNode");
+constexpr int kEmptyChild = 0x7fffffff;
+
+// Intersection record per primitive (leaf order), 48 B: v0, e1 = v1-v0, e2 = v2-v0 for Moeller-Trumbore
+// (src/mesh.h:45-66 recomputes the edges per test from a 176-B Primitive), or centre+radius for a sphere.
+//   q0 = v0.xyz, e1.x   q1 = e1.yz, e2.xy   q2 = e2.z, type(bits), last-in-leaf(bits), -
+struct WPrim { float4 q0, q1, q2; };
+static_assert(sizeof(WPrim) == 48, "WPrim");
+
+// Shading record per primitive, 96 B: fetched once per FINAL hit (the reference interpolates normal/uv/dpdu
+// for every accepted candidate, src/mesh.h:68-95).
+struct WShade {
+    float n1[3], n2[3], n3[3];      // vertex normals            (sphere: n1 = centre, n2.x = radius)
+    float uv1[2], uv2[2], uv3[2];
+    float ndpdv[3];                 // normalize(dpdv) of the triangle (constant per triangle)
+    int32_t matIdx, lightIdx, mediumInside, mediumOutside;
+    int32_t type, _pad;
+};
+static_assert(sizeof(WShade) == 96, "WShade");
+
+// Emitter record per Area light (src/area.h:7), 96 B.
+struct WLight {
+    float v1[3], v2[3], v3[3];
+    float n1[3], n2[3], n3[3];
+    float radiance[3];
+    float area;                     // Triangle::GetSurfaceArea (src/mesh.h:39), computed once on the device
+    float _pad[2];
+};
+static_assert(sizeof(WLight) == 96, "WLight");
+
+struct WMedium { float sigmaA[3], sigmaS[3], sigmaT[3]; float g; int32_t type; int32_t _pad; };   // homogeneous (src/medium.h:9)
+
+struct WInfinite {                  // src/infinite.h:6 with a device texel pointer
+    const float* data; int32_t width, height;
+    float center[3], radius, u[3], v[3], w[3];
+    int32_t isvalid;
+};
+
+struct SceneDev {
+    const WNode* nodes; const WPrim* prims; const WShade* shade; const WLight* lights;
+    const Material* mats; const WMedium* mediums; const float* cdf;
+    WInfinite inf;
+    float root_min[3], root_max[3];
+    int32_t n_nodes, n_prims, n_lights, n_cdf, n_mats, n_mediums;
+    int32_t root_leaf_count;        // > 0 when the whole scene is a single leaf (no inner node)
+    int32_t integrator, max_depth;
+    float eps;
+};
+
+// ---- path pool -------------------------------------------------------------------------------------------
+// flags word
+constexpr uint32_t F_ALIVE = 1u << 0;        // slot holds a live sample
+constexpr uint32_t F_CONT = 1u << 1;         // continuation ray to trace this step (closest hit -> hit0)
+constexpr uint32_t F_SHADOW = 1u << 2;       // shadow ray to trace (any hit, or Tr() walk for vpt)
+constexpr uint32_t F_MIS = 1u << 3;          // BSDF-sampled MIS ray to trace (closest hit -> hit1)
+constexpr uint32_t F_PENDING = 1u << 4;      // previous bounce's direct light still to be added
+constexpr uint32_t F_TERMINATE = 1u << 5;    // retire after the pending direct light is added
+constexpr uint32_t F_SPECULAR = 1u << 6;     // last bounce was a delta BSDF
+constexpr uint32_t F_MEDSCATTER = 1u << 7;   // pending contribution is a medium in-scatter (vpt)
+constexpr int kBounceShift = 8;              // bits 8..15: bounce counter
+constexpr int kMediumShift = 16;             // bits 16..23: continuation ray's medium index + 1 (0 = none)
+constexpr int kMedium2Shift = 24;            // bits 24..31: medium of the shadow / MIS rays + 1
+
+struct Pool {
+    float4* o_rng;        // ray origin xyz (shared by all three rays of the slot), rng state bits
+    float4* d_flags;      // continuation direction xyz, flags bits
+    float4* beta_s;       // throughput xyz, sample index bits
+    float4* li_t;         // radiance accumulated so far xyz, -
+    float4* shd;          // shadow ray direction xyz, tmax
+    float4* misd;         // MIS ray direction xyz, pdf
+    float4* ldl;          // direct-light term if unoccluded xyz, |cos| of the MIS direction
+    float4* misf;         // BSDF value of the MIS sample xyz, -
+    float4* beta_old;     // throughput in front of the pending direct light xyz, -
+    float4* hit0;         // continuation hit: t (<0 miss), prim bits, b1, b2
+    float4* hit1;         // MIS hit
+    float4* vis;          // shadow result: transmittance xyz (0 = occluded; 1 for `pt`), -
+    float4* aux;          // vpt only: emitter radiance xyz, MIS weight of the light sample
+    int32_t n;
+};
+
+struct Counters {
+    unsigned long long next_sample;    // next (iteration, pixel) pair to hand out
+    unsigned long long done_samples;   // retired samples
+    unsigned long long rays;           // rays traced (statistics)
+    unsigned long long _pad;
+};
+
+// Which pixels this context renders: interleaved screen tiles (multi-GPU sharding).
+struct ShardMap {
+    int32_t width, height;
+    int32_t tile_w, tile_h, tiles_x, tiles_y;
+    int32_t shard, n_shards;
+    int32_t n_local_tiles, n_local_pixels;
+};
+// local pixel index -> global pixel (x, y). Local order: tile-major, row-major inside the tile.
+__device__ __forceinline__ void local_to_xy(const ShardMap& m, uint32_t local, uint32_t& x, uint32_t& y) {
+    if (m.n_shards == 1) { x = local % (uint32_t)m.width; y = local / (uint32_t)m.width; return; }
+    uint32_t per_tile = (uint32_t)(m.tile_w * m.tile_h);
+    uint32_t lt = local / per_tile, in = local - lt * per_tile;
+    uint32_t tile = lt * (uint32_t)m.n_shards + (uint32_t)m.shard;
+    uint32_t ty = tile / (uint32_t)m.tiles_x, tx = tile - ty * (uint32_t)m.tiles_x;
+    uint32_t iy = in / (uint32_t)m.tile_w, ix = in - iy * (uint32_t)m.tile_w;
+    x = tx * (uint32_t)m.tile_w + ix; y = ty * (uint32_t)m.tile_h + iy;
+}
+
+struct BatchParams {
+    uint32_t first_iter;     // iteration number of sample plane 0 (1-based, part of the RNG seed)
+    uint32_t n_iters;        // iterations in this batch
+    unsigned long long total;  // n_iters * n_local_pixels
+};
+
+}  // namespace pt

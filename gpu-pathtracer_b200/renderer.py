@@ -49,14 +49,6 @@ class PathTracer:
                                           out.ctypes.data, 0), "render")
         return out
 
-    def render_async(self, iter, spp, reset=False, camera=None, output_device=None):
-        cam = self.scene.camera if camera is None else camera
-        _lib.check(self.lib.b200pt_render_async(self._ctx, cam.ctypes.data, int(iter), int(spp), int(bool(reset)),
-                                                C.c_void_p(int(output_device)) if output_device else None), "render_async")
-
-    def sync(self):
-        _lib.check(self.lib.b200pt_sync(self._ctx), "sync")
-
     def accum(self):
         """kernel_acc_image: linear sum over iterations, (h, w, 3)."""
         a = np.empty((self.height, self.width, 3), np.float32)

@@ -90,12 +90,6 @@ int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uint32_t heigh
 int b200pt_render(b200pt_ctx* ctx, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
                   float* output, int output_is_device);
 
-/* Same, asynchronous on the context's stream with everything device-resident (no host copies, no sync):
- * used for device-timed benchmarking; pair with b200pt_sync. */
-int b200pt_render_async(b200pt_ctx* ctx, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
-                        float* output_device);
-int b200pt_sync(b200pt_ctx* ctx);
-
 /* Linear accumulation buffer kernel_acc_image (src/pathtracer.cu:10,2525): w*h float3, sum over iterations.
  * dst may be host (dst_is_device=0) or device.  Pixels outside the shard are 0 (so shards sum exactly). */
 int b200pt_get_accum(b200pt_ctx* ctx, float* dst, int dst_is_device);
@@ -112,7 +106,7 @@ int b200pt_tonemap(b200pt_ctx* ctx, const float* acc_device, uint32_t iter, floa
 int b200pt_trace_primary(b200pt_ctx* ctx, const void* camera, uint32_t iter, float* hits_host);
 
 /* Counters of the last render call: [0]=samples, [1]=kernel launches, [2]=rays traced, [3]=wavefront steps,
- * [4]=device ms (CUDA events around the call's stream work). */
+ * [4]=device ms of the call (CUDA events on the context's stream around all kernels of the call). */
 int b200pt_stats(b200pt_ctx* ctx, double* out5);
 
 /* Tunables (pool = number of path slots in flight; 0 keeps default). */

@@ -1,0 +1,127 @@
+"""GPU (B200): the CUDA product through the C ABI against
+  (1) the reference's OWN CUDA integrator compiled for sm_100a (oracle/_ref/libref_cuda.so) — oracle of record,
+  (2) the CPU oracle (oracle/pt_oracle.cpp), at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes: tile shards sum bit-exactly to the unsharded
+      image, one batched call == one Render per iteration, determinism.
+Tolerance (north_star): per-channel RMSE of the linear image acc/spp <= 1e-4."""
+import numpy as np
+import pytest
+
+import gpu_pathtracer_b200 as pt
+from tests import refhost
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+SCENES = {
+    "cornell_c1": (lambda: pt.scenes.cornell_pt(256, 256, 4), 64),
+    "cornell_depth8": (lambda: pt.scenes.cornell_pt(256, 256, 8), 32),
+    "veach_c3": (lambda: pt.scenes.veach_standin(256, 192, 17), 32),
+    "random_tris_c4": (lambda: pt.scenes.random_triangles(50000, 256, 256, 8), 16),
+    "vol_caustic_c5": (lambda: pt.scenes.cornell_vol_caustic(256, 256, 17), 32),
+}
+
+
+def _rmse(a, b):
+    return np.sqrt(((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean(axis=(0, 1)))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _render(scene, first, spp, **kw):
+    with pt.PathTracer(scene, **kw) as r:
+        tone = r.render(first, reset=True, spp=spp)
+        acc = r.accum()
+        st = r.stats()
+    assert st["launches"] > 0 and st["rays"] > 0
+    return acc, tone
+
+
+@pytest.mark.skipif(not refhost.have("libref_cuda.so"), reason="oracle/_ref/libref_cuda.so not present")
+@pytest.mark.parametrize("name", list(SCENES))
+def test_matches_reference_cuda_integrator(name):
+    mk, spp = SCENES[name]
+    s = mk()
+    ref = refhost.RefCuda()
+    ref.begin(s)
+    try:
+        ref_tone, _ = ref.render(1, spp)
+        ref_acc = ref.accum()
+    finally:
+        ref.end()
+    acc, tone = _render(s, 1, spp)
+    rmse = _rmse(acc / spp, ref_acc / spp)
+    same = float((_bits(acc) == _bits(ref_acc)).all(-1).mean())
+    print(f"{name}: rmse={rmse} bit-identical pixels={same:.5f} mean={acc.mean((0, 1)) / spp}")
+    assert ref_acc.mean() / spp > 1e-3
+    assert (rmse <= TOL).all(), rmse
+    assert (_rmse(tone, ref_tone) <= TOL).all()
+
+
+@pytest.mark.parametrize("name", ["cornell_c1", "veach_c3", "vol_caustic_c5", "random_tris_c4"])
+def test_matches_cpu_oracle(name, oracle):
+    mk, _ = SCENES[name]
+    s = mk()
+    spp = 8
+    ref_acc, ref_tone = oracle.render(s, 3, spp)
+    acc, tone = _render(s, 3, spp)
+    rmse = _rmse(acc / spp, ref_acc / spp)
+    print(f"{name}: rmse vs cpu oracle={rmse} bit-identical pixels={float((_bits(acc) == _bits(ref_acc)).all(-1).mean()):.5f}")
+    # GPU libdevice sinf/cosf/rsqrtf differ from libm in the last ulp, so a handful of paths take another
+    # discrete decision; the bound is the north_star tolerance scaled by sqrt(64/spp) for the smaller sample count
+    assert (rmse <= TOL * np.sqrt(64 / spp)).all(), rmse
+
+
+def test_primary_hits_match_oracle_intersect(oracle):
+    s = pt.scenes.cornell_pt(64, 64, 4)
+    with pt.PathTracer(s) as r:
+        hits = r.trace_primary(iter=1)
+    oracle.begin(s)
+    try:
+        bad = 0
+        for y in range(0, 64, 3):
+            for x in range(0, 64, 3):
+                pixel = x + y * 64
+                u = oracle.rng(pixel, 1, 4)
+                o, d = oracle.camera_ray(s.camera, np.float32(x) + (u[0] - np.float32(0.5)), np.float32(y) + (u[1] - np.float32(0.5)), 0.0, 0.0)
+                h, t, isect = oracle.intersect(np.concatenate([o, d, [np.float32(0.001), np.inf]]).astype(np.float32))
+                got_t = hits[y, x, 0]
+                if h:
+                    bad += not (abs(got_t - t) <= 1e-5 * max(1.0, abs(t)))
+                else:
+                    bad += got_t >= 0
+        assert bad == 0
+    finally:
+        oracle.end()
+
+
+def test_full_size_properties_c2():
+    """1024x1024 Cornell, depth 8: 2 shards sum bit-exactly to the unsharded image; batched == iterated; deterministic."""
+    s = pt.scenes.cornell_pt(1024, 1024, 8)
+    spp = 4
+    full, tone = _render(s, 1, spp)
+    again, _ = _render(s, 1, spp, pool=200_000)
+    assert np.array_equal(_bits(full), _bits(again))
+    total = np.zeros_like(full)
+    for k in range(2):
+        a, _ = _render(s, 1, spp, shard=(k, 2, 32, 32))
+        total += a
+    assert np.array_equal(_bits(total), _bits(full))
+    with pt.PathTracer(s) as r:
+        for it in range(1, spp + 1):
+            t2 = r.render(it, reset=(it == 1))
+        assert np.array_equal(_bits(r.accum()), _bits(full))
+        assert np.array_equal(_bits(t2), _bits(tone))
+    assert np.isfinite(full).all() and full.mean() / spp > 0.05
+
+
+def test_full_size_properties_c4_sharded():
+    s = pt.scenes.random_triangles(200_000, 512, 512, 8)
+    full, _ = _render(s, 1, 2)
+    total = np.zeros_like(full)
+    for k in range(4):
+        a, _ = _render(s, 1, 2, shard=(k, 4, 32, 32))
+        total += a
+    assert np.array_equal(_bits(total), _bits(full))

@@ -1,0 +1,129 @@
+"""CPU: the product's own wavefront sources (k_trace / k_shade / k_resolve + the batching and polling host loop),
+compiled for the host by tests/emu, against the CPU oracle — bit-exact, because both run the same float
+expressions without FMA contraction.  Covers: regeneration with tiny pools, multi-batch renders, incremental
+Render calls vs one batched call, tile sharding (the N>1 path, exercised with world_size 2 over gloo in
+tests/test_multi_rank.py), error behaviour."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import gpu_pathtracer_b200 as pt
+from gpu_pathtracer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "libb200pt_emu.so")
+
+
+@pytest.fixture()
+def emu():
+    saved = _lib._lib
+    _lib.load(EMU)
+    yield
+    _lib._lib = saved
+
+
+SCENES = {
+    "cornell": lambda: pt.scenes.cornell_pt(64, 64, 8),
+    "vol_caustic": lambda: pt.scenes.cornell_vol_caustic(64, 64, 17),
+    "veach": lambda: pt.scenes.veach_standin(64, 48, 17),
+    "random_tris": lambda: pt.scenes.random_triangles(5000, 64, 64, 8),
+}
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("pool", [None, 512])
+def test_wavefront_equals_oracle_bit_exact(name, pool, emu, oracle):
+    s = SCENES[name]()
+    spp = 3
+    ref_acc, ref_tone = oracle.render(s, 1, spp)
+    with pt.PathTracer(s, pool=pool) as r:
+        tone = r.render(1, reset=True, spp=spp)
+        acc = r.accum()
+        assert r.stats()["samples"] == spp * s.width * s.height
+    assert np.array_equal(_bits(acc), _bits(ref_acc))
+    assert np.array_equal(_bits(tone), _bits(ref_tone))
+
+
+def test_batched_call_equals_one_render_per_iteration(emu, oracle):
+    s = SCENES["cornell"]()
+    with pt.PathTracer(s) as a, pt.PathTracer(s) as b:
+        a.set_option("max_batch_bytes", 1 << 20)            # forces several batches inside one call
+        ta = a.render(7, reset=True, spp=20)
+        for it in range(7, 27):
+            tb = b.render(it, reset=(it == 7))
+        assert np.array_equal(_bits(a.accum()), _bits(b.accum()))
+        assert np.array_equal(_bits(ta), _bits(tb))
+        assert np.array_equal(_bits(a.color()), _bits(b.color()))
+        acc_b = b.accum()
+    ref_acc, _ = oracle.render(s, 7, 20)
+    assert np.array_equal(_bits(acc_b), _bits(ref_acc))
+
+
+def test_accumulation_continues_without_reset(emu):
+    s = SCENES["cornell"]()
+    with pt.PathTracer(s) as a, pt.PathTracer(s) as b:
+        a.render(1, reset=True, spp=2); a.render(3, reset=False, spp=2)
+        b.render(1, reset=True, spp=4)
+        assert np.array_equal(_bits(a.accum()), _bits(b.accum()))
+        a.render(5, reset=True, spp=1)
+        b.render(5, reset=True, spp=1)
+        assert np.array_equal(_bits(a.accum()), _bits(b.accum()))
+
+
+@pytest.mark.parametrize("n_shards,tile", [(2, 32), (3, 16), (8, 32)])
+def test_tile_shards_sum_to_the_unsharded_image_exactly(n_shards, tile, emu):
+    s = pt.scenes.cornell_pt(128, 64, 6)
+    with pt.PathTracer(s) as r:
+        full_tone = r.render(1, reset=True, spp=2)
+        full = r.accum()
+    total = np.zeros_like(full)
+    tone = np.zeros_like(full)
+    owners = np.zeros(full.shape[:2], np.int32)
+    for k in range(n_shards):
+        with pt.PathTracer(s, shard=(k, n_shards, tile, tile)) as r:
+            t = r.render(1, reset=True, spp=2)
+            a = r.accum()
+        owners += (a != 0).any(-1)
+        total += a
+        tone += t
+    assert owners.max() == 1                               # disjoint tiles: one non-zero contributor per pixel
+    assert np.array_equal(_bits(total), _bits(full))       # => bit-identical to the 1-GPU image
+    assert np.array_equal(_bits(tone), _bits(full_tone))
+
+
+def test_camera_is_reread_every_call(emu, oracle):
+    s = SCENES["cornell"]()
+    cam2 = pt._lib.HostPrep().camera([0.3, 1.1, 6.0], [0, 1.0, 0], [0, 1, 0], 64, 64, 0.1, 25.0, 0.05, 6.0, False, False, -1)
+    with pt.PathTracer(s) as r:
+        r.render(1, reset=True, camera=cam2, spp=2)
+        acc = r.accum()
+    s2 = SCENES["cornell"](); s2.camera = cam2
+    ref_acc, _ = oracle.render(s2, 1, 2)
+    assert np.array_equal(_bits(acc), _bits(ref_acc))      # thin-lens + gamma path too
+
+
+def test_error_codes(emu):
+    s = SCENES["cornell"]()
+    with pytest.raises(ValueError):
+        pt.PathTracer(s, width=100, height=64)
+    lib = _lib.load()
+    view, keep = _lib.make_view(s)
+    ctx = C.c_void_p()
+    assert lib.b200pt_create(C.byref(view), 96, 64, 0.001, 0, None, C.byref(ctx)) == 0
+    cam = s.camera
+    assert lib.b200pt_render(ctx, cam.ctypes.data, 0, 1, 1, None, 0) == -1        # iter is 1-based
+    assert b"1-based" in lib.b200pt_last_error()
+    assert lib.b200pt_render(ctx, cam.ctypes.data, 1, 0, 1, None, 0) == -1
+    assert lib.b200pt_destroy(ctx) == 0
+    view.integrator_type = 4                                                       # IT_BDPT: out of the hot path
+    assert lib.b200pt_create(C.byref(view), 64, 64, 0.001, 0, None, C.byref(ctx)) == -4
+    view.integrator_type = 1
+    bad = s.prims.copy(); bad["triangle"]["matIdx"][0] = 99
+    view.prims = bad.ctypes.data
+    assert lib.b200pt_create(C.byref(view), 64, 64, 0.001, 0, None, C.byref(ctx)) == -1
