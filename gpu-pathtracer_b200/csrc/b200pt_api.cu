@@ -38,6 +38,9 @@ struct b200pt_ctx {
     uint32_t width = 0, height = 0;
     int num_sms = 148, trace_blocks = 0;
     uint32_t stage_nodes = 0, stage_prims = 0;
+    size_t stage_top_bytes = 32 * 1024;    // top-of-tree nodes staged per CTA when the scene does not fit
+    RayQueue q{};
+    int refill_below = 24;
     size_t max_batch_bytes = (size_t)2 << 30;
     int steps_per_poll = 8;
     double stats[5] = {0, 0, 0, 0, 0};
@@ -147,9 +150,23 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         if (s.mediumInside >= v->n_mediums || s.mediumOutside >= v->n_mediums) return fail(B200PT_EINVAL, "medium index out of range");
     }
     // -- nodes: reference DFS layout (left child = i+1, right = second_child_offset) -> two-child records
+    // inner nodes are renumbered breadth-first, so that the first K records are the top of the tree (the part
+    // k_trace stages into shared memory) and siblings/cousins share cache lines
     std::vector<int> inner_id(v->n_nodes, -1);
     int n_inner = 0;
-    for (int i = 0; i < v->n_nodes; ++i) if (!nodes[i].is_leaf) inner_id[i] = n_inner++;
+    {
+        std::vector<int> bfs; bfs.reserve(v->n_nodes);
+        if (!nodes[0].is_leaf) bfs.push_back(0);
+        for (size_t h = 0; h < bfs.size(); ++h) {
+            const int i = bfs[h];
+            inner_id[i] = n_inner++;
+            const int l = i + 1, r = nodes[i].second_child_offset;
+            if (l >= v->n_nodes || r <= 0 || r >= v->n_nodes) return fail(B200PT_EINVAL, "BVH node child index out of range");
+            if (!nodes[l].is_leaf) bfs.push_back(l);
+            if (!nodes[r].is_leaf) bfs.push_back(r);
+            if ((int)bfs.size() > v->n_nodes) return fail(B200PT_EINVAL, "BVH node links form a cycle");
+        }
+    }
     auto mark_leaf = [&](const RefLinearBVHNode& n) -> int {
         if (n.start < 0 || n.end >= v->n_prims || n.end < n.start) return -1;
         int one = 1; float onef; std::memcpy(&onef, &one, 4);
@@ -161,6 +178,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     for (int i = 0; i < v->n_nodes; ++i) {
         const RefLinearBVHNode& n = nodes[i];
         if (n.is_leaf) { if (mark_leaf(n)) return fail(B200PT_EINVAL, "leaf node with an invalid primitive range"); continue; }
+        if (inner_id[i] < 0) continue;                              // not reachable from the root
         int l = i + 1, r = n.second_child_offset;
         if (l >= v->n_nodes || r <= 0 || r >= v->n_nodes) return fail(B200PT_EINVAL, "BVH node child index out of range");
         const RefLinearBVHNode& L = nodes[l]; const RefLinearBVHNode& R = nodes[r];
@@ -244,8 +262,10 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     c->vol = v->integrator_type == B200PT_IT_VPT;
 
     // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
+    // (TMA bulk copy): everything when the scene is small, else the top of the breadth-first node array
     size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
     if (nb + pb <= 40 * 1024) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; }
+    else { c->stage_nodes = (uint32_t)std::min<size_t>(nb, c->stage_top_bytes); c->stage_prims = 0; }
     CK(cudaStreamSynchronize(c->stream));     // host staging vectors go out of scope
     return 0;
 }
@@ -253,8 +273,12 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
 static int alloc_pool(b200pt_ctx* c, int n) {
     Pool& p = c->pool;
     float4** arrs[] = {&p.o_rng, &p.d_flags, &p.beta_s, &p.li_t, &p.shd, &p.misd, &p.ldl, &p.misf, &p.beta_old, &p.hit0, &p.hit1, &p.vis, &p.aux};
+    n = (n + 255) & ~255;
     for (auto a : arrs) { int rc = dev_alloc(c, a, (size_t)n, true); if (rc) return rc; }
     p.n = n;
+    int rc = dev_alloc(c, &c->q.entries, (size_t)3 * n, true);     // at most three rays per slot and step
+    if (rc) return rc;
+    if (!c->q.ctl && (rc = dev_alloc(c, &c->q.ctl, 1, true))) return rc;
     return 0;
 }
 
@@ -308,8 +332,8 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     // persistent traversal grid: resident CTAs per SM x SM count
     int per_sm = 0;
     size_t smem = (size_t)c->stage_nodes + c->stage_prims;
-    if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, 256, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, 256, smem);
+    if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
     if (per_sm <= 0) per_sm = 1;
     c->trace_blocks = c->num_sms * per_sm;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));
@@ -328,6 +352,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     }
     if (n == "steps_per_poll") { if (value < 1 || value > 1024) return fail(B200PT_EINVAL, "steps_per_poll out of range"); c->steps_per_poll = (int)value; return 0; }
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
+    if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
     if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; } return 0; }
     return fail(B200PT_EINVAL, "unknown option " + n);
 }
@@ -348,12 +373,15 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
     }
     BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
     CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 2, c->stream));   // next_sample, done_samples (rays keeps counting)
-    ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.cam = cam; sa.map = c->map; sa.batch = bp;
-    TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.counters = c->counters; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
+    CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
+    ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
+    TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
     const int shade_blocks = (c->pool.n + 127) / 128;
     const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
-    auto shade = [&]() { if (c->vol) PT_LAUNCH(k_shade<true>, shade_blocks, 128, 0, c->stream, sa); else PT_LAUNCH(k_shade<false>, shade_blocks, 128, 0, c->stream, sa); };
-    auto trace = [&]() { if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, 256, smem, c->stream, ta); else PT_LAUNCH(k_trace<false>, c->trace_blocks, 256, smem, c->stream, ta); };
+    // step i: shade emits its rays into queue set (i & 1); trace consumes that set and clears the other one
+    uint32_t step = 0;
+    auto shade = [&]() { sa.parity = step & 1u; if (c->vol) PT_LAUNCH(k_shade<true>, shade_blocks, 128, 0, c->stream, sa); else PT_LAUNCH(k_shade<false>, shade_blocks, 128, 0, c->stream, sa); };
+    auto trace = [&]() { ta.parity = step & 1u; if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); ++step; };
     // all slots start dead: the first shade pass only regenerates
     CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)c->pool.n, c->stream));
     shade(); *launches += 1;
@@ -470,11 +498,12 @@ extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t 
         Counters z; std::memset(&z, 0, sizeof(z)); z.next_sample = base;
         CK(cudaMemcpyAsync(c->counters, &z, sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)P, c->stream));
-        ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.cam = cam; sa.map = c->map; sa.batch = bp;
-        TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.counters = c->counters; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
+        CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
+        ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
+        TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
         const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
-        if (c->vol) { PT_LAUNCH(k_shade<true>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<true>, c->trace_blocks, 256, smem, c->stream, ta); }
-        else { PT_LAUNCH(k_shade<false>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<false>, c->trace_blocks, 256, smem, c->stream, ta); }
+        if (c->vol) { PT_LAUNCH(k_shade<true>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); }
+        else { PT_LAUNCH(k_shade<false>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); }
         CK(cudaMemcpyAsync(tmp.data(), c->pool.hit0, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(bs.data(), c->pool.beta_s, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));

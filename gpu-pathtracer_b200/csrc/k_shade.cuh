@@ -19,6 +19,8 @@ struct ShadeArgs {
     Pool pool;
     Counters* counters;
     float4* samples;          // [n_iters][n_local_pixels] radiance of every finished sample (w = 1)
+    RayQueue q;               // rays emitted by this step, consumed by the k_trace launch that follows
+    uint32_t parity;          // QueueCtl set of this step
     Camera cam;
     ShardMap map;
     BatchParams batch;
@@ -133,10 +135,9 @@ __device__ __forceinline__ void inf_sample(const WInfinite& I, float ux, float u
 
 __device__ __forceinline__ f3 exp3(f3 c) { return mk3(expf(c.x), expf(c.y), expf(c.z)); }
 
+// One path slot, one step.  Returns the rays the slot wants traced next (F_CONT | F_SHADOW | F_MIS bits).
 template <bool VOL>
-__global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= (uint32_t)a.pool.n) return;
+__device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_t slot) {
     const SceneDev& sc = a.sc;
 
     float4 df = a.pool.d_flags[slot];
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
         beta = mk3(bs.x, bs.y, bs.z); sample = __float_as_uint(bs.w);
         Li = mk3(lt.x, lt.y, lt.z);
     } else {
-        if (a.counters->next_sample >= a.batch.total) return;    // nothing left to regenerate: stay dead
+        if (a.counters->next_sample >= a.batch.total) return 0u; // nothing left to regenerate: stay dead
         beta = mk3(1, 1, 1); Li = mk3(0, 0, 0); sample = 0;
         finished = true;                                         // take the regeneration path below
     }
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
         const unsigned long long s = atomicAdd(&a.counters->next_sample, 1ull);
         if (s >= a.batch.total) {
             a.pool.d_flags[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));            // dead
-            return;
+            return 0u;
         }
         sample = (uint32_t)s;
         const uint32_t npix = (uint32_t)a.map.n_local_pixels;
@@ -446,6 +447,27 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     a.pool.d_flags[slot] = make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf));
     a.pool.beta_s[slot] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample));
     a.pool.li_t[slot] = make_float4(Li.x, Li.y, Li.z, 0.f);
+    return nf & (F_CONT | F_SHADOW | F_MIS);
+}
+
+template <bool VOL>
+__global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t rays = 0u;
+    if (slot < (uint32_t)a.pool.n) rays = shade_slot<VOL>(a, slot);
+    // append this warp's rays to the queue, class by class, with ONE atomic per warp
+    const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
+    const uint32_t mc = __ballot_sync(kFullMask, (rays & F_CONT) != 0u);
+    const uint32_t ms = __ballot_sync(kFullMask, (rays & F_SHADOW) != 0u);
+    const uint32_t mm = __ballot_sync(kFullMask, (rays & F_MIS) != 0u);
+    const uint32_t nc = (uint32_t)__popc(mc), ns = (uint32_t)__popc(ms), nm = (uint32_t)__popc(mm);
+    if (nc + ns + nm == 0u) return;
+    uint32_t base = 0u;
+    if (lane == 0u) base = atomicAdd(&a.q.ctl->tail[a.parity & 1u], nc + ns + nm);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (rays & F_CONT) a.q.entries[base + (uint32_t)__popc(mc & lt)] = slot;
+    if (rays & F_SHADOW) a.q.entries[base + nc + (uint32_t)__popc(ms & lt)] = slot | (1u << kKindShift);
+    if (rays & F_MIS) a.q.entries[base + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
 }
 
 // ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------

@@ -1,11 +1,12 @@
 // k_trace.cuh — persistent-threads BVH traversal kernel (replaces Intersect / IntersectP / the ray walks of
 // Tr, src/pathtracer.cu:214-322).
 //
-// * One thread = one ray; three ray classes per path slot (continuation closest-hit, shadow any-hit, MIS
-//   closest-hit) are laid out class-major so a warp holds one class only.
-// * Grid = a multiple of the SM count; every CTA first stages the acceleration structure (two-child 64-B
-//   nodes + 48-B primitive records) into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) when
-//   it fits, else traverses from L2/HBM with 16-B vector loads; then it grid-strides over the ray list.
+// * One lane = one ray.  Rays come from the compact ray queue that k_shade fills (continuation closest-hit,
+//   shadow any-hit / transmittance walk, MIS closest-hit); a persistent grid of SM-count x resident-CTA warps
+//   pulls them with warp-ballot refills, so idle lanes are re-armed instead of waiting for the slowest ray.
+// * Every CTA first stages the top of the breadth-first numbered acceleration structure (two-child 64-B nodes)
+//   and, for small scenes, the 48-B primitive records into shared memory with TMA bulk copies
+//   (cp.async.bulk + mbarrier); deeper nodes / primitives are read from L2/HBM with 16-B vector loads.
 // * Ordered traversal (near child first) with the reference's exact slab and Moeller-Trumbore arithmetic, so
 //   hit/miss decisions are bit-identical to the reference's unordered DFS; exact-t ties resolve to the higher
 //   primitive index, which is what the reference's visiting order produces (src/mesh.h:64 accepts tt == tmax).
@@ -72,26 +73,31 @@ __device__ __forceinline__ int prim_test(const float4 q0, const float4 q1, const
         f3 v0 = mk3(q0.x, q0.y, q0.z);
         f3 e1 = mk3(q0.w, q1.x, q1.y);
         f3 e2 = mk3(q1.z, q1.w, q2.x);
-        f3 s1 = cross(d, e2);
-        float divisor = dot(s1, e1);
+        f3 s1 = cross_pinned(d, e2);
+        float divisor = dot_pinned(s1, e1);
         if (fabsf(divisor) < 1e-8f) return 0;
         float invDivisor = 1.0f / divisor;       // == (float)(1.0 / (double)divisor): IEEE division, 53 >= 2*24+2
         f3 s = o - v0;
-        float b1 = dot(s, s1) * invDivisor;
+        float b1 = dot_pinned(s, s1) * invDivisor;
         if (b1 < 0.0f || b1 > 1.0f) return 0;
-        f3 s2 = cross(s, e1);
-        float b2 = dot(d, s2) * invDivisor;
+        f3 s2 = cross_pinned(s, e1);
+        float b2 = dot_pinned(d, s2) * invDivisor;
         if (b2 < 0.0f || b1 + b2 > 1.0f) return 0;
-        float tt = dot(e2, s2) * invDivisor;
+        float tt = dot_pinned(e2, s2) * invDivisor;
         if (tt < tmin || tt > tmax) return 0;
         t_out = tt; b1_out = b1; b2_out = b2;
         return 1;
     } else {                                     // sphere: q0 = centre.xyz, radius
         f3 op = o - mk3(q0.x, q0.y, q0.z);
         float radius = q0.w;
-        float B = dot(op, d);
+        float B = dot_pinned(op, d);
+#if defined(__CUDA_ARCH__)
+        // B*B - (dot(op,op) - r*r) as the reference build contracts it: fma(B, B, r*r - dot(op,op))
+        float delta = __fmaf_rn(B, B, __fsub_rn(__fmul_rn(radius, radius), dot_pinned(op, op)));
+#else
         float C = dot(op, op) - radius * radius;
         float delta = B * B - C;
+#endif
         if (delta < 0.f) return 0;
         float sqrDelta = sqrtf(delta);
         float t1 = -B - sqrDelta;
@@ -113,120 +119,40 @@ __device__ __forceinline__ int prim_test(const float4 q0, const float4 q1, const
     }
 }
 
-// Closest hit (ANY == false) or any hit (ANY == true) of one ray against the staged structure.
-template <bool ANY>
-__device__ __forceinline__ bool traverse(const SceneDev& sc, const WNode* __restrict__ nodes, const WPrim* __restrict__ prims,
-                                         f3 o, f3 d, float tmin, float tmax, Hit& hit) {
-    hit.t = -1.f; hit.prim = -1; hit.b1 = 0.f; hit.b2 = 0.f;
-    const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-    float tn;
-    // the reference tests the root's own box first (node 0, src/pathtracer.cu:222-223)
-    if (!slab(sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], o, inv, tmax, tn))
-        return false;
-    bool found = false;
-    int stack[64];
-    int sp = 0;
-    // `cur` >= 0: inner node to visit; `leaf` >= 0: first primitive of a leaf to test (run ends at the record
-    // flagged "last in leaf")
-    int cur = sc.root_leaf_count > 0 ? -1 : 0;
-    int leaf = sc.root_leaf_count > 0 ? 0 : -1;
-    for (;;) {
-        // ---- leaf: test its primitives (reference leaf loop, src/pathtracer.cu:230-245)
-        if (leaf >= 0) {
-            for (int pi = leaf;; ++pi) {
-                const float4* pp = reinterpret_cast<const float4*>(prims + pi);
-                const float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
-                float t, b1, b2;
-                const int acc = prim_test(q0, q1, q2, o, d, tmin, tmax, t, b1, b2);
-                if (acc) {
-                    if (ANY) return true;
-                    // tt == tmax is accepted by the reference; the later (higher index) primitive then wins
-                    if (acc == 2 || t < tmax || pi > hit.prim) { hit.t = t; hit.prim = pi; hit.b1 = b1; hit.b2 = b2; }
-                    tmax = t; found = true;
-                }
-                if (__float_as_int(q2.z) != 0) break;    // last primitive of this leaf
-            }
-            leaf = -1;
-        }
-        if (cur < 0) {
-            if (sp == 0) break;
-            const int e = stack[--sp];
-            if (e < 0) { leaf = ~e; continue; }
-            cur = e;
-        }
-        // ---- inner node: two slab tests from one 64-B record
-        const float4* np = reinterpret_cast<const float4*>(nodes + cur);
-        const float4 q0 = np[0], q1 = np[1], q2 = np[2];
-        const int4 link = reinterpret_cast<const int4*>(np)[3];
-        float tl = 0.f, tr = 0.f;
-        bool hl = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tl);
-        bool hr = link.y != kEmptyChild && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tmax, tr);
-        int c0 = link.x, c1 = link.y;
-        if (hl && hr) {
-            if (tr < tl) { int t_ = c0; c0 = c1; c1 = t_; }   // near child first, far child on the stack
-            stack[sp++] = c1;
-        } else if (hr) {
-            c0 = c1;
-        } else if (!hl) {
-            cur = -1;
-            continue;
-        }
-        if (c0 >= 0) cur = c0;
-        else { cur = -1; leaf = ~c0; }
-    }
-    return found;
-}
-
 struct TraceArgs {
     SceneDev sc;
     Pool pool;
+    RayQueue q;
     Counters* counters;
-    uint32_t stage_bytes_nodes, stage_bytes_prims;   // > 0: stage into shared memory with TMA
+    uint32_t parity;                                 // which QueueCtl set this step consumes
+    int32_t refill_below;                            // refill a warp when fewer lanes than this still carry a ray
+    uint32_t stage_bytes_nodes, stage_bytes_prims;   // > 0: bytes staged into shared memory with TMA
 };
 
-// Transmittance walk of Tr() (src/pathtracer.cu:298-322) for `vpt` shadow rays: closest hits until an opaque
-// surface (matIdx != -1) blocks the ray, multiplying exp(-sigmaT * segment) of the current homogeneous medium
-// and switching medium at every boundary crossed.
-__device__ __forceinline__ f3 transmittance_walk(const SceneDev& sc, const WNode* nodes, const WPrim* prims,
-                                                 f3 o, f3 d, float tmax_total, int medium, uint32_t& nrays) {
-    f3 tr = mk3(1, 1, 1);
-    float tmax = tmax_total;
-    float seg_max = tmax_total;
-    for (;;) {
-        Hit h;
-        ++nrays;
-        bool invisible = traverse<false>(sc, nodes, prims, o, d, sc.eps, seg_max, h);
-        float seg = invisible ? h.t : seg_max;
-        if (invisible && sc.shade[h.prim].matIdx != -1) return mk3(0, 0, 0);
-        if (medium >= 0) {
-            f3 sigmaT = ld3(sc.mediums[medium].sigmaT);
-            f3 c = sigmaT * (-seg);                                   // Homogeneous::Tr, src/medium.h:14
-            tr *= mk3(expf(c.x), expf(c.y), expf(c.z));
-        }
-        if (!invisible) break;
-        const WShade& s = sc.shade[h.prim];
-        f3 nor;
-        if (s.type == 0) nor = normalize(ld3(s.n1) * (1.f - h.b1 - h.b2) + ld3(s.n2) * h.b1 + ld3(s.n3) * h.b2);
-        else nor = normalize((o + seg * d) - ld3(s.n1));
-        medium = dot(d, nor) > 0 ? s.mediumOutside : s.mediumInside;
-        tmax -= seg;
-        o = o + seg * d;                                              // Ray(ray(ray.tmax), ray.d, m, eps, tmax)
-        seg_max = tmax;
-    }
-    return tr;
-}
+constexpr int kDone = (int)0x80000000;               // traversal cursor: nothing left to visit
+constexpr int kTraceThreads = 256;
 
+// One persistent warp = 32 independent rays in flight.  Lanes whose ray has finished are re-armed from the ray
+// queue as soon as fewer than `refill_below` lanes are busy (warp ballot + one aggregated atomic), so the
+// SIMT width stays full even though incoherent rays need very different numbers of node visits.  The traversal
+// is "while-while": descend inner nodes until a leaf is reached, then test that leaf's primitives; all lanes
+// reconverge after each (descend, leaf) round.
+//
+// Nodes are numbered breadth-first; the first `stage_bytes_nodes / 64` of them (the top of the tree, or the whole
+// tree for small scenes) and, when they fit, all primitive records are staged into shared memory by one TMA bulk
+// copy per CTA.  Everything else is read from L2/HBM with 16-byte vector loads.
 template <bool VOL>
-__global__ void __launch_bounds__(256) k_trace(const TraceArgs a) {
-    const WNode* nodes = a.sc.nodes;
-    const WPrim* prims = a.sc.prims;
+__global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
+    const WNode* __restrict__ gnodes = a.sc.nodes;
+    const WPrim* __restrict__ gprims = a.sc.prims;
+    int n_staged = 0;
+    bool prims_staged = false;
 #ifndef B200PT_EMULATE
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    const WNode* s_nodes = reinterpret_cast<const WNode*>(smem_raw);
+    const WPrim* s_prims = reinterpret_cast<const WPrim*>(smem_raw + a.stage_bytes_nodes);
     if (a.stage_bytes_nodes + a.stage_bytes_prims > 0) {
-        // stage the whole acceleration structure with one TMA bulk transaction per array
-        WNode* s_nodes = reinterpret_cast<WNode*>(smem_raw);
-        WPrim* s_prims = reinterpret_cast<WPrim*>(smem_raw + a.stage_bytes_nodes);
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,54 +160,181 @@ __global__ void __launch_bounds__(256) k_trace(const TraceArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, a.stage_bytes_nodes + a.stage_bytes_prims);
-            if (a.stage_bytes_nodes) tma_bulk_g2s(s_nodes, a.sc.nodes, a.stage_bytes_nodes, &bar);
-            tma_bulk_g2s(s_prims, a.sc.prims, a.stage_bytes_prims, &bar);
+            if (a.stage_bytes_nodes) tma_bulk_g2s(smem_raw, a.sc.nodes, a.stage_bytes_nodes, &bar);
+            if (a.stage_bytes_prims) tma_bulk_g2s(smem_raw + a.stage_bytes_nodes, a.sc.prims, a.stage_bytes_prims, &bar);
         }
         mbar_wait(&bar, 0);
-        nodes = s_nodes; prims = s_prims;
+        n_staged = (int)(a.stage_bytes_nodes / sizeof(WNode));
+        prims_staged = a.stage_bytes_prims > 0;
     }
 #endif
-    const uint32_t P = (uint32_t)a.pool.n;
-    const uint32_t total = 3u * P;
+    const uint32_t lane = pt_lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t par = a.parity & 1u;
+    const uint32_t tail = a.q.ctl->tail[par];
+    uint32_t* head = &a.q.ctl->head[par];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.q.ctl->tail[par ^ 1u] = 0u; a.q.ctl->head[par ^ 1u] = 0u; }
+
+    // per-lane ray state
+    bool active = false, exhausted = false, anyhit = false;
+    uint32_t entry = 0u;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
+    float tmax = 0.f, hb1 = 0.f, hb2 = 0.f;
+    int hprim = -1, cur = kDone, sp = 0;
+    int stack[64];
+    f3 tr = mk3(1, 1, 1);          // vpt shadow rays: transmittance so far, remaining length, current medium
+    float remain = 0.f;
+    int medium = -1;
     uint32_t nrays = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t kind = i / P;              // 0 continuation, 1 shadow, 2 MIS  (class-major: warps are homogeneous)
-        const uint32_t slot = i - kind * P;
-        const float4 df = a.pool.d_flags[slot];
-        const uint32_t flags = __float_as_uint(df.w);
-        const uint32_t need = kind == 0 ? F_CONT : (kind == 1 ? F_SHADOW : F_MIS);
-        if (!(flags & need)) continue;
-        const float4 orng = a.pool.o_rng[slot];
-        const f3 o = mk3(orng.x, orng.y, orng.z);
-        if (kind == 0) {
-            Hit h;
-            traverse<false>(a.sc, nodes, prims, o, mk3(df.x, df.y, df.z), a.sc.eps, INFINITY, h);
-            a.pool.hit0[slot] = make_float4(h.t, __int_as_float(h.prim), h.b1, h.b2);
-            ++nrays;
-        } else if (kind == 1) {
-            const float4 sd = a.pool.shd[slot];
-            f3 tr;
-            if (!VOL) {
-                Hit h;
-                bool occluded = traverse<true>(a.sc, nodes, prims, o, mk3(sd.x, sd.y, sd.z), a.sc.eps, sd.w, h);
-                tr = occluded ? mk3(0, 0, 0) : mk3(1, 1, 1);
+    const float eps = a.sc.eps;
+
+    for (;;) {
+        // ---- refill idle lanes from the queue
+        const uint32_t idle = __ballot_sync(kFullMask, !active);
+        if (idle != 0u && !exhausted) {
+            const uint32_t n = (uint32_t)__popc(idle);
+            uint32_t base = 0u;
+            if (lane == 0u) base = atomicAdd(head, n);
+            base = __shfl_sync(kFullMask, base, 0);
+            const uint32_t idx = base + (uint32_t)__popc(idle & lt);
+            if (!active && idx < tail) {
+                entry = a.q.entries[idx];
+                const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
+                const float4 orng = a.pool.o_rng[slot];
+                o = mk3(orng.x, orng.y, orng.z);
+                float4 dv;
+                if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
+                else if (kind == 1u) dv = a.pool.shd[slot];
+                else { dv = a.pool.misd[slot]; dv.w = INFINITY; }
+                d = mk3(dv.x, dv.y, dv.z);
+                tmax = dv.w;
+                anyhit = !VOL && kind == 1u;
+                if (VOL && kind == 1u) {
+                    const uint32_t flags = __float_as_uint(a.pool.d_flags[slot].w);
+                    medium = (int)((flags >> kMedium2Shift) & 0xffu) - 1;
+                    tr = mk3(1, 1, 1);
+                    remain = tmax;
+                }
+                inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+                hprim = -1; sp = 0;
+                float tn;
+                // the reference tests the root's own box first (node 0, src/pathtracer.cu:222-223)
+                const bool in = slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn);
+                cur = !in ? kDone : (a.sc.root_leaf_count > 0 ? ~0 : 0);
+                active = true;
                 ++nrays;
-            } else {
-                int medium = (int)((flags >> kMedium2Shift) & 0xffu) - 1;
-                tr = transmittance_walk(a.sc, nodes, prims, o, mk3(sd.x, sd.y, sd.z), sd.w, medium, nrays);
             }
-            a.pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
-        } else {
-            const float4 md = a.pool.misd[slot];
-            Hit h;
-            traverse<false>(a.sc, nodes, prims, o, mk3(md.x, md.y, md.z), a.sc.eps, INFINITY, h);
-            a.pool.hit1[slot] = make_float4(h.t, __int_as_float(h.prim), h.b1, h.b2);
-            ++nrays;
+            exhausted = base + n >= tail;
         }
+        uint32_t busy = __ballot_sync(kFullMask, active);
+        if (busy == 0u) break;
+
+        // ---- traversal rounds until too few lanes are busy (then refill) or, with the queue drained, all are done
+        do {
+            if (active) {
+                // descend: inner nodes, two slab tests per 64-B record, near child first
+                while (cur >= 0) {
+                    float4 q0, q1, q2; int2 link;
+#ifndef B200PT_EMULATE
+                    if (cur < n_staged) {
+                        const float4* np = reinterpret_cast<const float4*>(s_nodes + cur);
+                        q0 = np[0]; q1 = np[1]; q2 = np[2]; link = *reinterpret_cast<const int2*>(np + 3);
+                    } else
+#endif
+                    {
+                        const float4* np = reinterpret_cast<const float4*>(gnodes + cur);
+                        q0 = np[0]; q1 = np[1]; q2 = np[2]; link = *reinterpret_cast<const int2*>(np + 3);
+                    }
+                    float tl = 0.f, tr_ = 0.f;
+                    const bool hl = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tl);
+                    const bool hr = link.y != kEmptyChild && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tmax, tr_);
+                    int c0 = link.x, c1 = link.y;
+                    if (hl && hr) {
+                        if (tr_ < tl) { const int t_ = c0; c0 = c1; c1 = t_; }
+                        stack[sp++] = c1;
+                        cur = c0;
+                    } else if (hl) cur = c0;
+                    else if (hr) cur = c1;
+                    else cur = sp > 0 ? stack[--sp] : kDone;
+                }
+                // leaf: Moeller-Trumbore / sphere test on its primitive run (reference leaf loop, :230-245)
+                if (cur != kDone) {
+                    bool stop = false;
+                    for (int pi = ~cur;; ++pi) {
+                        float4 p0, p1, p2;
+#ifndef B200PT_EMULATE
+                        if (prims_staged) {
+                            const float4* pp = reinterpret_cast<const float4*>(s_prims + pi);
+                            p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+                        } else
+#endif
+                        {
+                            const float4* pp = reinterpret_cast<const float4*>(gprims + pi);
+                            p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+                        }
+                        float t, b1, b2;
+                        const int acc = prim_test(p0, p1, p2, o, d, eps, tmax, t, b1, b2);
+                        if (acc) {
+                            if (anyhit) { hprim = pi; stop = true; break; }
+                            // tt == tmax is accepted by the reference; the later (higher index) primitive then wins
+                            if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
+                            tmax = t;
+                        }
+                        if (__float_as_int(p2.z) != 0) break;      // last primitive of this leaf
+                    }
+                    cur = (stop || sp == 0) ? kDone : stack[--sp];
+                }
+                // ---- finished: write the result (or start the next segment of a transmittance walk)
+                if (cur == kDone) {
+                    const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
+                    active = false;
+                    if (kind != 1u) {
+                        const float4 h = make_float4(hprim >= 0 ? tmax : -1.f, __int_as_float(hprim), hb1, hb2);
+                        if (kind == 0u) a.pool.hit0[slot] = h; else a.pool.hit1[slot] = h;
+                    } else if (!VOL) {
+                        const float v = hprim >= 0 ? 0.f : 1.f;
+                        a.pool.vis[slot] = make_float4(v, v, v, 0.f);
+                    } else {
+                        // Tr() (src/pathtracer.cu:298-322): closest hits until an opaque surface blocks the ray,
+                        // exp(-sigmaT * segment) of the current homogeneous medium, medium switch at boundaries
+                        const bool invisible = hprim >= 0;
+                        const float seg = invisible ? tmax : remain;
+                        bool again = false;
+                        if (invisible && a.sc.shade[hprim].matIdx != -1) tr = mk3(0, 0, 0);
+                        else {
+                            if (medium >= 0) {
+                                const f3 c = ld3(a.sc.mediums[medium].sigmaT) * (-seg);        // Homogeneous::Tr, src/medium.h:14
+                                tr *= mk3(expf(c.x), expf(c.y), expf(c.z));
+                            }
+                            if (invisible) {
+                                const WShade& s = a.sc.shade[hprim];
+                                f3 nor;
+                                if (s.type == 0) nor = normalize(ld3(s.n1) * (1.f - hb1 - hb2) + ld3(s.n2) * hb1 + ld3(s.n3) * hb2);
+                                else nor = normalize((o + seg * d) - ld3(s.n1));
+                                medium = dot(d, nor) > 0 ? s.mediumOutside : s.mediumInside;
+                                remain -= seg;
+                                o = o + seg * d;                                               // Ray(ray(ray.tmax), ray.d, m, eps, tmax)
+                                tmax = remain;
+                                hprim = -1; sp = 0;
+                                float tn;
+                                const bool in = slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn);
+                                cur = !in ? kDone : (a.sc.root_leaf_count > 0 ? ~0 : 0);
+                                again = true; active = true;
+                                ++nrays;
+                            }
+                        }
+                        if (!again) a.pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
+                    }
+                }
+            }
+            busy = __ballot_sync(kFullMask, active);
+        } while (busy != 0u && (exhausted || __popc(busy) >= a.refill_below));
     }
     // ray statistics: one atomic per warp
-    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
-    if ((threadIdx.x & 31) == 0 && nrays) atomicAdd(&a.counters->rays, (unsigned long long)nrays);
+#ifndef B200PT_EMULATE
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
+#endif
+    if (lane == 0u && nrays) atomicAdd(&a.counters->rays, (unsigned long long)nrays);
 }
 
 }  // namespace pt

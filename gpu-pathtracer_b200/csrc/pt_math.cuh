@@ -51,6 +51,26 @@ PT_HD f2 operator*(f2 a, float b) { return mk2(a.x * b, a.y * b); }
 
 PT_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }                                   // cutil_math.h:1126
 PT_HD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }  // :1298
+// Hit/miss decisions must not depend on how the compiler happens to contract a*b+c in a given inlining context
+// (nvcc's choice of WHICH product of a dot/cross gets fused changes with the surrounding code).  These two spell
+// out the contraction the reference's own sm_100a build uses at every Triangle::Intersect site
+// (verified in its PTX/SASS: dot = fma(z, fma(x, mul(y))), cross component = fma(first product, -mul(second))),
+// with intrinsics that ptxas never re-fuses.  Host builds (oracle parity, no FMA) keep the plain expressions.
+PT_HD float dot_pinned(f3 a, f3 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+#else
+    return a.x * b.x + a.y * b.y + a.z * b.z;
+#endif
+}
+PT_HD f3 cross_pinned(f3 a, f3 b) {
+#if defined(__CUDA_ARCH__)
+    return mk3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+               __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+#else
+    return cross(a, b);
+#endif
+}
 PT_HD float rsqrt_ref(float x) {
 #if defined(__CUDA_ARCH__)
     return rsqrtf(x);          // device normalize uses the hardware rsqrt approximation (cutil_math.h:1189)

@@ -99,6 +99,25 @@ struct Pool {
     int32_t n;
 };
 
+// ---- ray queue ---------------------------------------------------------------------------------------------
+// k_shade appends one 4-byte entry per ray it emits (slot | kind << 30; kind 0 = continuation closest-hit,
+// 1 = shadow any-hit / transmittance walk, 2 = MIS closest-hit) with one warp-aggregated atomic per warp; the
+// persistent k_trace warps pull entries with one atomic per refill, so every lane of a traversal warp carries a
+// live ray.  Two control sets alternate by step parity: the trace kernel of step i consumes set i & 1 and zeroes
+// the other set for the shade kernel that follows it.
+constexpr int kKindShift = 30;
+constexpr uint32_t kSlotMask = (1u << kKindShift) - 1u;
+struct QueueCtl { uint32_t tail[2]; uint32_t head[2]; };
+struct RayQueue { uint32_t* entries; QueueCtl* ctl; };
+
+// ---- warp helpers (a "warp" is one lane wide in the CPU emulation build of the test suite) ------------------
+#ifndef B200PT_EMULATE
+__device__ __forceinline__ uint32_t pt_lane() { return threadIdx.x & 31u; }
+#else
+static inline uint32_t pt_lane() { return 0u; }
+#endif
+constexpr uint32_t kFullMask = 0xffffffffu;
+
 struct Counters {
     unsigned long long next_sample;    // next (iteration, pixel) pair to hand out
     unsigned long long done_samples;   // retired samples

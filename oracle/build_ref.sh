@@ -3,6 +3,7 @@
 #   oracle/_ref/libref_cuda.so       the reference CUDA integrator for sm_100a + headless C-ABI driver (GPU oracle of record)
 #   oracle/_ref/libref_host.so       the same kernel bodies compiled by g++ (no FMA contraction; pins oracle/pt_oracle.cpp)
 #   oracle/_ref/libref_host_fast.so  same, -O3 -march=x86-64-v3, for the CPU-baseline timing only
+#   oracle/_ref/libadapter.so        the product's reference-signature adapter compiled against the reference headers
 # Only binaries are written into the repo tree (oracle/_ref/ is git-ignored, but travels with gpurun).
 # The reference's own build system (CMake + Windows libs) is NOT used; see DESIGN.md.
 set -euo pipefail
@@ -57,4 +58,14 @@ g++ -O2 -ffp-contract=off $HOSTFLAGS -c "$HERE/refbuild/ref_host_harness.cpp" -o
 g++ -shared -fopenmp "$WORK/hh.o" "$WORK/bvh.o" -o "$OUT/libref_host.so" -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 g++ -O3 -march=x86-64-v3 $HOSTFLAGS -c "$HERE/refbuild/ref_host_harness.cpp" -o "$WORK/hhf.o"
 g++ -shared -fopenmp "$WORK/hhf.o" "$WORK/bvh.o" -o "$OUT/libref_host_fast.so" -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+
+# ---- drop-in adapter check: the product's BeginRender/Render/EndRender (gpu-pathtracer_b200/host/pathtracer_adapter.cpp)
+# compiled against the reference's own headers + a headless driver; links the product library libb200pt.so ----
+HOSTDIR="$HERE/../gpu-pathtracer_b200/host"; CSRC="$HERE/../gpu-pathtracer_b200/csrc"
+if [ -f "$CSRC/libb200pt.so" ]; then
+  g++ -O2 -w -fPIC -std=c++17 -I"$WORK/src" $INC -I/usr/local/cuda/include -c "$HOSTDIR/pathtracer_adapter.cpp" -o "$WORK/adapter.o"
+  g++ -O2 -w -fPIC -std=c++17 -I"$WORK/src" $INC -I/usr/local/cuda/include -c "$HOSTDIR/adapter_harness.cpp" -o "$WORK/adapter_h.o"
+  g++ -shared "$WORK/adapter.o" "$WORK/adapter_h.o" "$WORK/bvh.o" -o "$OUT/libadapter.so" -L"$CSRC" -lb200pt \
+      -Wl,-rpath,'$ORIGIN/../../gpu-pathtracer_b200/csrc' -L/usr/local/cuda/lib64 -lcudart
+fi
 ls -la "$OUT"

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--dump", default="")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to b200pt_set_option")
     a = ap.parse_args()
     t0 = time.time()
     s = make(a.scene, a.size)
@@ -54,6 +55,9 @@ def main():
         res["ref_ms"] = ms; res["ref_msamples_s"] = n / ms / 1e3
         print(f"reference CUDA: {ms:.2f} ms  -> {n / ms / 1e3:.1f} Msamples/s", flush=True)
     with pt.PathTracer(s, pool=a.pool or None) as r:
+        for kv in a.opt:
+            k, v = kv.split("=")
+            r.set_option(k, int(v))
         r.render(1, reset=True, spp=2)
         t0 = time.time()
         r.render(1, reset=True, spp=a.spp)

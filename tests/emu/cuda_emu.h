@@ -22,6 +22,7 @@
 
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 
 struct emu_idx { unsigned x, y, z; };
@@ -33,7 +34,12 @@ static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; 
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+// warp built-ins with a ONE-lane warp: every emulated thread is its own warp (lane 0)
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return (T)0; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void __syncthreads() {}
 
 typedef int cudaError_t;
