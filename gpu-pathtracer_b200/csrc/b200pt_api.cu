@@ -41,6 +41,9 @@ struct b200pt_ctx {
     size_t stage_top_bytes = 32 * 1024;    // top-of-tree nodes staged per CTA when the scene does not fit
     RayQueue q{};
     int refill_below = 24;
+    bool lambert_only = false;             // every material is lambertian -> specialised shade kernel
+    float4* leaves = nullptr; int n_leaves = 0;   // flat leaf list (scenes with <= 64 leaves)
+    bool small_scene = false;              // use k_trace_small
     size_t max_batch_bytes = (size_t)2 << 30;
     int steps_per_poll = 8;
     double stats[5] = {0, 0, 0, 0, 0};
@@ -190,6 +193,26 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         w.link.y = R.is_leaf ? ~R.start : inner_id[r];
         w.link.z = 0; w.link.w = 0;
     }
+    // flat leaf list for k_trace_small: leaf box + primitive run, in leaf (= primitive) order
+    {
+        std::vector<float4> wl;
+        for (int i = 0; i < v->n_nodes; ++i) {
+            const RefLinearBVHNode& n = nodes[i];
+            if (!n.is_leaf || (i != 0 && inner_id[0] < 0)) continue;
+            float4 a = make_float4(n.fmin[0], n.fmin[1], n.fmin[2], n.fmax[0]);
+            int first = n.start, count = n.end - n.start + 1;
+            float ff, cf; std::memcpy(&ff, &first, 4); std::memcpy(&cf, &count, 4);
+            wl.push_back(a); wl.push_back(make_float4(n.fmax[1], n.fmax[2], ff, cf));
+        }
+        std::sort(reinterpret_cast<std::pair<float4, float4>*>(wl.data()), reinterpret_cast<std::pair<float4, float4>*>(wl.data()) + wl.size() / 2,
+                  [](const std::pair<float4, float4>& x, const std::pair<float4, float4>& y) {
+                      int fx, fy; std::memcpy(&fx, &x.second.z, 4); std::memcpy(&fy, &y.second.z, 4); return fx < fy; });
+        c->n_leaves = (int)(wl.size() / 2);
+        if (c->n_leaves > 0 && c->n_leaves <= 64) {
+            int rc2 = dev_upload(c, &c->leaves, wl.data(), wl.size());
+            if (rc2) return rc2;
+        }
+    }
     SceneDev& sc = c->sc;
     std::memcpy(sc.root_min, nodes[0].fmin, 12); std::memcpy(sc.root_max, nodes[0].fmax, 12);
     sc.root_leaf_count = nodes[0].is_leaf ? (nodes[0].end - nodes[0].start + 1) : 0;
@@ -221,6 +244,12 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     Material* d_mats;
     if ((rc = dev_upload(c, &d_mats, (const Material*)v->materials, (size_t)v->n_materials))) return rc;
     sc.mats = d_mats; sc.n_mats = v->n_materials;
+    // material set actually referenced by primitives (scene files often define materials they do not use)
+    c->lambert_only = true;
+    for (int i = 0; i < v->n_prims; ++i) {
+        const int m = ws[i].matIdx;
+        if (m >= 0 && mats[m].type != MT_LAMBERTIAN) { c->lambert_only = false; break; }
+    }
     std::vector<WMedium> wm(std::max(v->n_mediums, 1));
     std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
     const RefMedium* med = (const RefMedium*)v->mediums;
@@ -264,7 +293,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
     // (TMA bulk copy): everything when the scene is small, else the top of the breadth-first node array
     size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
-    if (nb + pb <= 40 * 1024) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; }
+    if (nb + pb <= 40 * 1024) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; c->small_scene = c->leaves != nullptr; }
     else { c->stage_nodes = (uint32_t)std::min<size_t>(nb, c->stage_top_bytes); c->stage_prims = 0; }
     CK(cudaStreamSynchronize(c->stream));     // host staging vectors go out of scope
     return 0;
@@ -353,8 +382,31 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "steps_per_poll") { if (value < 1 || value > 1024) return fail(B200PT_EINVAL, "steps_per_poll out of range"); c->steps_per_poll = (int)value; return 0; }
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
-    if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; } return 0; }
+    if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr && c->stage_prims > 0; return 0; }
+    if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; } return 0; }
     return fail(B200PT_EINVAL, "unknown option " + n);
+}
+
+static void launch_shade(b200pt_ctx* c, const ShadeArgs& sa) {
+    const int blocks = c->pool.n / 128;
+    if (c->vol) {
+        if (c->lambert_only) PT_LAUNCH((k_shade<true, kMatsLambertOnly>), blocks, 128, 0, c->stream, sa);
+        else PT_LAUNCH((k_shade<true, kMatsAll>), blocks, 128, 0, c->stream, sa);
+    } else {
+        if (c->lambert_only) PT_LAUNCH((k_shade<false, kMatsLambertOnly>), blocks, 128, 0, c->stream, sa);
+        else PT_LAUNCH((k_shade<false, kMatsAll>), blocks, 128, 0, c->stream, sa);
+    }
+}
+static void launch_trace(b200pt_ctx* c, const TraceArgs& ta) {
+    if (c->small_scene) {
+        const size_t smem = (size_t)c->stage_prims + (size_t)c->n_leaves * 32;
+        if (c->vol) PT_LAUNCH(k_trace_small<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
+        else PT_LAUNCH(k_trace_small<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
+        return;
+    }
+    const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+    if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
+    else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
 }
 
 // One batch = n_iters iterations of every local pixel through the wavefront, then the ordered resolve.
@@ -375,13 +427,11 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
     CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 2, c->stream));   // next_sample, done_samples (rays keeps counting)
     CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
     ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
-    TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
-    const int shade_blocks = (c->pool.n + 127) / 128;
-    const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+    TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
     // step i: shade emits its rays into queue set (i & 1); trace consumes that set and clears the other one
     uint32_t step = 0;
-    auto shade = [&]() { sa.parity = step & 1u; if (c->vol) PT_LAUNCH(k_shade<true>, shade_blocks, 128, 0, c->stream, sa); else PT_LAUNCH(k_shade<false>, shade_blocks, 128, 0, c->stream, sa); };
-    auto trace = [&]() { ta.parity = step & 1u; if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); ++step; };
+    auto shade = [&]() { sa.parity = step & 1u; launch_shade(c, sa); };
+    auto trace = [&]() { ta.parity = step & 1u; launch_trace(c, ta); ++step; };
     // all slots start dead: the first shade pass only regenerates
     CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)c->pool.n, c->stream));
     shade(); *launches += 1;
@@ -490,7 +540,7 @@ extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t 
     std::vector<float4> hits(npix);
     const uint32_t P = (uint32_t)c->pool.n;
     if (c->samples_cap < npix) { int rc = dev_alloc(c, &c->samples, (size_t)npix); if (rc) return rc; c->samples_cap = npix; }
-    std::vector<float4> tmp(P), bs(P);
+    std::vector<float4> tmp(P), bs(P), fl(P);
     for (uint32_t base = 0; base < npix; base += P) {
         // hand out exactly the samples [base, base + P) of this iteration
         uint32_t cnt = std::min(P, npix - base);
@@ -500,16 +550,16 @@ extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t 
         CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)P, c->stream));
         CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
         ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
-        TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims;
-        const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
-        if (c->vol) { PT_LAUNCH(k_shade<true>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); }
-        else { PT_LAUNCH(k_shade<false>, (P + 127) / 128, 128, 0, c->stream, sa); PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta); }
+        TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
+        launch_shade(c, sa);
+        launch_trace(c, ta);
         CK(cudaMemcpyAsync(tmp.data(), c->pool.hit0, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(bs.data(), c->pool.beta_s, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(fl.data(), c->pool.d_flags, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (uint32_t s = 0; s < P; ++s) {
-            uint32_t sample; std::memcpy(&sample, &bs[s].w, 4);
-            if (sample >= base && sample < base + cnt) hits[sample] = tmp[s];
+            uint32_t sample, flags; std::memcpy(&sample, &bs[s].w, 4); std::memcpy(&flags, &fl[s].w, 4);
+            if ((flags & F_ALIVE) && sample >= base && sample < base + cnt) hits[sample] = tmp[s];
         }
     }
     CK(cudaGetLastError());

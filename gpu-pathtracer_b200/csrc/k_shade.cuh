@@ -135,64 +135,100 @@ __device__ __forceinline__ void inf_sample(const WInfinite& I, float ux, float u
 
 __device__ __forceinline__ f3 exp3(f3 c) { return mk3(expf(c.x), expf(c.y), expf(c.z)); }
 
-// One path slot, one step.  Returns the rays the slot wants traced next (F_CONT | F_SHADOW | F_MIS bits).
-template <bool VOL>
-__device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_t slot) {
-    const SceneDev& sc = a.sc;
+// Pool accesses are streaming (each record is read and written once per step).  Reads: the whole CTA tile of every
+// pool array comes in through TMA bulk copies into shared memory, so ONE asynchronous round trip covers the record
+// (per-thread loads were sunk by the compiler behind each dependent branch: ~6 serial DRAM round trips) and L1 is
+// left to the scene records (WShade / Material / WLight / CDF).  Writes bypass L1 allocation.
+#ifndef B200PT_EMULATE
+__device__ __forceinline__ void st_pool(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#else
+static inline void st_pool(float4* p, float4 v) { *p = v; }
+#endif
 
-    float4 df = a.pool.d_flags[slot];
+// Material specialisation: a scene whose materials are all lambertian gets a kernel without the GGX / dielectric
+// code (a quarter of the instructions and registers of the general one); MATS is the set of MaterialTypes present.
+constexpr uint32_t kMatsLambertOnly = 1u << MT_LAMBERTIAN;
+constexpr uint32_t kMatsAll = 0xffffffffu;
+
+template <bool VOL, uint32_t MATS>
+__global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;      // the pool size is a multiple of the block size
+    const SceneDev& sc = a.sc;
+    const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
+
+    // ---------------------------------------------------------------- loads: the CTA's 128 pool records, all arrays,
+    // staged into shared memory by TMA bulk copies (one elected thread issues them, everyone waits on the mbarrier)
+    constexpr int kArrays = VOL ? 12 : 11;
+#ifndef B200PT_EMULATE
+    __shared__ __align__(128) float4 s_rec[kArrays][128];
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const float4* src[12] = {a.pool.d_flags, a.pool.o_rng, a.pool.beta_s, a.pool.li_t, a.pool.hit0, a.pool.beta_old,
+                                 a.pool.vis, a.pool.ldl, a.pool.misd, a.pool.misf, a.pool.hit1, a.pool.aux};
+        mbar_expect_tx(&bar, (uint32_t)(kArrays * 128 * sizeof(float4)));
+#pragma unroll
+        for (int k = 0; k < kArrays; ++k) tma_bulk_g2s(&s_rec[k][0], src[k] + (size_t)blockIdx.x * 128, 128 * sizeof(float4), &bar);
+    }
+    __syncthreads();                       // the barrier object is initialised before anyone polls it
+    mbar_wait(&bar, 0);
+    const float4 df = s_rec[0][threadIdx.x], orng = s_rec[1][threadIdx.x], bs = s_rec[2][threadIdx.x], lt4 = s_rec[3][threadIdx.x];
+    const float4 h0 = s_rec[4][threadIdx.x], bo = s_rec[5][threadIdx.x], pv = s_rec[6][threadIdx.x], pl = s_rec[7][threadIdx.x];
+    const float4 pmd = s_rec[8][threadIdx.x], pmf = s_rec[9][threadIdx.x], h1 = s_rec[10][threadIdx.x];
+    const float4 pax = VOL ? s_rec[kArrays - 1][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+    const float4 df = a.pool.d_flags[slot], orng = a.pool.o_rng[slot], bs = a.pool.beta_s[slot], lt4 = a.pool.li_t[slot];
+    const float4 h0 = a.pool.hit0[slot], bo = a.pool.beta_old[slot], pv = a.pool.vis[slot], pl = a.pool.ldl[slot];
+    const float4 pmd = a.pool.misd[slot], pmf = a.pool.misf[slot], h1 = a.pool.hit1[slot];
+    const float4 pax = VOL ? a.pool.aux[slot] : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+    const unsigned long long next_snapshot = a.counters->next_sample;
+
     uint32_t flags = __float_as_uint(df.w);
-    float4 orng = a.pool.o_rng[slot];
     uint32_t rng = __float_as_uint(orng.w);
     f3 o = mk3(orng.x, orng.y, orng.z);
     f3 d = mk3(df.x, df.y, df.z);
-    f3 beta, Li;
-    uint32_t sample;
-    bool alive = (flags & F_ALIVE) != 0;
-    bool finished = false;
-    if (alive) {
-        float4 bs = a.pool.beta_s[slot];
-        float4 lt = a.pool.li_t[slot];
-        beta = mk3(bs.x, bs.y, bs.z); sample = __float_as_uint(bs.w);
-        Li = mk3(lt.x, lt.y, lt.z);
-    } else {
-        if (a.counters->next_sample >= a.batch.total) return 0u; // nothing left to regenerate: stay dead
-        beta = mk3(1, 1, 1); Li = mk3(0, 0, 0); sample = 0;
-        finished = true;                                         // take the regeneration path below
-    }
+    const bool alive = (flags & F_ALIVE) != 0;
+    f3 beta = alive ? mk3(bs.x, bs.y, bs.z) : mk3(1, 1, 1);
+    f3 Li = alive ? mk3(lt4.x, lt4.y, lt4.z) : mk3(0, 0, 0);
+    uint32_t sample = alive ? __float_as_uint(bs.w) : 0u;
+    // a dead slot regenerates while samples are left (snapshot of the counter: exact enough, see below)
+    bool finished = !alive && next_snapshot < a.batch.total;
+    const bool idle_dead = !alive && !finished;
     int bounces = (int)((flags >> kBounceShift) & 0xffu);
     int medium = (int)((flags >> kMediumShift) & 0xffu) - 1;      // medium of the continuation ray (vpt)
 
     // ---------------------------------------------------------------- A. pending direct light of the previous bounce
     if (alive && (flags & F_PENDING)) {
-        const float4 bo = a.pool.beta_old[slot];
         const f3 beta_old = mk3(bo.x, bo.y, bo.z);
         const int medium2 = (int)((flags >> kMedium2Shift) & 0xffu) - 1;
         if (VOL && (flags & F_MEDSCATTER)) {
             // Li += tr*beta*phase*radiance / (lightPdf*choicePdf)   (src/pathtracer.cu:1092-1093)
             if (flags & F_SHADOW) {
-                const float4 v = a.pool.vis[slot]; const float4 l = a.pool.ldl[slot]; const float4 mf = a.pool.misf[slot];
+                const float4 v = pv; const float4 l = pl; const float4 mf = pmf;
                 f3 tr = mk3(v.x, v.y, v.z), radiance = mk3(l.x, l.y, l.z);
                 Li += tr * beta_old * mf.x * radiance / mf.y;
             }
         } else {
             f3 Ld = mk3(0.f, 0.f, 0.f);
             if (flags & F_SHADOW) {
-                const float4 v = a.pool.vis[slot]; const float4 l = a.pool.ldl[slot];
+                const float4 v = pv; const float4 l = pl;
                 if (!VOL) {
                     if (v.x != 0.f) Ld += mk3(l.x, l.y, l.z);                                   // :942-951
                 } else {
                     // Ld += weight*tr*fr*radiance*|cos| / (lightPdf*choicePdf)                  // :1153-1154
-                    const float4 ax = a.pool.aux[slot];   // radiance xyz, weight
-                    const float4 mf = a.pool.misf[slot];
+                    const float4 ax = pax;                 // radiance xyz, weight
+                    const float4 mf = pmf;
                     f3 tr = mk3(v.x, v.y, v.z), fr = mk3(l.x, l.y, l.z), radiance = mk3(ax.x, ax.y, ax.z);
                     Ld += ax.w * tr * fr * radiance * bo.w / mf.w;
                 }
             }
             if (flags & F_MIS) {
-                const float4 md = a.pool.misd[slot]; const float4 mf = a.pool.misf[slot];
-                const float4 h1 = a.pool.hit1[slot];
-                const float absdot = a.pool.ldl[slot].w;
+                const float4 md = pmd; const float4 mf = pmf;
+                const float absdot = pl.w;
                 const f3 out = mk3(md.x, md.y, md.z), fr = mk3(mf.x, mf.y, mf.z);
                 const float pdf = md.w;
                 if (h1.x >= 0.f) {
@@ -241,7 +277,6 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
     f3 new_o = o, new_d = d;
     bool specular = (flags & F_SPECULAR) != 0;
     if (alive && !finished) {
-        const float4 h0 = a.pool.hit0[slot];
         if (h0.x < 0.f) {                                                                       // miss, :905-909
             if ((bounces == 0 || specular) && sc.inf.isvalid) Li += beta * inf_le(sc.inf, d);
             finished = true;
@@ -282,12 +317,12 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
                         phase = kInvFourPi * (1.f - M.g * M.g) / sqrtf(cubicTerm * cubicTerm * cubicTerm);
                     }
                     nf |= F_PENDING | F_MEDSCATTER;
-                    a.pool.beta_old[slot] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                    st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, 0.f));
                     if (!is_black(ls.radiance)) {                                               // Tr() is side-effect free otherwise
                         nf |= F_SHADOW;
-                        a.pool.shd[slot] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax);
-                        a.pool.ldl[slot] = make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f);
-                        a.pool.misf[slot] = make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f);
+                        st_pool(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
+                        st_pool(a.pool.ldl + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f));
+                        st_pool(a.pool.misf + slot, make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f));
                     }
                     float pa = rng_next(rng), pb = rng_next(rng);                               // Medium::SamplePhase, src/medium.h:197
                     f3 dir;
@@ -336,7 +371,8 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
                     nf |= F_CONT | ((uint32_t)(m + 1) << kMediumShift);
                     // bounces unchanged, no Russian roulette (the reference `continue`s)
                 } else {
-                    const Material mat = sc.mats[h.matIdx];
+                    Material mat = sc.mats[h.matIdx];
+                    if (MATS == kMatsLambertOnly) mat.type = MT_LAMBERTIAN;    // scene-level fact: drops the other BSDFs
                     const f3 albedo = ld3(mat.diffuse);                                         // GetTexel, textureIdx == -1
                     const f3 wo = -d;
                     if (!is_delta(mat.type)) {                                                  // :925-995
@@ -349,7 +385,7 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
                         if (idx != sc.n_lights) area_sample(sc.lights[idx], h.pos, ua, ub, sc.eps, ls);
                         else inf_sample(sc.inf, ua, ub, sc.eps, ls);
                         nf |= F_PENDING;
-                        a.pool.beta_old[slot] = make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir)));
+                        st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
                         float mis_absdot = 0.f;
                         f3 ldl = mk3(0, 0, 0);
                         if (!is_black(ls.radiance)) {
@@ -357,11 +393,11 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
                             eval_bsdf(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
                             float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
                             nf |= F_SHADOW;
-                            a.pool.shd[slot] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax);
+                            st_pool(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
                             if (!VOL) ldl = weight * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
                             else {
                                 ldl = fr;
-                                a.pool.aux[slot] = make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight);
+                                st_pool(a.pool.aux + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight));
                             }
                         }
                         float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
@@ -371,12 +407,12 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
                         if (!(is_black(fr) || pdf == 0)) {
                             nf |= F_MIS;
                             mis_absdot = fabsf(dot(out, h.nor));
-                            a.pool.misd[slot] = make_float4(out.x, out.y, out.z, pdf);
-                            a.pool.misf[slot] = make_float4(fr.x, fr.y, fr.z, denom);
+                            st_pool(a.pool.misd + slot, make_float4(out.x, out.y, out.z, pdf));
+                            st_pool(a.pool.misf + slot, make_float4(fr.x, fr.y, fr.z, denom));
                         } else if (VOL) {
-                            a.pool.misf[slot] = make_float4(0.f, 0.f, 0.f, denom);
+                            st_pool(a.pool.misf + slot, make_float4(0.f, 0.f, 0.f, denom));
                         }
-                        a.pool.ldl[slot] = make_float4(ldl.x, ldl.y, ldl.z, mis_absdot);
+                        st_pool(a.pool.ldl + slot, make_float4(ldl.x, ldl.y, ldl.z, mis_absdot));
                         nf |= ((uint32_t)(medium + 1) << kMedium2Shift);
                     }
                     float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :997-1003
@@ -412,16 +448,42 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
         }
     }
 
+
     // ---------------------------------------------------------------- C. retire + regenerate
+    // One aggregated atomic per warp hands out the next samples; the ray-queue reservation is issued right behind
+    // it (a regenerated slot always emits exactly one continuation ray), so both round trips overlap.
+    if (finished && alive) {
+        st_pool(a.samples + sample, make_float4(Li.x, Li.y, Li.z, 1.f));
+    }
+    const uint32_t m_fin = __ballot_sync(kFullMask, finished);
+    const uint32_t m_ret = __ballot_sync(kFullMask, finished && alive);
+    uint32_t rays = finished ? F_CONT : (idle_dead ? 0u : (nf & (F_CONT | F_SHADOW | F_MIS)));
+    const uint32_t mc = __ballot_sync(kFullMask, (rays & F_CONT) != 0u);
+    const uint32_t ms = __ballot_sync(kFullMask, (rays & F_SHADOW) != 0u);
+    const uint32_t mm = __ballot_sync(kFullMask, (rays & F_MIS) != 0u);
+    const uint32_t nc = (uint32_t)__popc(mc), ns = (uint32_t)__popc(ms), nm = (uint32_t)__popc(mm);
+    unsigned long long sbase = 0ull;
+    uint32_t qbase = 0u;
+    if (lane == 0u) {
+        if (m_fin) sbase = atomicAdd(&a.counters->next_sample, (unsigned long long)__popc(m_fin));
+        if (nc + ns + nm) qbase = atomicAdd(&a.q.ctl->tail[a.parity & 1u], nc + ns + nm);
+        if (m_ret) atomicAdd(&a.counters->done_samples, (unsigned long long)__popc(m_ret));
+    }
+    sbase = __shfl_sync(kFullMask, sbase, 0);
+    qbase = __shfl_sync(kFullMask, qbase, 0);
+    if (rays & F_CONT) a.q.entries[qbase + (uint32_t)__popc(mc & lt)] = slot;
+    if (rays & F_SHADOW) a.q.entries[qbase + nc + (uint32_t)__popc(ms & lt)] = slot | (1u << kKindShift);
+    if (rays & F_MIS) a.q.entries[qbase + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
+    if (idle_dead) return;
+
     if (finished) {
-        if (alive) {
-            a.samples[sample] = make_float4(Li.x, Li.y, Li.z, 1.f);
-            atomicAdd(&a.counters->done_samples, 1ull);
-        }
-        const unsigned long long s = atomicAdd(&a.counters->next_sample, 1ull);
+        const unsigned long long s = sbase + (unsigned long long)__popc(m_fin & lt);
         if (s >= a.batch.total) {
-            a.pool.d_flags[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));            // dead
-            return 0u;
+            // the batch ran out between the snapshot and the atomic: the slot dies; its queue entry stays and
+            // traces one harmless ray (this happens in at most one step per batch)
+            st_pool(a.pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
+            st_pool(a.pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
+            return;
         }
         sample = (uint32_t)s;
         const uint32_t npix = (uint32_t)a.map.n_local_pixels;
@@ -443,31 +505,10 @@ __device__ __forceinline__ uint32_t shade_slot(const ShadeArgs& a, const uint32_
     }
     if (specular) nf |= F_SPECULAR;
     nf |= ((uint32_t)bounces & 0xffu) << kBounceShift;
-    a.pool.o_rng[slot] = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng));
-    a.pool.d_flags[slot] = make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf));
-    a.pool.beta_s[slot] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample));
-    a.pool.li_t[slot] = make_float4(Li.x, Li.y, Li.z, 0.f);
-    return nf & (F_CONT | F_SHADOW | F_MIS);
-}
-
-template <bool VOL>
-__global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t rays = 0u;
-    if (slot < (uint32_t)a.pool.n) rays = shade_slot<VOL>(a, slot);
-    // append this warp's rays to the queue, class by class, with ONE atomic per warp
-    const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
-    const uint32_t mc = __ballot_sync(kFullMask, (rays & F_CONT) != 0u);
-    const uint32_t ms = __ballot_sync(kFullMask, (rays & F_SHADOW) != 0u);
-    const uint32_t mm = __ballot_sync(kFullMask, (rays & F_MIS) != 0u);
-    const uint32_t nc = (uint32_t)__popc(mc), ns = (uint32_t)__popc(ms), nm = (uint32_t)__popc(mm);
-    if (nc + ns + nm == 0u) return;
-    uint32_t base = 0u;
-    if (lane == 0u) base = atomicAdd(&a.q.ctl->tail[a.parity & 1u], nc + ns + nm);
-    base = __shfl_sync(kFullMask, base, 0);
-    if (rays & F_CONT) a.q.entries[base + (uint32_t)__popc(mc & lt)] = slot;
-    if (rays & F_SHADOW) a.q.entries[base + nc + (uint32_t)__popc(ms & lt)] = slot | (1u << kKindShift);
-    if (rays & F_MIS) a.q.entries[base + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
+    st_pool(a.pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
+    st_pool(a.pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
+    st_pool(a.pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));
+    st_pool(a.pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
 }
 
 // ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------

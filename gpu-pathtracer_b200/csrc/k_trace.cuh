@@ -15,32 +15,6 @@
 
 namespace pt {
 
-#ifndef B200PT_EMULATE
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-#endif  // !B200PT_EMULATE
 
 // ---- the reference's slab test, BBox::Intersect (src/bbox.h:77-96), on one child box ---------------------
 // inv = 1/d is hoisted out of the node loop (the reference recomputes the same value per node).
@@ -127,9 +101,12 @@ struct TraceArgs {
     uint32_t parity;                                 // which QueueCtl set this step consumes
     int32_t refill_below;                            // refill a warp when fewer lanes than this still carry a ray
     uint32_t stage_bytes_nodes, stage_bytes_prims;   // > 0: bytes staged into shared memory with TMA
+    const float4* leaves;                            // small scenes: WLeaf records (leaf box + primitive run)
+    int32_t n_leaves;
 };
 
-constexpr int kDone = (int)0x80000000;               // traversal cursor: nothing left to visit
+constexpr int kDone = (int)0x80000000;               // traversal cursor: nothing left to visit (also "no postponed leaf")
+constexpr int kPop = (int)0x80000001;                // traversal cursor: take the next entry from the stack
 constexpr int kTraceThreads = 256;
 
 // One persistent warp = 32 independent rays in flight.  Lanes whose ray has finished are re-armed from the ray
@@ -180,8 +157,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
     uint32_t entry = 0u;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
     float tmax = 0.f, hb1 = 0.f, hb2 = 0.f;
-    int hprim = -1, cur = kDone, sp = 0;
+    int hprim = -1, cur = kDone, leaf = kDone, sp = 0;
     int stack[64];
+    float stack_t[64];                                   // entry distance of every stacked subtree (cull on pop)
     f3 tr = mk3(1, 1, 1);          // vpt shadow rays: transmittance so far, remaining length, current medium
     float remain = 0.f;
     int medium = -1;
@@ -216,7 +194,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                     remain = tmax;
                 }
                 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-                hprim = -1; sp = 0;
+                hprim = -1; sp = 0; leaf = kDone;
                 float tn;
                 // the reference tests the root's own box first (node 0, src/pathtracer.cu:222-223)
                 const bool in = slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn);
@@ -232,57 +210,79 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
         // ---- traversal rounds until too few lanes are busy (then refill) or, with the queue drained, all are done
         do {
             if (active) {
-                // descend: inner nodes, two slab tests per 64-B record, near child first
-                while (cur >= 0) {
-                    float4 q0, q1, q2; int2 link;
+                // descend: inner nodes, two slab tests per 64-B record, near child first.  The first leaf a lane
+                // reaches is POSTPONED and the lane keeps descending speculatively while any other lane of the warp
+                // is still looking for its leaf, so the (expensive) primitive tests start with most lanes on board.
+                for (;;) {
+                    if (cur >= 0) {
+                        float4 q0, q1, q2; int2 link;
 #ifndef B200PT_EMULATE
-                    if (cur < n_staged) {
-                        const float4* np = reinterpret_cast<const float4*>(s_nodes + cur);
-                        q0 = np[0]; q1 = np[1]; q2 = np[2]; link = *reinterpret_cast<const int2*>(np + 3);
-                    } else
-#endif
-                    {
-                        const float4* np = reinterpret_cast<const float4*>(gnodes + cur);
-                        q0 = np[0]; q1 = np[1]; q2 = np[2]; link = *reinterpret_cast<const int2*>(np + 3);
-                    }
-                    float tl = 0.f, tr_ = 0.f;
-                    const bool hl = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tl);
-                    const bool hr = link.y != kEmptyChild && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tmax, tr_);
-                    int c0 = link.x, c1 = link.y;
-                    if (hl && hr) {
-                        if (tr_ < tl) { const int t_ = c0; c0 = c1; c1 = t_; }
-                        stack[sp++] = c1;
-                        cur = c0;
-                    } else if (hl) cur = c0;
-                    else if (hr) cur = c1;
-                    else cur = sp > 0 ? stack[--sp] : kDone;
-                }
-                // leaf: Moeller-Trumbore / sphere test on its primitive run (reference leaf loop, :230-245)
-                if (cur != kDone) {
-                    bool stop = false;
-                    for (int pi = ~cur;; ++pi) {
-                        float4 p0, p1, p2;
-#ifndef B200PT_EMULATE
-                        if (prims_staged) {
-                            const float4* pp = reinterpret_cast<const float4*>(s_prims + pi);
-                            p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+                        if (cur < n_staged) {
+                            const float4* np = reinterpret_cast<const float4*>(s_nodes + cur);
+                            q0 = np[0]; q1 = np[1]; q2 = np[2]; link = *reinterpret_cast<const int2*>(np + 3);
                         } else
 #endif
                         {
-                            const float4* pp = reinterpret_cast<const float4*>(gprims + pi);
-                            p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+                            const float4* np = reinterpret_cast<const float4*>(gnodes + cur);
+                            q0 = np[0]; q1 = np[1]; q2 = np[2]; link = *reinterpret_cast<const int2*>(np + 3);
                         }
-                        float t, b1, b2;
-                        const int acc = prim_test(p0, p1, p2, o, d, eps, tmax, t, b1, b2);
-                        if (acc) {
-                            if (anyhit) { hprim = pi; stop = true; break; }
-                            // tt == tmax is accepted by the reference; the later (higher index) primitive then wins
-                            if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
-                            tmax = t;
-                        }
-                        if (__float_as_int(p2.z) != 0) break;      // last primitive of this leaf
+                        float tl = 0.f, tr_ = 0.f;
+                        const bool hl = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tl);
+                        const bool hr = link.y != kEmptyChild && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, tmax, tr_);
+                        int c0 = link.x, c1 = link.y;
+                        if (hl && hr) {
+                            if (tr_ < tl) { const int t_ = c0; c0 = c1; c1 = t_; const float f_ = tl; tl = tr_; tr_ = f_; }
+                            stack[sp] = c1; stack_t[sp] = tr_; ++sp;
+                            cur = c0;
+                        } else if (hl) cur = c0;
+                        else if (hr) cur = c1;
+                        else cur = kPop;
+                    } else if (cur == kPop) {
+                        // one pop per iteration; subtrees whose entry distance is already behind the closest hit are
+                        // dropped (the same `tmin > ray.tmax` rejection BBox::Intersect would make on visiting them,
+                        // src/bbox.h:93)
+                        if (sp > 0) { --sp; cur = (stack_t[sp] > tmax) ? kPop : stack[sp]; }
+                        else cur = kDone;
                     }
-                    cur = (stop || sp == 0) ? kDone : stack[--sp];
+                    if (cur < 0 && cur > kPop && leaf == kDone) { leaf = cur; cur = kPop; }   // postpone the first leaf
+                    if (cur < 0 && cur != kPop) break;                                // second leaf, or nothing left
+#ifndef B200PT_EMULATE
+                    if (!__any_sync(__activemask(), leaf == kDone)) break;            // every lane has its leaf
+#else
+                    if (leaf != kDone) break;
+#endif
+                }
+                // leaves: Moeller-Trumbore / sphere test, one primitive per iteration (reference leaf loop, :230-245);
+                // a lane that found a second leaf while speculating continues straight into it
+                int pi = ~leaf;
+                while (leaf != kDone) {
+                    float4 p0, p1, p2;
+#ifndef B200PT_EMULATE
+                    if (prims_staged) {
+                        const float4* pp = reinterpret_cast<const float4*>(s_prims + pi);
+                        p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+                    } else
+#endif
+                    {
+                        const float4* pp = reinterpret_cast<const float4*>(gprims + pi);
+                        p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+                    }
+                    float t, b1, b2;
+                    const int acc = prim_test(p0, p1, p2, o, d, eps, tmax, t, b1, b2);
+                    if (acc) {
+                        if (anyhit) { hprim = pi; cur = kDone; sp = 0; leaf = kDone; break; }
+                        // tt == tmax is accepted by the reference; the later (higher index) primitive then wins
+                        if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
+                        tmax = t;
+                    }
+                    if (__float_as_int(p2.z) == 0) { ++pi; continue; }                 // more primitives in this leaf
+                    if (cur < 0 && cur > kPop) { leaf = cur; pi = ~cur; cur = kPop; }  // the leaf found while speculating
+                    else leaf = kDone;
+                }
+                if (cur == kPop) {                                                    // resolve a pending pop before the round ends
+                    cur = kDone;
+                    while (sp > 0) { --sp; if (!(stack_t[sp] > tmax)) { cur = stack[sp]; break; } }
+                    if (cur < 0 && cur != kDone) { leaf = cur; cur = kPop; }          // a leaf: handled first thing next round
                 }
                 // ---- finished: write the result (or start the next segment of a transmittance walk)
                 if (cur == kDone) {
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                                 remain -= seg;
                                 o = o + seg * d;                                               // Ray(ray(ray.tmax), ray.d, m, eps, tmax)
                                 tmax = remain;
-                                hprim = -1; sp = 0;
+                                hprim = -1; sp = 0; leaf = kDone;
                                 float tn;
                                 const bool in = slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn);
                                 cur = !in ? kDone : (a.sc.root_leaf_count > 0 ? ~0 : 0);
@@ -331,6 +331,132 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
         } while (busy != 0u && (exhausted || __popc(busy) >= a.refill_below));
     }
     // ray statistics: one atomic per warp
+#ifndef B200PT_EMULATE
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
+#endif
+    if (lane == 0u && nrays) atomicAdd(&a.counters->rays, (unsigned long long)nrays);
+}
+
+// ---- small scenes (<= 64 leaves): flat leaf list instead of a tree walk -------------------------------------
+// A Cornell-box-sized scene has a dozen leaves.  Walking its tree costs more in divergence (every lane is at a
+// different depth) than the tree saves, so this kernel tests ALL leaf boxes in one warp-uniform loop (box records
+// come out of shared memory as broadcasts), keeps the hit leaves of a ray as a 64-bit mask, and then runs one
+// flat primitive loop in which every iteration is one Moeller-Trumbore / sphere test for every lane that still
+// has a primitive.  Same slab and primitive arithmetic as the tree kernel; a leaf is tested iff its own box is
+// hit, which is a superset of what the reference's descent tests, so the closest / any hit is the same.
+//   leaf record (32 B): q0 = bmin.xyz, bmax.x   q1 = bmax.yz, first primitive (bits), primitive count (bits)
+template <bool VOL>
+__global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a) {
+    const WPrim* __restrict__ prims = a.sc.prims;
+    const float4* __restrict__ leaves = a.leaves;
+#ifndef B200PT_EMULATE
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    {
+        const uint32_t lb = (uint32_t)a.n_leaves * 32u;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, a.stage_bytes_prims + lb);
+            tma_bulk_g2s(smem_raw, a.sc.prims, a.stage_bytes_prims, &bar);
+            tma_bulk_g2s(smem_raw + a.stage_bytes_prims, a.leaves, lb, &bar);
+        }
+        mbar_wait(&bar, 0);
+        prims = reinterpret_cast<const WPrim*>(smem_raw);
+        leaves = reinterpret_cast<const float4*>(smem_raw + a.stage_bytes_prims);
+    }
+#endif
+    const uint32_t lane = pt_lane();
+    const uint32_t par = a.parity & 1u;
+    const uint32_t tail = a.q.ctl->tail[par];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.q.ctl->tail[par ^ 1u] = 0u; a.q.ctl->head[par ^ 1u] = 0u; }
+    const float eps = a.sc.eps;
+    const int n_leaves = a.n_leaves;
+    uint32_t nrays = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tail; idx += stride) {
+        const uint32_t entry = a.q.entries[idx];
+        const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
+        const float4 orng = a.pool.o_rng[slot];
+        f3 o = mk3(orng.x, orng.y, orng.z);
+        float4 dv;
+        if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
+        else if (kind == 1u) dv = a.pool.shd[slot];
+        else { dv = a.pool.misd[slot]; dv.w = INFINITY; }
+        const f3 d = mk3(dv.x, dv.y, dv.z);
+        float tmax = dv.w;
+        const bool anyhit = !VOL && kind == 1u;
+        f3 tr = mk3(1, 1, 1);
+        float remain = tmax;
+        int medium = -1;
+        if (VOL && kind == 1u) medium = (int)((__float_as_uint(a.pool.d_flags[slot].w) >> kMedium2Shift) & 0xffu) - 1;
+        const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+        int hprim; float hb1 = 0.f, hb2 = 0.f;
+        for (;;) {                                   // one pass per ray; vpt shadow rays repeat it per segment (Tr())
+            ++nrays;
+            hprim = -1;
+            // ---- all leaf boxes, warp-uniform
+            unsigned long long mask = 0ull;
+            float tn;
+            if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
+                for (int l = 0; l < n_leaves; ++l) {
+                    const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
+                    if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) mask |= 1ull << l;
+                }
+            }
+            // ---- flat primitive loop over the hit leaves, in leaf (= primitive index) order
+            int pi = 0, left = 0;
+            for (;;) {
+                if (left == 0) {
+                    if (mask == 0ull) break;
+                    const int l = __ffsll((long long)mask) - 1;
+                    mask &= mask - 1ull;
+                    const float4 q1 = leaves[2 * l + 1];
+                    pi = __float_as_int(q1.z); left = __float_as_int(q1.w);
+                }
+                const float4* pp = reinterpret_cast<const float4*>(prims + pi);
+                const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+                float t, b1, b2;
+                const int acc = prim_test(p0, p1, p2, o, d, eps, tmax, t, b1, b2);
+                if (acc) {
+                    if (anyhit) { hprim = pi; break; }
+                    if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
+                    tmax = t;
+                }
+                ++pi; --left;
+            }
+            if (!(VOL && kind == 1u)) break;
+            // Tr() (src/pathtracer.cu:298-322), same walk as in k_trace
+            const bool invisible = hprim >= 0;
+            const float seg = invisible ? tmax : remain;
+            if (invisible && a.sc.shade[hprim].matIdx != -1) { tr = mk3(0, 0, 0); break; }
+            if (medium >= 0) {
+                const f3 c = ld3(a.sc.mediums[medium].sigmaT) * (-seg);
+                tr *= mk3(expf(c.x), expf(c.y), expf(c.z));
+            }
+            if (!invisible) break;
+            const WShade& sh = a.sc.shade[hprim];
+            f3 nor;
+            if (sh.type == 0) nor = normalize(ld3(sh.n1) * (1.f - hb1 - hb2) + ld3(sh.n2) * hb1 + ld3(sh.n3) * hb2);
+            else nor = normalize((o + seg * d) - ld3(sh.n1));
+            medium = dot(d, nor) > 0 ? sh.mediumOutside : sh.mediumInside;
+            remain -= seg;
+            o = o + seg * d;
+            tmax = remain;
+        }
+        if (kind != 1u) {
+            const float4 h = make_float4(hprim >= 0 ? tmax : -1.f, __int_as_float(hprim), hb1, hb2);
+            if (kind == 0u) a.pool.hit0[slot] = h; else a.pool.hit1[slot] = h;
+        } else if (!VOL) {
+            const float v = hprim >= 0 ? 0.f : 1.f;
+            a.pool.vis[slot] = make_float4(v, v, v, 0.f);
+        } else {
+            a.pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
+        }
+    }
 #ifndef B200PT_EMULATE
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
 #endif

@@ -40,6 +40,7 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline void __syncthreads() {}
 
 typedef int cudaError_t;

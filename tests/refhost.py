@@ -241,3 +241,32 @@ class RefCuda:
 
     def end(self):
         self.lib.refcuda_end()
+
+
+class Adapter:
+    """The product behind the reference-signature C++ entry points (gpu-pathtracer_b200/host/pathtracer_adapter.cpp
+    compiled against the reference's headers into oracle/_ref/libadapter.so) — what main.cpp would call."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(REF_DIR, "libadapter.so"))
+
+    def begin(self, scene, width=None, height=None):
+        from gpu_pathtracer_b200 import _lib
+        self.w, self.h = width or scene.width, height or scene.height
+        view, self._keep = _lib.make_view(scene)
+        rc = self.lib.adapter_begin(C.byref(view), C.c_uint(self.w), C.c_uint(self.h), C.c_float(scene.epsilon))
+        assert rc == 0, rc
+
+    def render(self, first_iter, spp, reset_first=True):
+        out = np.empty((self.h, self.w, 3), np.float32)
+        rc = self.lib.adapter_render(C.c_uint(first_iter), C.c_uint(spp), C.c_int(int(reset_first)), C.c_void_p(out.ctypes.data))
+        assert rc == 0, rc
+        return out
+
+    def accum(self):
+        a = np.empty((self.h, self.w, 3), np.float32)
+        assert self.lib.adapter_get_accum(C.c_void_p(a.ctypes.data)) == 0
+        return a
+
+    def end(self):
+        self.lib.adapter_end()

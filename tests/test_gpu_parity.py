@@ -134,3 +134,21 @@ def test_full_size_properties_c4_sharded():
         a, _ = _render(s, 1, 2, shard=(k, 4, 32, 32))
         total += a
     assert np.array_equal(_bits(total), _bits(full))
+
+
+@pytest.mark.skipif(not refhost.have("libadapter.so"), reason="oracle/_ref/libadapter.so not present")
+def test_reference_signature_adapter_is_a_drop_in():
+    """BeginRender / Render(iter) x spp / EndRender through the C++ adapter (what the reference's main.cpp calls,
+    device output pointer) == the direct C-ABI path, bit for bit."""
+    s = pt.scenes.cornell_pt(256, 256, 8)
+    spp = 6
+    ad = refhost.Adapter()
+    ad.begin(s)
+    try:
+        tone_a = ad.render(1, spp)
+        acc_a = ad.accum()
+    finally:
+        ad.end()
+    acc, tone = _render(s, 1, spp)
+    assert np.array_equal(_bits(acc_a), _bits(acc))
+    assert np.array_equal(_bits(tone_a), _bits(tone))
