@@ -7,6 +7,7 @@
 #include "k_trace.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -48,6 +49,7 @@ struct b200pt_ctx {
     int steps_per_poll = 8;
     double stats[5] = {0, 0, 0, 0, 0};
     double total_ms = 0;
+    unsigned long long counter_init[2] = {0, 0};
     bool vol = false;
     int last_filmic = 1;
 };
@@ -193,22 +195,62 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         w.link.y = R.is_leaf ? ~R.start : inner_id[r];
         w.link.z = 0; w.link.w = 0;
     }
-    // flat leaf list for k_trace_small: leaf box + primitive run, in leaf (= primitive) order
-    {
-        std::vector<float4> wl;
-        for (int i = 0; i < v->n_nodes; ++i) {
-            const RefLinearBVHNode& n = nodes[i];
-            if (!n.is_leaf || (i != 0 && inner_id[0] < 0)) continue;
-            float4 a = make_float4(n.fmin[0], n.fmin[1], n.fmin[2], n.fmax[0]);
-            int first = n.start, count = n.end - n.start + 1;
-            float ff, cf; std::memcpy(&ff, &first, 4); std::memcpy(&cf, &count, 4);
-            wl.push_back(a); wl.push_back(make_float4(n.fmax[1], n.fmax[2], ff, cf));
+    // primitive groups for k_trace_small (<= 256 primitives): greedy agglomeration of tight primitive boxes under the
+    // cost model  cost(group) = C_BOX + P(ray hits box) * C_PRIM * |group|,  P ~ surface area of the box / root's
+    if (v->n_prims <= 256) {
+        struct Grp { float mn[3], mx[3]; int n; int p[4]; };
+        std::vector<Grp> g(v->n_prims);
+        for (int i = 0; i < v->n_prims; ++i) {
+            const RefPrimitive& p = prims[i];
+            Grp& G = g[i]; G.n = 1; G.p[0] = i;
+            if (p.type == REF_GT_TRIANGLE) {
+                const float* vv[3] = {p.u.triangle.v1.v, p.u.triangle.v2.v, p.u.triangle.v3.v};
+                for (int k = 0; k < 3; ++k) {
+                    G.mn[k] = std::min(vv[0][k], std::min(vv[1][k], vv[2][k]));
+                    G.mx[k] = std::max(vv[0][k], std::max(vv[1][k], vv[2][k]));
+                }
+            } else {
+                for (int k = 0; k < 3; ++k) { G.mn[k] = p.u.sphere.origin[k] - p.u.sphere.radius; G.mx[k] = p.u.sphere.origin[k] + p.u.sphere.radius; }
+                // one ulp of slack per side: centre -/+ radius is itself rounded
+                for (int k = 0; k < 3; ++k) { G.mn[k] = std::nextafter(G.mn[k], -INFINITY); G.mx[k] = std::nextafter(G.mx[k], INFINITY); }
+            }
         }
-        std::sort(reinterpret_cast<std::pair<float4, float4>*>(wl.data()), reinterpret_cast<std::pair<float4, float4>*>(wl.data()) + wl.size() / 2,
-                  [](const std::pair<float4, float4>& x, const std::pair<float4, float4>& y) {
-                      int fx, fy; std::memcpy(&fx, &x.second.z, 4); std::memcpy(&fy, &y.second.z, 4); return fx < fy; });
-        c->n_leaves = (int)(wl.size() / 2);
-        if (c->n_leaves > 0 && c->n_leaves <= 64) {
+        auto area = [](const float* mn, const float* mx) {
+            double dx = (double)mx[0] - mn[0], dy = (double)mx[1] - mn[1], dz = (double)mx[2] - mn[2];
+            return 2.0 * (dx * dy + dy * dz + dz * dx);
+        };
+        const double root_area = std::max(area(nodes[0].fmin, nodes[0].fmax), 1e-30);
+        const double C_BOX = 22.0, C_PRIM = 186.0;
+        auto cost = [&](const float* mn, const float* mx, int n) { return C_BOX + std::min(1.0, area(mn, mx) / root_area) * C_PRIM * n; };
+        for (;;) {
+            double best = 0.0; int bi = -1, bj = -1;
+            const bool forced = g.size() > 64;
+            for (size_t i = 0; i < g.size(); ++i)
+                for (size_t j = i + 1; j < g.size(); ++j) {
+                    if (g[i].n + g[j].n > 4) continue;
+                    float mn[3], mx[3];
+                    for (int k = 0; k < 3; ++k) { mn[k] = std::min(g[i].mn[k], g[j].mn[k]); mx[k] = std::max(g[i].mx[k], g[j].mx[k]); }
+                    const double delta = cost(mn, mx, g[i].n + g[j].n) - cost(g[i].mn, g[i].mx, g[i].n) - cost(g[j].mn, g[j].mx, g[j].n);
+                    if (bi < 0 || delta < best) { best = delta; bi = (int)i; bj = (int)j; }
+                }
+            if (bi < 0 || (!forced && best >= 0.0)) break;
+            Grp& A = g[bi]; const Grp& B = g[bj];
+            for (int k = 0; k < 3; ++k) { A.mn[k] = std::min(A.mn[k], B.mn[k]); A.mx[k] = std::max(A.mx[k], B.mx[k]); }
+            for (int k = 0; k < B.n; ++k) A.p[A.n++] = B.p[k];
+            g.erase(g.begin() + bj);
+        }
+        if (g.size() <= 64) {
+            std::vector<float4> wl;
+            for (const Grp& G : g) {
+                int idx[4] = {0xffff, 0xffff, 0xffff, 0xffff};
+                for (int k = 0; k < G.n; ++k) idx[k] = G.p[k];
+                std::sort(idx, idx + G.n);
+                const uint32_t u0 = (uint32_t)idx[0] | ((uint32_t)idx[1] << 16), u1 = (uint32_t)idx[2] | ((uint32_t)idx[3] << 16);
+                float f0, f1; std::memcpy(&f0, &u0, 4); std::memcpy(&f1, &u1, 4);
+                wl.push_back(make_float4(G.mn[0], G.mn[1], G.mn[2], G.mx[0]));
+                wl.push_back(make_float4(G.mx[1], G.mx[2], f0, f1));
+            }
+            c->n_leaves = (int)g.size();
             int rc2 = dev_upload(c, &c->leaves, wl.data(), wl.size());
             if (rc2) return rc2;
         }
@@ -381,6 +423,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     }
     if (n == "steps_per_poll") { if (value < 1 || value > 1024) return fail(B200PT_EINVAL, "steps_per_poll out of range"); c->steps_per_poll = (int)value; return 0; }
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
+    if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
     if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr && c->stage_prims > 0; return 0; }
     if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; } return 0; }
@@ -424,7 +467,11 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         c->samples_cap = need;
     }
     BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
-    CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 2, c->stream));   // next_sample, done_samples (rays keeps counting)
+    bp.k_static = (uint32_t)((need - need / 4) / (unsigned long long)c->pool.n);      // ~3/4 of the batch by static assignment
+    // next_sample starts behind the statically assigned range; done_samples at 0 (rays keeps counting)
+    c->counter_init[0] = (unsigned long long)bp.k_static * (unsigned long long)c->pool.n; c->counter_init[1] = 0ull;
+    CK(cudaMemcpyAsync(c->counters, c->counter_init, sizeof(c->counter_init), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->pool.li_t, 0, sizeof(float4) * (size_t)c->pool.n, c->stream));   // no static samples consumed yet
     CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
     ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
     TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
@@ -544,7 +591,7 @@ extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t 
     for (uint32_t base = 0; base < npix; base += P) {
         // hand out exactly the samples [base, base + P) of this iteration
         uint32_t cnt = std::min(P, npix - base);
-        BatchParams bp; bp.first_iter = iter; bp.n_iters = 1; bp.total = base + cnt;
+        BatchParams bp; bp.first_iter = iter; bp.n_iters = 1; bp.total = base + cnt; bp.k_static = 0;
         Counters z; std::memset(&z, 0, sizeof(z)); z.next_sample = base;
         CK(cudaMemcpyAsync(c->counters, &z, sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)P, c->stream));

@@ -195,8 +195,10 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     f3 beta = alive ? mk3(bs.x, bs.y, bs.z) : mk3(1, 1, 1);
     f3 Li = alive ? mk3(lt4.x, lt4.y, lt4.z) : mk3(0, 0, 0);
     uint32_t sample = alive ? __float_as_uint(bs.w) : 0u;
-    // a dead slot regenerates while samples are left (snapshot of the counter: exact enough, see below)
-    bool finished = !alive && next_snapshot < a.batch.total;
+    uint32_t kdone = __float_as_uint(lt4.w);                        // static samples this slot has consumed
+    // a dead slot regenerates while samples are left for it (its static share, then the global counter — a snapshot
+    // of it is exact enough, see below)
+    bool finished = !alive && (kdone < a.batch.k_static || next_snapshot < a.batch.total);
     const bool idle_dead = !alive && !finished;
     int bounces = (int)((flags >> kBounceShift) & 0xffu);
     int medium = (int)((flags >> kMediumShift) & 0xffu) - 1;      // medium of the continuation ray (vpt)
@@ -455,7 +457,8 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     if (finished && alive) {
         st_pool(a.samples + sample, make_float4(Li.x, Li.y, Li.z, 1.f));
     }
-    const uint32_t m_fin = __ballot_sync(kFullMask, finished);
+    const bool take_static = finished && kdone < a.batch.k_static;
+    const uint32_t m_fin = __ballot_sync(kFullMask, finished && !take_static);      // lanes that need the global counter
     const uint32_t m_ret = __ballot_sync(kFullMask, finished && alive);
     uint32_t rays = finished ? F_CONT : (idle_dead ? 0u : (nf & (F_CONT | F_SHADOW | F_MIS)));
     const uint32_t mc = __ballot_sync(kFullMask, (rays & F_CONT) != 0u);
@@ -477,7 +480,9 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     if (idle_dead) return;
 
     if (finished) {
-        const unsigned long long s = sbase + (unsigned long long)__popc(m_fin & lt);
+        unsigned long long s;
+        if (take_static) { s = (unsigned long long)slot + (unsigned long long)kdone * (unsigned long long)a.pool.n; ++kdone; }
+        else s = sbase + (unsigned long long)__popc(m_fin & lt);
         if (s >= a.batch.total) {
             // the batch ran out between the snapshot and the atomic: the slot dies; its queue entry stays and
             // traces one harmless ray (this happens in at most one step per batch)
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     st_pool(a.pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
     st_pool(a.pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
     st_pool(a.pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));
-    st_pool(a.pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
+    st_pool(a.pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, __uint_as_float(kdone)));
 }
 
 // ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------

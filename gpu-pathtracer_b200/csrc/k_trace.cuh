@@ -337,14 +337,17 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
     if (lane == 0u && nrays) atomicAdd(&a.counters->rays, (unsigned long long)nrays);
 }
 
-// ---- small scenes (<= 64 leaves): flat leaf list instead of a tree walk -------------------------------------
-// A Cornell-box-sized scene has a dozen leaves.  Walking its tree costs more in divergence (every lane is at a
-// different depth) than the tree saves, so this kernel tests ALL leaf boxes in one warp-uniform loop (box records
-// come out of shared memory as broadcasts), keeps the hit leaves of a ray as a 64-bit mask, and then runs one
-// flat primitive loop in which every iteration is one Moeller-Trumbore / sphere test for every lane that still
-// has a primitive.  Same slab and primitive arithmetic as the tree kernel; a leaf is tested iff its own box is
-// hit, which is a superset of what the reference's descent tests, so the closest / any hit is the same.
-//   leaf record (32 B): q0 = bmin.xyz, bmax.x   q1 = bmax.yz, first primitive (bits), primitive count (bits)
+// ---- small scenes (<= 256 primitives): flat list of tight primitive groups instead of a tree walk ----------
+// A Cornell-box-sized scene has a few dozen primitives.  Walking its tree costs more in divergence (every lane is
+// at a different depth) than the tree saves, so this kernel tests ALL group boxes in one warp-uniform loop (box
+// records come out of shared memory as broadcasts), keeps the hit groups of a ray as a 64-bit mask, and then runs
+// one flat primitive loop in which every iteration is one Moeller-Trumbore / sphere test for every lane that still
+// has a primitive.  Groups (<= 64 per scene, <= 4 primitives each) are built at upload by greedy agglomeration
+// under a box-test/primitive-test cost model, so a quad's two triangles share one tight box while unrelated
+// triangles are not lumped together as the SAH leaves do.  Same slab and primitive arithmetic as the tree kernel;
+// a primitive is tested iff its group's box is hit, which (up to rounding at box faces) is a superset of the
+// primitives that can be hit, so the closest / any hit is the same.
+//   group record (32 B): q0 = bmin.xyz, bmax.x   q1 = bmax.yz, prims 0|1 (2 x u16 bits), prims 2|3 (0xffff = none)
 template <bool VOL>
 __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a) {
     const WPrim* __restrict__ prims = a.sc.prims;
@@ -407,16 +410,21 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
                     if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) mask |= 1ull << l;
                 }
             }
-            // ---- flat primitive loop over the hit leaves, in leaf (= primitive index) order
-            int pi = 0, left = 0;
+            // ---- flat primitive loop over the hit groups
+            uint32_t w0 = 0u, w1 = 0u;        // remaining primitive indices of the current group, 16 bits each
+            int left = 0;
             for (;;) {
                 if (left == 0) {
                     if (mask == 0ull) break;
                     const int l = __ffsll((long long)mask) - 1;
                     mask &= mask - 1ull;
                     const float4 q1 = leaves[2 * l + 1];
-                    pi = __float_as_int(q1.z); left = __float_as_int(q1.w);
+                    w0 = __float_as_uint(q1.z); w1 = __float_as_uint(q1.w);
+                    left = (w0 >> 16) == 0xffffu ? 1 : ((w1 & 0xffffu) == 0xffffu ? 2 : ((w1 >> 16) == 0xffffu ? 3 : 4));
                 }
+                const int pi = (int)(w0 & 0xffffu);
+                w0 = (w0 >> 16) | (w1 << 16); w1 >>= 16;
+                --left;
                 const float4* pp = reinterpret_cast<const float4*>(prims + pi);
                 const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
                 float t, b1, b2;
@@ -426,7 +434,6 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
                     if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
                     tmax = t;
                 }
-                ++pi; --left;
             }
             if (!(VOL && kind == 1u)) break;
             // Tr() (src/pathtracer.cu:298-322), same walk as in k_trace

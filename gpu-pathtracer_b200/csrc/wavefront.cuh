@@ -86,7 +86,7 @@ struct Pool {
     float4* o_rng;        // ray origin xyz (shared by all three rays of the slot), rng state bits
     float4* d_flags;      // continuation direction xyz, flags bits
     float4* beta_s;       // throughput xyz, sample index bits
-    float4* li_t;         // radiance accumulated so far xyz, -
+    float4* li_t;         // radiance accumulated so far xyz, static samples this slot has consumed (bits)
     float4* shd;          // shadow ray direction xyz, tmax
     float4* misd;         // MIS ray direction xyz, pdf
     float4* ldl;          // direct-light term if unoccluded xyz, |cos| of the MIS direction
@@ -175,6 +175,9 @@ struct BatchParams {
     uint32_t first_iter;     // iteration number of sample plane 0 (1-based, part of the RNG seed)
     uint32_t n_iters;        // iterations in this batch
     unsigned long long total;  // n_iters * n_local_pixels
+    // Sample hand-out: slot s takes samples s, s + P, ... for its first k_static regenerations (no atomic, ~3/4 of
+    // the batch); the rest comes from the global counter, which starts at k_static * P and evens out the tail.
+    uint32_t k_static;
 };
 
 }  // namespace pt
