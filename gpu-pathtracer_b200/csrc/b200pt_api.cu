@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -24,32 +25,47 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail(B200PT_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
     } while (0)
 
-struct b200pt_ctx {
-    int device = 0;
+// One LANE = an independent wavefront (own stream, path pool, ray queue, counters, sample planes) over an
+// interleaved subset of the context's screen tiles.  A context runs kLanes of them side by side on the same GPU:
+// while one lane's traversal kernel (instruction-issue bound) drains, the other lane's shading kernel
+// (latency bound) fills the machine, and the launch gaps of one chain hide behind the kernels of the other.
+struct Lane {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
-    SceneDev sc{};
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr}, ev_done = nullptr;
     ShardMap map{};
     Pool pool{};
-    std::vector<void*> allocs;            // everything cudaMalloc'ed (freed in destroy)
+    RayQueue q{};
     Counters* counters = nullptr;
     Counters* h_counters = nullptr;       // pinned, 2 polling slots
     float4* samples = nullptr; size_t samples_cap = 0;   // in float4
+    unsigned long long counter_init[2] = {0, 0};
+    std::vector<void*> pool_allocs;       // cudaMalloc'ed pool/queue planes (re-allocated by the "pool" option)
+    ShadeArgs sa; TraceArgs ta;
+    int chunk = 0; bool done = false;
+};
+
+struct b200pt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;        // lane 0's stream: uploads, resolve of lane 0, output copies
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;
+    SceneDev sc{};
+    ShardMap map{};                       // the whole context's share of the image (rank-level shard)
+    std::vector<Lane> lanes;
+    std::vector<void*> allocs;            // everything else cudaMalloc'ed (freed in destroy)
     float *acc = nullptr, *color = nullptr, *out = nullptr;
     uint32_t width = 0, height = 0;
     int num_sms = 148, trace_blocks = 0;
     uint32_t stage_nodes = 0, stage_prims = 0;
     size_t stage_top_bytes = 32 * 1024;    // top-of-tree nodes staged per CTA when the scene does not fit
-    RayQueue q{};
     int refill_below = 24;
-    bool lambert_only = false;             // every material is lambertian -> specialised shade kernel
-    float4* leaves = nullptr; int n_leaves = 0;   // flat leaf list (scenes with <= 64 leaves)
+    bool lambert_only = false;             // every referenced material is lambertian -> specialised shade kernel
+    float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
     bool small_scene = false;              // use k_trace_small
     size_t max_batch_bytes = (size_t)2 << 30;
     int steps_per_poll = 8;
+    int pool_total = 1 << 20;              // path slots over all lanes
     double stats[5] = {0, 0, 0, 0, 0};
     double total_ms = 0;
-    unsigned long long counter_init[2] = {0, 0};
     bool vol = false;
     int last_filmic = 1;
 };
@@ -341,16 +357,41 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     return 0;
 }
 
-static int alloc_pool(b200pt_ctx* c, int n) {
-    Pool& p = c->pool;
+static void free_pool(Lane& L) {
+    for (void* p : L.pool_allocs) cudaFree(p);
+    L.pool_allocs.clear();
+    L.pool = Pool{}; L.q.entries = nullptr;
+}
+static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
+    free_pool(L);
+    Pool& p = L.pool;
     float4** arrs[] = {&p.o_rng, &p.d_flags, &p.beta_s, &p.li_t, &p.shd, &p.misd, &p.ldl, &p.misf, &p.beta_old, &p.hit0, &p.hit1, &p.vis, &p.aux};
     n = (n + 255) & ~255;
-    for (auto a : arrs) { int rc = dev_alloc(c, a, (size_t)n, true); if (rc) return rc; }
+    auto grab = [&](void** q, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(q, bytes);
+        if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc ") + std::to_string(bytes) + " B: " + cudaGetErrorString(e));
+        cudaMemsetAsync(*q, 0, bytes, L.stream);
+        L.pool_allocs.push_back(*q);
+        return 0;
+    };
+    for (auto a : arrs) { int rc = grab((void**)a, (size_t)n * sizeof(float4)); if (rc) return rc; }
     p.n = n;
-    int rc = dev_alloc(c, &c->q.entries, (size_t)3 * n, true);     // at most three rays per slot and step
-    if (rc) return rc;
-    if (!c->q.ctl && (rc = dev_alloc(c, &c->q.ctl, 1, true))) return rc;
-    return 0;
+    return grab((void**)&L.q.entries, (size_t)3 * n * sizeof(uint32_t));     // at most three rays per slot and step
+}
+// Pool slots per lane: the context total split evenly, never more than 4 slots per pixel of the lane.
+static int lane_pool_size(const b200pt_ctx* c, const Lane& L) {
+    int pool = std::max(1024, c->pool_total / (int)c->lanes.size());
+    if ((size_t)pool > (size_t)L.map.n_local_pixels * 4) pool = std::max(1024, L.map.n_local_pixels * 4);
+    return pool;
+}
+
+static void fill_map(ShardMap& m, uint32_t width, uint32_t height, int shard, int n_shards, int tile_w, int tile_h) {
+    m.width = (int)width; m.height = (int)height;
+    m.shard = shard; m.n_shards = n_shards; m.tile_w = tile_w; m.tile_h = tile_h;
+    m.tiles_x = (int)width / tile_w; m.tiles_y = (int)height / tile_h;
+    const int n_tiles = m.tiles_x * m.tiles_y;
+    m.n_local_tiles = n_shards == 1 ? n_tiles : (shard < n_tiles ? (n_tiles - shard + n_shards - 1) / n_shards : 0);
+    m.n_local_pixels = n_shards == 1 ? (int)(width * height) : m.n_local_tiles * tile_w * tile_h;
 }
 
 extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uint32_t height, float epsilon,
@@ -366,39 +407,49 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     b200pt_ctx* c = new b200pt_ctx();
     c->device = device; c->width = width; c->height = height;
     auto bail = [&](int rc) { std::string keep = g_err; b200pt_destroy(c); g_err = keep; return rc; };
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B200PT_ECUDA, "stream create failed"));
+
+    // rank-level shard of the image
+    int sh = 0, nsh = 1, tw = 32, th = 32;
+    if (shard && shard->n_shards > 1) {
+        if (shard->shard < 0 || shard->shard >= shard->n_shards || shard->tile_w <= 0 || shard->tile_h <= 0 ||
+            width % shard->tile_w || height % shard->tile_h)
+            return bail(fail(B200PT_EINVAL, "bad shard description (tiles must divide the image)"));
+        sh = shard->shard; nsh = shard->n_shards; tw = shard->tile_w; th = shard->tile_h;
+    }
+    fill_map(c->map, width, height, sh, nsh, tw, th);
+
+    // lanes: local tile j of this context goes to lane j % kLanes, i.e. lane k is shard (sh + nsh * k) of nsh * kLanes
+    int n_lanes = 2;
+    if (const char* env = getenv("B200PT_LANES")) n_lanes = std::max(1, std::min(8, atoi(env)));
+    if (width % tw || height % th || c->map.n_local_tiles < n_lanes) n_lanes = 1;
+    c->lanes.resize(n_lanes);
+    for (int k = 0; k < n_lanes; ++k) {
+        Lane& L = c->lanes[k];
+        if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B200PT_ECUDA, "stream create failed"));
+        cudaEventCreateWithFlags(&L.ev_poll[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&L.ev_poll[1], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming);
+        if (n_lanes == 1) L.map = c->map;
+        else fill_map(L.map, width, height, sh + nsh * k, nsh * n_lanes, tw, th);
+    }
+    c->stream = c->lanes[0].stream;
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
-    cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     c->sc.eps = epsilon;
     int rc = build_scene(c, scene);
     if (rc) return bail(rc);
 
-    // shard map
-    ShardMap& m = c->map;
-    m.width = (int)width; m.height = (int)height;
-    m.shard = 0; m.n_shards = 1; m.tile_w = 32; m.tile_h = 32;
-    if (shard && shard->n_shards > 1) {
-        if (shard->shard < 0 || shard->shard >= shard->n_shards || shard->tile_w <= 0 || shard->tile_h <= 0 ||
-            width % shard->tile_w || height % shard->tile_h)
-            return bail(fail(B200PT_EINVAL, "bad shard description (tiles must divide the image)"));
-        m.shard = shard->shard; m.n_shards = shard->n_shards; m.tile_w = shard->tile_w; m.tile_h = shard->tile_h;
-    }
-    m.tiles_x = (int)width / m.tile_w; m.tiles_y = (int)height / m.tile_h;
-    int n_tiles = m.tiles_x * m.tiles_y;
-    m.n_local_tiles = m.n_shards == 1 ? n_tiles : (n_tiles - m.shard + m.n_shards - 1) / m.n_shards;
-    m.n_local_pixels = m.n_shards == 1 ? (int)(width * height) : m.n_local_tiles * m.tile_w * m.tile_h;
-
     size_t npix = (size_t)width * height;
     if ((rc = dev_alloc(c, &c->acc, 3 * npix, true))) return bail(rc);
     if ((rc = dev_alloc(c, &c->color, 3 * npix, true))) return bail(rc);
     if ((rc = dev_alloc(c, &c->out, 3 * npix, true))) return bail(rc);
-    if ((rc = dev_alloc(c, &c->counters, 1, true))) return bail(rc);
-    if (cudaMallocHost((void**)&c->h_counters, 2 * sizeof(Counters)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
-    int pool = 1 << 20;
-    if ((size_t)pool > (size_t)m.n_local_pixels * 4) pool = std::max(1024, m.n_local_pixels * 4);
-    if ((rc = alloc_pool(c, pool))) return bail(rc);
+    for (Lane& L : c->lanes) {
+        if ((rc = dev_alloc(c, &L.counters, 1, true))) return bail(rc);
+        if ((rc = dev_alloc(c, &L.q.ctl, 1, true))) return bail(rc);
+        if (cudaMallocHost((void**)&L.h_counters, 2 * sizeof(Counters)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
+        if ((rc = alloc_pool(c, L, lane_pool_size(c, L)))) return bail(rc);
+    }
 
     // persistent traversal grid: resident CTAs per SM x SM count
     int per_sm = 0;
@@ -407,7 +458,7 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
     if (per_sm <= 0) per_sm = 1;
     c->trace_blocks = c->num_sms * per_sm;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));
     *out_ctx = c;
     return B200PT_OK;
 }
@@ -418,8 +469,13 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "pool") {
         if (value < 256 || value > (1 << 26)) return fail(B200PT_EINVAL, "pool must be in [256, 2^26]");
         CK(cudaSetDevice(c->device));
-        CK(cudaStreamSynchronize(c->stream));
-        return alloc_pool(c, (int)value);      // the old pool is released with the context
+        CK(cudaDeviceSynchronize());
+        c->pool_total = (int)value;
+        for (Lane& L : c->lanes) {
+            int rc = alloc_pool(c, L, std::max(256, (int)value / (int)c->lanes.size()));
+            if (rc) return rc;
+        }
+        return 0;
     }
     if (n == "steps_per_poll") { if (value < 1 || value > 1024) return fail(B200PT_EINVAL, "steps_per_poll out of range"); c->steps_per_poll = (int)value; return 0; }
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
@@ -430,80 +486,108 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     return fail(B200PT_EINVAL, "unknown option " + n);
 }
 
-static void launch_shade(b200pt_ctx* c, const ShadeArgs& sa) {
-    const int blocks = c->pool.n / 128;
+static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
+    const int blocks = L.pool.n / 128;
     if (c->vol) {
-        if (c->lambert_only) PT_LAUNCH((k_shade<true, kMatsLambertOnly>), blocks, 128, 0, c->stream, sa);
-        else PT_LAUNCH((k_shade<true, kMatsAll>), blocks, 128, 0, c->stream, sa);
+        if (c->lambert_only) PT_LAUNCH((k_shade<true, kMatsLambertOnly>), blocks, 128, 0, L.stream, sa);
+        else PT_LAUNCH((k_shade<true, kMatsAll>), blocks, 128, 0, L.stream, sa);
     } else {
-        if (c->lambert_only) PT_LAUNCH((k_shade<false, kMatsLambertOnly>), blocks, 128, 0, c->stream, sa);
-        else PT_LAUNCH((k_shade<false, kMatsAll>), blocks, 128, 0, c->stream, sa);
+        if (c->lambert_only) PT_LAUNCH((k_shade<false, kMatsLambertOnly>), blocks, 128, 0, L.stream, sa);
+        else PT_LAUNCH((k_shade<false, kMatsAll>), blocks, 128, 0, L.stream, sa);
     }
 }
-static void launch_trace(b200pt_ctx* c, const TraceArgs& ta) {
+static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
     if (c->small_scene) {
         const size_t smem = (size_t)c->stage_prims + (size_t)c->n_leaves * 32;
-        if (c->vol) PT_LAUNCH(k_trace_small<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
-        else PT_LAUNCH(k_trace_small<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
+        if (c->vol) PT_LAUNCH(k_trace_small<true>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
+        else PT_LAUNCH(k_trace_small<false>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
         return;
     }
     const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
-    if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
-    else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, c->stream, ta);
+    if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
+    else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
+}
+static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
+    ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
+    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp;
+    ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
+    ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
 }
 
-// One batch = n_iters iterations of every local pixel through the wavefront, then the ordered resolve.
+// One batch = n_iters iterations of every local pixel through the wavefronts of all lanes, then the ordered resolve.
+// Lane streams are forked from / joined into lane 0's stream with events, so the caller sees one ordered stream.
 static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint32_t n_iters, int reset, float* out_dev, int write_out,
                      double* launches, double* steps) {
-    const size_t need = (size_t)n_iters * c->map.n_local_pixels;
-    if (need > c->samples_cap) {
-        if (c->samples) {
-            CK(cudaStreamSynchronize(c->stream));
-            c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)c->samples), c->allocs.end());
-            cudaFree(c->samples); c->samples = nullptr; c->samples_cap = 0;
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    for (size_t k = 0; k < c->lanes.size(); ++k) {
+        Lane& L = c->lanes[k];
+        L.done = L.map.n_local_pixels == 0; L.chunk = 0;
+        if (L.done) continue;
+        if (k) CK(cudaStreamWaitEvent(L.stream, c->ev_fork, 0));
+        const size_t need = (size_t)n_iters * L.map.n_local_pixels;
+        if (need > L.samples_cap) {
+            if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
+            cudaError_t e = cudaMalloc((void**)&L.samples, need * sizeof(float4));
+            if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc of the sample planes: ") + cudaGetErrorString(e));
+            L.samples_cap = need;
         }
-        int rc = dev_alloc(c, &c->samples, need);
-        if (rc) return rc;
-        c->samples_cap = need;
+        BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
+        bp.k_static = (uint32_t)((need - need / 4) / (unsigned long long)L.pool.n);      // ~3/4 of the batch by static assignment
+        // next_sample starts behind the statically assigned range; done_samples at 0 (rays keeps counting)
+        L.counter_init[0] = (unsigned long long)bp.k_static * (unsigned long long)L.pool.n; L.counter_init[1] = 0ull;
+        CK(cudaMemcpyAsync(L.counters, L.counter_init, sizeof(L.counter_init), cudaMemcpyHostToDevice, L.stream));
+        CK(cudaMemsetAsync(L.pool.li_t, 0, sizeof(float4) * (size_t)L.pool.n, L.stream));   // no static samples consumed yet
+        CK(cudaMemsetAsync(L.q.ctl, 0, sizeof(QueueCtl), L.stream));
+        // all slots start dead: the first shade pass only regenerates
+        CK(cudaMemsetAsync(L.pool.d_flags, 0, sizeof(float4) * (size_t)L.pool.n, L.stream));
+        fill_args(c, L, cam, bp);
+        L.sa.parity = 0; launch_shade(c, L, L.sa); *launches += 1;
     }
-    BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
-    bp.k_static = (uint32_t)((need - need / 4) / (unsigned long long)c->pool.n);      // ~3/4 of the batch by static assignment
-    // next_sample starts behind the statically assigned range; done_samples at 0 (rays keeps counting)
-    c->counter_init[0] = (unsigned long long)bp.k_static * (unsigned long long)c->pool.n; c->counter_init[1] = 0ull;
-    CK(cudaMemcpyAsync(c->counters, c->counter_init, sizeof(c->counter_init), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->pool.li_t, 0, sizeof(float4) * (size_t)c->pool.n, c->stream));   // no static samples consumed yet
-    CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
-    ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
-    TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
-    // step i: shade emits its rays into queue set (i & 1); trace consumes that set and clears the other one
-    uint32_t step = 0;
-    auto shade = [&]() { sa.parity = step & 1u; launch_shade(c, sa); };
-    auto trace = [&]() { ta.parity = step & 1u; launch_trace(c, ta); ++step; };
-    // all slots start dead: the first shade pass only regenerates
-    CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)c->pool.n, c->stream));
-    shade(); *launches += 1;
-    // Launch in chunks and poll the retired-sample counter one chunk behind, so the GPU never waits on the host.
-    int chunk = 0;
-    bool done = false;
-    while (!done) {
-        for (int s = 0; s < c->steps_per_poll; ++s) { trace(); shade(); }
-        *launches += 2.0 * c->steps_per_poll; *steps += c->steps_per_poll;
-        const int slot = chunk & 1;
-        CK(cudaMemcpyAsync(&c->h_counters[slot], c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaEventRecord(c->ev_poll[slot], c->stream));
-        if (chunk >= 1) {
-            const int prev = (chunk - 1) & 1;
-            CK(cudaEventSynchronize(c->ev_poll[prev]));
-            if (c->h_counters[prev].done_samples >= bp.total) done = true;
+    // Launch in chunks, lanes interleaved, and poll each lane's retired-sample counter one chunk behind, so the GPU
+    // never waits on the host.  Step i of a lane: trace consumes queue set (i & 1), the shade after it fills the other.
+    for (;;) {
+        bool all_done = true;
+        for (Lane& L : c->lanes) {
+            if (L.done) continue;
+            all_done = false;
+            for (int s = 0; s < c->steps_per_poll; ++s) {
+                launch_trace(c, L, L.ta); L.ta.parity ^= 1u;
+                L.sa.parity ^= 1u; launch_shade(c, L, L.sa);
+            }
+            *launches += 2.0 * c->steps_per_poll; *steps += c->steps_per_poll;
+            const int slot = L.chunk & 1;
+            CK(cudaMemcpyAsync(&L.h_counters[slot], L.counters, sizeof(Counters), cudaMemcpyDeviceToHost, L.stream));
+            CK(cudaEventRecord(L.ev_poll[slot], L.stream));
+            if (L.chunk >= 1) {
+                const int prev = (L.chunk - 1) & 1;
+                CK(cudaEventSynchronize(L.ev_poll[prev]));
+                if (L.h_counters[prev].done_samples >= L.sa.batch.total) L.done = true;
+            }
+            if (++L.chunk > (1 << 22)) return fail(B200PT_ECUDA, "wavefront did not converge (internal error)");
         }
-        ++chunk;
-        if (chunk > (1 << 22)) return fail(B200PT_ECUDA, "wavefront did not converge (internal error)");
+        if (all_done) break;
     }
-    ResolveArgs ra; ra.samples = c->samples; ra.acc = c->acc; ra.color = c->color; ra.out = out_dev ? out_dev : c->out;
-    ra.map = c->map; ra.batch = bp; ra.reset = reset; ra.filmic = cam.filmic; ra.write_out = write_out;
-    PT_LAUNCH(k_resolve, (c->map.n_local_pixels + 255) / 256, 256, 0, c->stream, ra);
-    *launches += 1;
+    for (size_t k = 0; k < c->lanes.size(); ++k) {
+        Lane& L = c->lanes[k];
+        if (L.map.n_local_pixels == 0) continue;
+        ResolveArgs ra; ra.samples = L.samples; ra.acc = c->acc; ra.color = c->color; ra.out = out_dev ? out_dev : c->out;
+        ra.map = L.map; ra.batch = L.sa.batch; ra.reset = reset; ra.filmic = cam.filmic; ra.write_out = write_out;
+        PT_LAUNCH(k_resolve, (L.map.n_local_pixels + 255) / 256, 256, 0, L.stream, ra);
+        *launches += 1;
+        if (k) { CK(cudaEventRecord(L.ev_done, L.stream)); CK(cudaStreamWaitEvent(c->stream, L.ev_done, 0)); }
+    }
     CK(cudaGetLastError());
+    return 0;
+}
+
+static int read_rays(b200pt_ctx* c, unsigned long long* total) {
+    *total = 0;
+    for (Lane& L : c->lanes) {
+        unsigned long long r = 0;
+        CK(cudaMemcpyAsync(&r, &L.counters->rays, sizeof(r), cudaMemcpyDeviceToHost, L.stream));
+        CK(cudaStreamSynchronize(L.stream));
+        *total += r;
+    }
     return 0;
 }
 
@@ -518,32 +602,32 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     c->last_filmic = cam.filmic;
     float* out_dev = (output && output_is_device) ? output : c->out;
     const size_t npix = (size_t)c->width * c->height;
-    unsigned long long rays0 = 0;
-    CK(cudaMemcpyAsync(&rays0, &c->counters->rays, sizeof(rays0), cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long rays0 = 0, rays1 = 0;
+    int rc = read_rays(c, &rays0);
+    if (rc) return rc;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (reset && c->map.n_shards > 1) CK(cudaMemsetAsync(c->acc, 0, 3 * npix * sizeof(float), c->stream));
     if (c->map.n_shards > 1 && out_dev) CK(cudaMemsetAsync(out_dev, 0, 3 * npix * sizeof(float), c->stream));
     // batch size: as many iterations as fit the sample-plane budget
-    size_t per_iter = (size_t)c->map.n_local_pixels * sizeof(float4);
+    size_t per_iter = (size_t)std::max(1, c->map.n_local_pixels) * sizeof(float4);
     uint32_t max_iters = (uint32_t)std::max<size_t>(1, c->max_batch_bytes / per_iter);
     double launches = 0, steps = 0;
     uint32_t done = 0;
     while (done < spp) {
         uint32_t n = std::min(max_iters, spp - done);
         bool last = done + n == spp;
-        int rc = run_batch(c, cam, first_iter + done, n, reset && done == 0, out_dev, last ? 1 : 0, &launches, &steps);
+        rc = run_batch(c, cam, first_iter + done, n, reset && done == 0, out_dev, last ? 1 : 0, &launches, &steps);
         if (rc) return rc;
         done += n;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     if (output && !output_is_device) CK(cudaMemcpyAsync(output, out_dev, 3 * npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long rays1 = 0;
-    CK(cudaMemcpyAsync(&rays1, &c->counters->rays, sizeof(rays1), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if ((rc = read_rays(c, &rays1))) return rc;
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats[0] = (double)spp * c->map.n_local_pixels; c->stats[1] = launches; c->stats[2] = (double)(rays1 - rays0);
-    c->stats[3] = steps; c->stats[4] = ms;
+    c->stats[3] = steps / (double)c->lanes.size(); c->stats[4] = ms;
     c->total_ms += ms;
     return B200PT_OK;
 }
@@ -578,37 +662,47 @@ extern "C" int b200pt_tonemap(b200pt_ctx* c, const float* acc_device, uint32_t i
 }
 
 // Primary-visibility query through the production traversal kernel: regenerate one iteration, trace once.
+// Uses lane 0's pool with a whole-image map.
 extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t iter, float* hits_host) {
     if (!c || !camera || !hits_host || iter == 0) return fail(B200PT_EINVAL, "bad argument");
     CK(cudaSetDevice(c->device));
     if (c->map.n_shards != 1) return fail(B200PT_EINVAL, "trace_primary needs an unsharded context");
     Camera cam; std::memcpy(&cam, camera, sizeof(Camera));
+    Lane& L = c->lanes[0];
+    const ShardMap saved_map = L.map;
+    L.map = c->map;
     const uint32_t npix = c->width * c->height;
     std::vector<float4> hits(npix);
-    const uint32_t P = (uint32_t)c->pool.n;
-    if (c->samples_cap < npix) { int rc = dev_alloc(c, &c->samples, (size_t)npix); if (rc) return rc; c->samples_cap = npix; }
+    const uint32_t P = (uint32_t)L.pool.n;
+    int rc = 0;
+    if (L.samples_cap < npix) {
+        if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
+        if (cudaMalloc((void**)&L.samples, (size_t)npix * sizeof(float4)) != cudaSuccess) { L.map = saved_map; return fail(B200PT_ENOMEM, "cudaMalloc of the sample plane"); }
+        L.samples_cap = npix;
+    }
     std::vector<float4> tmp(P), bs(P), fl(P);
-    for (uint32_t base = 0; base < npix; base += P) {
+    for (uint32_t base = 0; base < npix && !rc; base += P) {
         // hand out exactly the samples [base, base + P) of this iteration
         uint32_t cnt = std::min(P, npix - base);
         BatchParams bp; bp.first_iter = iter; bp.n_iters = 1; bp.total = base + cnt; bp.k_static = 0;
         Counters z; std::memset(&z, 0, sizeof(z)); z.next_sample = base;
-        CK(cudaMemcpyAsync(c->counters, &z, sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->pool.d_flags, 0, sizeof(float4) * (size_t)P, c->stream));
-        CK(cudaMemsetAsync(c->q.ctl, 0, sizeof(QueueCtl), c->stream));
-        ShadeArgs sa; sa.sc = c->sc; sa.pool = c->pool; sa.counters = c->counters; sa.samples = c->samples; sa.q = c->q; sa.parity = 0; sa.cam = cam; sa.map = c->map; sa.batch = bp;
-        TraceArgs ta; ta.sc = c->sc; ta.pool = c->pool; ta.q = c->q; ta.counters = c->counters; ta.parity = 0; ta.refill_below = c->refill_below; ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
-        launch_shade(c, sa);
-        launch_trace(c, ta);
-        CK(cudaMemcpyAsync(tmp.data(), c->pool.hit0, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(bs.data(), c->pool.beta_s, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(fl.data(), c->pool.d_flags, sizeof(float4) * P, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        for (uint32_t s = 0; s < P; ++s) {
+        cudaMemcpyAsync(L.counters, &z, sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, L.stream);
+        cudaMemsetAsync(L.pool.d_flags, 0, sizeof(float4) * (size_t)P, L.stream);
+        cudaMemsetAsync(L.q.ctl, 0, sizeof(QueueCtl), L.stream);
+        fill_args(c, L, cam, bp);
+        launch_shade(c, L, L.sa);
+        launch_trace(c, L, L.ta);
+        cudaMemcpyAsync(tmp.data(), L.pool.hit0, sizeof(float4) * P, cudaMemcpyDeviceToHost, L.stream);
+        cudaMemcpyAsync(bs.data(), L.pool.beta_s, sizeof(float4) * P, cudaMemcpyDeviceToHost, L.stream);
+        cudaMemcpyAsync(fl.data(), L.pool.d_flags, sizeof(float4) * P, cudaMemcpyDeviceToHost, L.stream);
+        if (cudaStreamSynchronize(L.stream) != cudaSuccess) rc = fail(B200PT_ECUDA, std::string("trace_primary: ") + cudaGetErrorString(cudaGetLastError()));
+        for (uint32_t s = 0; s < P && !rc; ++s) {
             uint32_t sample, flags; std::memcpy(&sample, &bs[s].w, 4); std::memcpy(&flags, &fl[s].w, 4);
             if ((flags & F_ALIVE) && sample >= base && sample < base + cnt) hits[sample] = tmp[s];
         }
     }
+    L.map = saved_map;
+    if (rc) return rc;
     CK(cudaGetLastError());
     std::memcpy(hits_host, hits.data(), sizeof(float4) * npix);
     return 0;
@@ -623,16 +717,22 @@ extern "C" int b200pt_stats(b200pt_ctx* c, double* out5) {
 extern "C" int b200pt_destroy(b200pt_ctx* c) {
     if (!c) return fail(B200PT_EINVAL, "null context");
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
-    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (Lane& L : c->lanes) {
+        free_pool(L);
+        if (L.samples) cudaFree(L.samples);
+        if (L.h_counters) cudaFreeHost(L.h_counters);
+        for (auto& e : L.ev_poll) if (e) cudaEventDestroy(e);
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    for (auto& e : c->ev_poll) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     delete c;
     return 0;
 }
 
 extern "C" const char* b200pt_last_error(void) { return g_err.c_str(); }
-extern "C" int b200pt_version(void) { return 100; }
+extern "C" int b200pt_version(void) { return 101; }
