@@ -5,7 +5,7 @@
 
 A "step" = one batch of `--spp-per-step` iterations (Render calls) of the workload image through the hot path.
 Default workload: C2 = Cornell box 1024x1024, depth 8 (the configuration the metric is quoted on; K steps of
-64 spp -> 16 steps are the full 1024-spp config).  N > 1 (launched by torchrun, one rank per GPU): the image's
+128 spp -> 8 steps are the full 1024-spp config).  N > 1 (launched by torchrun, one rank per GPU): the image's
 32x32 screen tiles are interleaved over the ranks (strong scaling); after every step the float3
 accumulation framebuffer is reduced to rank 0 with one NCCL reduce over NVLink, inside the timed region.
 
@@ -36,6 +36,10 @@ ALGO = {
     "c4": dict(R=10.26, N=233.7, P=66.9),
     "c5": dict(R=12.92, N=10.68, P=4.01),
 }
+
+
+# ncu-measured DRAM traffic per sample, whole wavefront (see profiles/); filled in from the capture of the round
+DRAM_BYTES_PER_SAMPLE = {"c2": 2017.0}     # profiles/r01j_launches_summary.txt: 25.4 GB over 12.6 Msamples
 
 
 def algo_bytes_per_sample(w):
@@ -134,7 +138,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--spp-per-step", type=int, default=64)
+    ap.add_argument("--spp-per-step", type=int, default=128)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -252,14 +256,20 @@ def main():
         bps = algo_bytes_per_sample(a.workload)
         kernel_s = dev_ms / 1e3                       # wavefront kernels (trace+shade+resolve) of all timed steps, CUDA events
         achieved = bps * samples / world / kernel_s / 1e9 if kernel_s > 0 else 0.0
+        # measured DRAM bytes per sample (ncu dram__bytes_read+write summed over every kernel of one bench step,
+        # profiles/<round>_dram_bytes_*.txt) x samples of one step, per GPU; None for workloads without a capture
+        dram_bps = DRAM_BYTES_PER_SAMPLE.get(a.workload)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "measured" if peaks else "fallback",
-                    "algorithmic_bytes_per_sample": bps, "kernel": "k_trace+k_shade wavefront (per GPU)"}
+                    "traffic": (dram_bps * float(npix) * spp / world) if dram_bps else None,
+                    "peak_source": "measured" if peaks else "fallback",
+                    "algorithmic_bytes_per_sample": bps, "algorithmic_bytes_per_step": bps * float(npix) * spp / world,
+                    "measured_dram_bytes_per_sample": dram_bps,
+                    "kernel": "wavefront step = k_shade + k_trace(_small) + k_resolve of one spp batch (per GPU); the per-sample "
+                              "figure of SURVEY 8(d) spans all three, so they are timed together with CUDA events"}
         cb = None
         if not a.no_cpu_baseline and world == 1:
-            c1, _ = make_scene(pt, "c1")
-            cb, _, _ = cpu_reference(c1 if a.workload == "c2" else scene, 12.0)
-            cb["sample"] += " of " + ("configs[0] cornell 256x256 depth 4" if a.workload == "c2" else a.workload)
+            cb, _, _ = cpu_reference(scene, 12.0)          # bounded sample of the SAME workload on the host cores
+            cb["sample"] += " of " + desc
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config, "device_ms_per_step": dev_ms / a.steps,
