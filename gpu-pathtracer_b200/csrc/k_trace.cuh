@@ -401,23 +401,37 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
         for (;;) {                                   // one pass per ray; vpt shadow rays repeat it per segment (Tr())
             ++nrays;
             hprim = -1;
-            // ---- all leaf boxes, warp-uniform
+            // ---- all group boxes, warp-uniform; remember the group the ray enters first
             unsigned long long mask = 0ull;
-            float tn;
+            float tn, best_t = INFINITY;
+            int best = -1;
             if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
                 for (int l = 0; l < n_leaves; ++l) {
                     const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
-                    if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) mask |= 1ull << l;
+                    if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
+                        mask |= 1ull << l;
+                        if (tn < best_t) { best_t = tn; best = l; }
+                    }
                 }
             }
-            // ---- flat primitive loop over the hit groups
+            // ---- flat primitive loop over the hit groups: nearest group first, then the others in index order; once
+            // a closest hit is known, a group is re-tested against the shrunken interval before its primitives are
+            // (the `tmin > ray.tmax` rejection of BBox::Intersect, src/bbox.h:93)
             uint32_t w0 = 0u, w1 = 0u;        // remaining primitive indices of the current group, 16 bits each
             int left = 0;
             for (;;) {
                 if (left == 0) {
-                    if (mask == 0ull) break;
-                    const int l = __ffsll((long long)mask) - 1;
-                    mask &= mask - 1ull;
+                    int l;
+                    if (best >= 0) { l = best; mask &= ~(1ull << best); best = -1; }
+                    else {
+                        if (mask == 0ull) break;
+                        l = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1ull;
+                        if (hprim >= 0) {
+                            const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
+                            if (!slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) continue;
+                        }
+                    }
                     const float4 q1 = leaves[2 * l + 1];
                     w0 = __float_as_uint(q1.z); w1 = __float_as_uint(q1.w);
                     left = (w0 >> 16) == 0xffffu ? 1 : ((w1 & 0xffffu) == 0xffffu ? 2 : ((w1 >> 16) == 0xffffu ? 3 : 4));

@@ -104,7 +104,11 @@ PT_HD uint32_t rng_seed(uint32_t pixel, uint32_t iter) {
 }
 // thrust::uniform_real_distribution<float>(0,1): float(x - 1) / 2^31 — can return exactly 1.0f.
 PT_HD float rng_next(uint32_t& x) {
-    x = (uint32_t)(((uint64_t)x * 48271ull) % 2147483647ull);
+    // x * 48271 mod (2^31 - 1) by Mersenne folding: p = hi * 2^31 + lo  ==>  p mod M = (hi + lo) mod M, and
+    // hi + lo < 2M because p < 2^47.  Bit-identical to the 64-bit `%` (thrust's Schrage form gives the same value).
+    const uint64_t p = (uint64_t)x * 48271ull;
+    uint32_t r = (uint32_t)(p & 0x7fffffffull) + (uint32_t)(p >> 31);
+    x = r >= 2147483647u ? r - 2147483647u : r;
     return (float)(x - 1u) * 4.656612873077393e-10f;   // exact power of two: identical to the division
 }
 
