@@ -56,11 +56,12 @@ struct b200pt_ctx {
     uint32_t width = 0, height = 0;
     int num_sms = 148, trace_blocks = 0;
     uint32_t stage_nodes = 0, stage_prims = 0;
-    size_t stage_top_bytes = 32 * 1024;    // top-of-tree nodes staged per CTA when the scene does not fit
+    size_t stage_top_bytes = 20 * 1024;    // top-of-tree nodes staged per CTA when the scene does not fit
     int refill_below = 24;
     bool lambert_only = false;             // every referenced material is lambertian -> specialised shade kernel
     float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
     bool small_scene = false;              // use k_trace_small
+    uint32_t small_prim_bytes = 0;
     size_t max_batch_bytes = (size_t)2 << 30;
     int steps_per_poll = 8;
     int pool_total = 1 << 20;              // path slots over all lanes
@@ -351,8 +352,11 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
     // (TMA bulk copy): everything when the scene is small, else the top of the breadth-first node array
     size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
-    if (nb + pb <= 40 * 1024) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; c->small_scene = c->leaves != nullptr; }
+    // (k_trace also keeps 24 KB of traversal stack in shared memory; 20 KB of structure keeps 5 CTAs per SM resident)
+    if (nb + pb <= c->stage_top_bytes) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; }
     else { c->stage_nodes = (uint32_t)std::min<size_t>(nb, c->stage_top_bytes); c->stage_prims = 0; }
+    c->small_prim_bytes = (uint32_t)pb;
+    c->small_scene = c->leaves != nullptr && pb + 64 * 32 <= 40 * 1024;
     CK(cudaStreamSynchronize(c->stream));     // host staging vectors go out of scope
     return 0;
 }
@@ -453,7 +457,8 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
 
     // persistent traversal grid: resident CTAs per SM x SM count
     int per_sm = 0;
-    size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+    size_t smem = (size_t)c->stage_nodes + c->stage_prims + kTraceStackBytes;
+    if (c->small_scene) smem = (size_t)c->small_prim_bytes + (size_t)c->n_leaves * 32;
     if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
     if (per_sm <= 0) per_sm = 1;
@@ -481,7 +486,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
     if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
-    if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr && c->stage_prims > 0; return 0; }
+    if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr; return 0; }
     if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; } return 0; }
     return fail(B200PT_EINVAL, "unknown option " + n);
 }
@@ -498,12 +503,12 @@ static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
 }
 static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
     if (c->small_scene) {
-        const size_t smem = (size_t)c->stage_prims + (size_t)c->n_leaves * 32;
+        const size_t smem = (size_t)c->small_prim_bytes + (size_t)c->n_leaves * 32;
         if (c->vol) PT_LAUNCH(k_trace_small<true>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
         else PT_LAUNCH(k_trace_small<false>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
         return;
     }
-    const size_t smem = (size_t)c->stage_nodes + c->stage_prims;
+    const size_t smem = (size_t)c->stage_nodes + c->stage_prims + kTraceStackBytes;
     if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
     else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
 }
@@ -511,7 +516,7 @@ static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchPara
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
     sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
-    ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
+    ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
 }
 
 // One batch = n_iters iterations of every local pixel through the wavefronts of all lanes, then the ordered resolve.

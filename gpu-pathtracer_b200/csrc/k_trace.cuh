@@ -101,13 +101,16 @@ struct TraceArgs {
     uint32_t parity;                                 // which QueueCtl set this step consumes
     int32_t refill_below;                            // refill a warp when fewer lanes than this still carry a ray
     uint32_t stage_bytes_nodes, stage_bytes_prims;   // > 0: bytes staged into shared memory with TMA
-    const float4* leaves;                            // small scenes: WLeaf records (leaf box + primitive run)
+    uint32_t small_prim_bytes;                       // k_trace_small: bytes of ALL primitive records (always staged)
+    const float4* leaves;                            // small scenes: primitive-group records (box + <= 4 primitives)
     int32_t n_leaves;
 };
 
 constexpr int kDone = (int)0x80000000;               // traversal cursor: nothing left to visit (also "no postponed leaf")
 constexpr int kPop = (int)0x80000001;                // traversal cursor: take the next entry from the stack
 constexpr int kTraceThreads = 256;
+constexpr int kSmemStack = 12;                       // stack levels kept in shared memory (8 B x 256 threads each)
+constexpr size_t kTraceStackBytes = (size_t)kSmemStack * kTraceThreads * 8;
 
 // One persistent warp = 32 independent rays in flight.  Lanes whose ray has finished are re-armed from the ray
 // queue as soon as fewer than `refill_below` lanes are busy (warp ballot + one aggregated atomic), so the
@@ -158,8 +161,23 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
     float tmax = 0.f, hb1 = 0.f, hb2 = 0.f;
     int hprim = -1, cur = kDone, leaf = kDone, sp = 0;
+    // Traversal stack: (subtree, entry distance) pairs.  The first kSmemStack levels live in shared memory, laid out
+    // [level][thread] so any mix of depths across a warp is bank-conflict free; deeper levels (rare with near-first
+    // ordering) spill to thread-local memory.  Keeping the hot levels out of local memory also keeps them out of L1,
+    // which the node / primitive fetches of a large scene need for themselves.
     int stack[64];
-    float stack_t[64];                                   // entry distance of every stacked subtree (cull on pop)
+    float stack_t[64];
+#ifndef B200PT_EMULATE
+    int* const s_stk = reinterpret_cast<int*>(smem_raw + a.stage_bytes_nodes + a.stage_bytes_prims) + threadIdx.x;
+    float* const s_stk_t = reinterpret_cast<float*>(s_stk + kSmemStack * kTraceThreads);
+#define STK_PUSH(node_, t_) do { if (sp < kSmemStack) { s_stk[sp * kTraceThreads] = (node_); s_stk_t[sp * kTraceThreads] = (t_); } \
+                                 else { stack[sp - kSmemStack] = (node_); stack_t[sp - kSmemStack] = (t_); } ++sp; } while (0)
+#define STK_POP(node_, t_) do { --sp; if (sp < kSmemStack) { (node_) = s_stk[sp * kTraceThreads]; (t_) = s_stk_t[sp * kTraceThreads]; } \
+                                else { (node_) = stack[sp - kSmemStack]; (t_) = stack_t[sp - kSmemStack]; } } while (0)
+#else
+#define STK_PUSH(node_, t_) do { stack[sp] = (node_); stack_t[sp] = (t_); ++sp; } while (0)
+#define STK_POP(node_, t_) do { --sp; (node_) = stack[sp]; (t_) = stack_t[sp]; } while (0)
+#endif
     f3 tr = mk3(1, 1, 1);          // vpt shadow rays: transmittance so far, remaining length, current medium
     float remain = 0.f;
     int medium = -1;
@@ -232,16 +250,17 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                         int c0 = link.x, c1 = link.y;
                         if (hl && hr) {
                             if (tr_ < tl) { const int t_ = c0; c0 = c1; c1 = t_; const float f_ = tl; tl = tr_; tr_ = f_; }
-                            stack[sp] = c1; stack_t[sp] = tr_; ++sp;
+                            STK_PUSH(c1, tr_);
                             cur = c0;
                         } else if (hl) cur = c0;
                         else if (hr) cur = c1;
                         else cur = kPop;
-                    } else if (cur == kPop) {
-                        // one pop per iteration; subtrees whose entry distance is already behind the closest hit are
-                        // dropped (the same `tmin > ray.tmax` rejection BBox::Intersect would make on visiting them,
-                        // src/bbox.h:93)
-                        if (sp > 0) { --sp; cur = (stack_t[sp] > tmax) ? kPop : stack[sp]; }
+                    }
+                    if (cur == kPop) {
+                        // one pop per iteration (right after the visit that ran dry); subtrees whose entry distance is
+                        // already behind the closest hit are dropped (the same `tmin > ray.tmax` rejection
+                        // BBox::Intersect would make on visiting them, src/bbox.h:93)
+                        if (sp > 0) { int n_; float t_; STK_POP(n_, t_); cur = (t_ > tmax) ? kPop : n_; }
                         else cur = kDone;
                     }
                     if (cur < 0 && cur > kPop && leaf == kDone) { leaf = cur; cur = kPop; }   // postpone the first leaf
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                 }
                 if (cur == kPop) {                                                    // resolve a pending pop before the round ends
                     cur = kDone;
-                    while (sp > 0) { --sp; if (!(stack_t[sp] > tmax)) { cur = stack[sp]; break; } }
+                    while (sp > 0) { int n_; float t_; STK_POP(n_, t_); if (!(t_ > tmax)) { cur = n_; break; } }
                     if (cur < 0 && cur != kDone) { leaf = cur; cur = kPop; }          // a leaf: handled first thing next round
                 }
                 // ---- finished: write the result (or start the next segment of a transmittance walk)
@@ -337,6 +356,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
     if (lane == 0u && nrays) atomicAdd(&a.counters->rays, (unsigned long long)nrays);
 }
 
+#undef STK_PUSH
+#undef STK_POP
+
 // ---- small scenes (<= 256 primitives): flat list of tight primitive groups instead of a tree walk ----------
 // A Cornell-box-sized scene has a few dozen primitives.  Walking its tree costs more in divergence (every lane is
 // at a different depth) than the tree saves, so this kernel tests ALL group boxes in one warp-uniform loop (box
@@ -363,13 +385,13 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, a.stage_bytes_prims + lb);
-            tma_bulk_g2s(smem_raw, a.sc.prims, a.stage_bytes_prims, &bar);
-            tma_bulk_g2s(smem_raw + a.stage_bytes_prims, a.leaves, lb, &bar);
+            mbar_expect_tx(&bar, a.small_prim_bytes + lb);
+            tma_bulk_g2s(smem_raw, a.sc.prims, a.small_prim_bytes, &bar);
+            tma_bulk_g2s(smem_raw + a.small_prim_bytes, a.leaves, lb, &bar);
         }
         mbar_wait(&bar, 0);
         prims = reinterpret_cast<const WPrim*>(smem_raw);
-        leaves = reinterpret_cast<const float4*>(smem_raw + a.stage_bytes_prims);
+        leaves = reinterpret_cast<const float4*>(smem_raw + a.small_prim_bytes);
     }
 #endif
     const uint32_t lane = pt_lane();
