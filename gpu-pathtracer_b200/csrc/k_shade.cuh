@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                     int b_old = bounces;
                     bounces = bounces + 1;
                     if (b_old > 3) {
-                        float illumate = clampf(1.f - luminance(beta), 0.f, 1.f);
+                        float illumate = clampf(1.f - luminance_rr<VOL>(beta), 0.f, 1.f);
                         if (rng_next(rng) < illumate) nf = (nf | F_TERMINATE) & ~F_CONT;
                         else beta /= (1 - illumate);
                     }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                         int b_old = bounces;
                         bounces = bounces + 1;
                         if (b_old > 3) {                                                        // :1010-1016
-                            float illumate = clampf(1.f - luminance(beta), 0.f, 1.f);
+                            float illumate = clampf(1.f - luminance_rr<VOL>(beta), 0.f, 1.f);
                             if (rng_next(rng) < illumate) nf = (nf | F_TERMINATE) & ~F_CONT;
                             else beta /= (1 - illumate);
                         }

@@ -85,6 +85,17 @@ PT_HD bool is_black(f3 c) { return c.x == 0 && c.y == 0 && c.z == 0; }          
 PT_HD bool is_nan3(f3 c) { return isnan(c.x) || isnan(c.y) || isnan(c.z); }
 PT_HD bool is_inf3(f3 c) { return isinf(c.x) || isinf(c.y) || isinf(c.z); }
 PT_HD float luminance(f3 c) { return dot(c, mk3(0.212671f, 0.715160f, 0.072169f)); }                         // pathtracer.cu:206
+// Luminance of the throughput in the Russian-roulette test (`u < 1 - Y(beta)` decides whether the path lives):
+// contraction pinned to what the reference's sm_100a build does at that site — Path: fma(z, fma(x, mul(y)));
+// Volpath: fma(z, fma(y, mul(x))) (read off its PTX; the two kernels differ).
+template <bool VOL> PT_HD float luminance_rr(f3 c) {
+#if defined(__CUDA_ARCH__)
+    if (VOL) return __fmaf_rn(c.z, 0.072169f, __fmaf_rn(c.y, 0.715160f, __fmul_rn(c.x, 0.212671f)));
+    return __fmaf_rn(c.z, 0.072169f, __fmaf_rn(c.x, 0.212671f, __fmul_rn(c.y, 0.715160f)));
+#else
+    return luminance(c);
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------ RNG (a1)
 // WangHash, src/pathtracer.cu:40
@@ -202,9 +213,19 @@ struct Material {          // 72-B reference Material (src/material.h:19)
 PT_HD bool is_delta(int type) { return type == MT_MIRROR || type == MT_DIELECTRIC; }                          // material.h:37
 
 PT_HD float dielectric_fresnel(float cosi, float cost, float etai, float etat) {                            // pathtracer.cu:51
+#if defined(__CUDA_ARCH__)
+    // feeds the reflect/refract decision `u > fresnel`: contraction pinned to the reference build's
+    // (products shared by numerator and denominator stay plain; Rparl^2 is fused onto mul(Rperp^2))
+    const float a = __fmul_rn(etat, cosi), b = __fmul_rn(etai, cost);
+    const float Rparl = __fdiv_rn(__fsub_rn(a, b), __fadd_rn(a, b));
+    const float c = __fmul_rn(etai, cosi), d = __fmul_rn(etat, cost);
+    const float Rperp = __fdiv_rn(__fsub_rn(c, d), __fadd_rn(c, d));
+    return __fmul_rn(__fmaf_rn(Rparl, Rparl, __fmul_rn(Rperp, Rperp)), 0.5f);
+#else
     float Rparl = (etat * cosi - etai * cost) / (etat * cosi + etai * cost);
     float Rperp = (etai * cosi - etat * cost) / (etai * cosi + etat * cost);
     return (Rparl * Rparl + Rperp * Rperp) * 0.5f;
+#endif
 }
 PT_HD f3 conduct_fresnel(float cosi, f3 eta, f3 k) {                                                        // pathtracer.cu:58
     f3 tmp = (eta * eta + k * k) * cosi * cosi;
