@@ -87,10 +87,19 @@ def make_view(s):
     v.camera = _ptr(s.camera); v.prims = _ptr(s.prims); v.nodes = _ptr(s.nodes)
     v.materials = _ptr(s.materials); v.mediums = _ptr(s.mediums); v.lights = _ptr(s.lights)
     v.infinite = _ptr(s.infinite) if s.infinite is not None else None
-    v.light_distribution = _ptr(s.light_distribution); v.textures = None
+    v.light_distribution = _ptr(s.light_distribution)
+    texs = getattr(s, "textures", None) or []
+    if texs:
+        arr = (Texture * len(texs))()
+        for i, t in enumerate(texs):
+            arr[i].texels = t.ctypes.data; arr[i].width = t.shape[1]; arr[i].height = t.shape[0]
+        keep += [arr] + list(texs)
+        v.textures = C.cast(arr, C.c_void_p)
+    else:
+        v.textures = None
     v.n_prims = len(s.prims); v.n_nodes = len(s.nodes); v.n_materials = len(s.materials)
     v.n_mediums = len(s.mediums); v.n_lights = len(s.lights)
-    v.n_light_distribution = len(s.light_distribution); v.n_textures = 0
+    v.n_light_distribution = len(s.light_distribution); v.n_textures = len(texs)
     v.integrator_type = s.integrator_type; v.max_depth = s.max_depth
     return v, keep
 

@@ -126,13 +126,13 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         return fail(B200PT_EUNSUPPORTED, "only the `pt` and `vpt` integrators are on the hot path");
     if (v->n_prims <= 0 || v->n_nodes <= 0 || !v->prims || !v->nodes || !v->camera || !v->materials || !v->light_distribution)
         return fail(B200PT_EINVAL, "scene view is missing primitives / nodes / camera / materials / light distribution");
-    if (v->n_textures > 0) return fail(B200PT_EUNSUPPORTED, "textured materials are not implemented yet (SURVEY 8(f).2)");
+    if (v->n_textures > 0 && !v->textures) return fail(B200PT_EINVAL, "n_textures > 0 without a texture table");
     if (v->n_mediums > 254) return fail(B200PT_EINVAL, "too many media");
     const RefPrimitive* prims = (const RefPrimitive*)v->prims;
     const RefLinearBVHNode* nodes = (const RefLinearBVHNode*)v->nodes;
     const RefMaterial* mats = (const RefMaterial*)v->materials;
     for (int i = 0; i < v->n_materials; ++i)
-        if (mats[i].textureIdx != -1) return fail(B200PT_EUNSUPPORTED, "textured materials are not implemented yet (SURVEY 8(f).2)");
+        if (mats[i].textureIdx < -1 || mats[i].textureIdx >= v->n_textures) return fail(B200PT_EINVAL, "material texture index out of range");
 
     // -- primitives: intersection records + shading records
     std::vector<WPrim> wp(v->n_prims);
@@ -166,8 +166,19 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
             s.type = 1;
             if (sp.matIdx >= v->n_materials || (sp.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
                 return fail(B200PT_EINVAL, "sphere material index out of range");
+        } else if (p.type == REF_GT_LINES) {
+            // Line::Intersect leaves the hit's medium fields untouched (src/line.h:74-83), which Volpath would then read
+            if (v->integrator_type != B200PT_IT_PT) return fail(B200PT_EUNSUPPORTED, "line primitives are only defined for the `pt` integrator");
+            const RefLine& ln = p.u.line;
+            int two = 2; float twof; std::memcpy(&twof, &two, 4);
+            q.q0 = make_float4(ln.p0[0], ln.p0[1], ln.p0[2], ln.p1[0]);
+            q.q1 = make_float4(ln.p1[1], ln.p1[2], ln.width0, ln.width1);
+            q.q2 = make_float4(0.f, twof, 0.f, 0.f);
+            s.matIdx = ln.matIdx; s.lightIdx = -1; s.mediumInside = -1; s.mediumOutside = -1;
+            s.type = 2;
+            if (ln.matIdx < 0 || ln.matIdx >= v->n_materials) return fail(B200PT_EINVAL, "line material index out of range");
         } else {
-            return fail(B200PT_EUNSUPPORTED, "line primitives are not implemented yet (SURVEY 8(f).2)");
+            return fail(B200PT_EINVAL, "unknown primitive type");
         }
         if (s.mediumInside >= v->n_mediums || s.mediumOutside >= v->n_mediums) return fail(B200PT_EINVAL, "medium index out of range");
     }
@@ -225,6 +236,13 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
                 for (int k = 0; k < 3; ++k) {
                     G.mn[k] = std::min(vv[0][k], std::min(vv[1][k], vv[2][k]));
                     G.mx[k] = std::max(vv[0][k], std::max(vv[1][k], vv[2][k]));
+                }
+            } else if (p.type == REF_GT_LINES) {           // Line::GetBBox, src/line.h:16
+                const RefLine& ln = p.u.line;
+                const float mw = ln.width0 > ln.width1 ? ln.width0 : ln.width1;
+                for (int k = 0; k < 3; ++k) {
+                    G.mn[k] = std::nextafter(std::min(ln.p0[k], ln.p1[k]) - mw, -INFINITY);
+                    G.mx[k] = std::nextafter(std::max(ln.p0[k], ln.p1[k]) + mw, INFINITY);
                 }
             } else {
                 for (int k = 0; k < 3; ++k) { G.mn[k] = p.u.sphere.origin[k] - p.u.sphere.radius; G.mx[k] = p.u.sphere.origin[k] + p.u.sphere.radius; }
@@ -326,6 +344,25 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     cdf.push_back(cdf.empty() ? 0.f : cdf.back());
     if ((rc = dev_upload(c, &d_cdf, cdf.data(), cdf.size()))) return rc;
     sc.cdf = d_cdf; sc.n_cdf = v->n_light_distribution;
+
+    // -- textures: all uchar4 texels back to back + {first texel, w, h} per texture (src/pathtracer.cu:2646-2661)
+    sc.texels = nullptr; sc.tex_info = nullptr;
+    if (v->n_textures > 0) {
+        std::vector<int4> info(v->n_textures);
+        std::vector<unsigned char> texels;
+        for (int i = 0; i < v->n_textures; ++i) {
+            const b200pt_texture& t = v->textures[i];
+            if (!t.texels || t.width <= 0 || t.height <= 0) return fail(B200PT_EINVAL, "texture without texels");
+            info[i].x = (int)(texels.size() / 4); info[i].y = t.width; info[i].z = t.height; info[i].w = 0;
+            const unsigned char* src = (const unsigned char*)t.texels;
+            texels.insert(texels.end(), src, src + 4 * (size_t)t.width * t.height);
+        }
+        unsigned char* d_tex; int4* d_info;
+        if ((rc = dev_upload(c, &d_tex, texels.data(), texels.size()))) return rc;
+        if ((rc = dev_upload(c, &d_info, info.data(), info.size()))) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        sc.texels = d_tex; sc.tex_info = d_info;
+    }
 
     // -- infinite light
     std::memset(&sc.inf, 0, sizeof(sc.inf));

@@ -26,7 +26,35 @@ struct ShadeArgs {
     BatchParams batch;
 };
 
-struct SurfaceHit { f3 pos, nor, dpdu; int matIdx, lightIdx, mediumInside, mediumOutside; };
+struct SurfaceHit { f3 pos, nor, dpdu; f2 uv; int matIdx, lightIdx, mediumInside, mediumOutside; };
+
+// getTexel / GetTexel (src/pathtracer.cu:324-359): wrap + clamp bilinear lookup of a uchar4 texture.
+__device__ __forceinline__ f3 tex_texel(const SceneDev& sc, const int4 info, int x, int y) {
+    const float inv = 1.f / 255.f;
+    const int w = info.y, h = info.z;
+    float rx = x - (x / w) * w;
+    float ry = y - (y / h) * h;
+    x = (rx < 0) ? rx + w : rx;
+    y = (ry < 0) ? ry + h : ry;
+    if (x < 0) x = 0;
+    if (x > w - 1) x = w - 1;
+    if (y < 0) y = 0;
+    if (y > h - 1) y = h - 1;
+    const unsigned char* c = sc.texels + 4 * ((size_t)info.x + (size_t)y * w + x);
+    return mk3(c[0] * inv, c[1] * inv, c[2] * inv);
+}
+__device__ __forceinline__ f3 material_albedo(const SceneDev& sc, const Material& m, f2 uv) {
+    if (m.textureIdx == -1) return ld3(m.diffuse);
+    const int4 info = sc.tex_info[m.textureIdx];
+    float xx = info.y * uv.x;
+    float yy = info.z * uv.y;
+    int x = floorf(xx);
+    int y = floorf(yy);
+    float dx = fabsf(xx - x);
+    float dy = fabsf(yy - y);
+    f3 c00 = tex_texel(sc, info, x, y), c10 = tex_texel(sc, info, x + 1, y), c01 = tex_texel(sc, info, x, y + 1), c11 = tex_texel(sc, info, x + 1, y + 1);
+    return (1 - dy) * ((1 - dx) * c00 + dx * c10) + dy * ((1 - dx) * c01 + dx * c11);
+}
 
 // Epilogue of Triangle::Intersect (src/mesh.h:68-95) / Sphere::Intersect (src/sphere.h:74-91), evaluated once
 // for the final hit from (t, prim, b1, b2).
@@ -35,9 +63,22 @@ __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, 
     h.pos = o + t * d;
     if (s.type == 0) {
         h.nor = normalize(ld3(s.n1) * (1.f - b1 - b2) + ld3(s.n2) * b1 + ld3(s.n3) * b2);
+        h.uv = mk2(s.uv1[0], s.uv1[1]) * (1.f - b1 - b2) + mk2(s.uv2[0], s.uv2[1]) * b1 + mk2(s.uv3[0], s.uv3[1]) * b2;
         h.dpdu = normalize(cross(h.nor, ld3(s.ndpdv)));
-    } else {
+    } else if (s.type == 2) {                                            // hair segment, src/line.h:74-83
+        h.nor = -d;
+        h.uv = mk2(b1, b2);
+        f3 dpdv;
+        make_coordinate(h.nor, h.dpdu, dpdv);
+    } else {                                                             // sphere, src/sphere.h:74-91
         h.nor = normalize(h.pos - ld3(s.n1));
+        const f3 normal = h.nor;
+        float costheta = dot(normal, mk3(0.f, 1.f, 0.f));
+        float v = acosf(costheta) * kInvPi;
+        float cosphi = dot(mk3(1.f, 0.f, 0.f), mk3(normal.x, 0.f, normal.z));
+        float phi = acosf(cosphi);
+        phi = normal.z > 0.f ? kTwoPi - phi : phi;
+        h.uv = mk2(phi * kInvTwoPi, v);
         h.dpdu = normalize(mk3(-kTwoPi * h.pos.y, kTwoPi * h.pos.x, 0));
     }
     h.matIdx = s.matIdx; h.lightIdx = s.lightIdx; h.mediumInside = s.mediumInside; h.mediumOutside = s.mediumOutside;
@@ -46,7 +87,7 @@ __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, 
 __device__ __forceinline__ f3 hit_normal(const SceneDev& sc, f3 pos, int prim, float b1, float b2) {
     const WShade& s = sc.shade[prim];
     if (s.type == 0) return normalize(ld3(s.n1) * (1.f - b1 - b2) + ld3(s.n2) * b1 + ld3(s.n3) * b2);
-    return normalize(pos - ld3(s.n1));
+    return normalize(pos - ld3(s.n1));     // sphere (hair segments never carry a light, so their normal is not needed here)
 }
 
 // Infinite::getTexel / getTexelBilinear (src/infinite.h:66-94)
@@ -375,7 +416,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                 } else {
                     Material mat = sc.mats[h.matIdx];
                     if (MATS == kMatsLambertOnly) mat.type = MT_LAMBERTIAN;    // scene-level fact: drops the other BSDFs
-                    const f3 albedo = ld3(mat.diffuse);                                         // GetTexel, textureIdx == -1
+                    const f3 albedo = material_albedo(sc, mat, h.uv);                          // GetTexel, :341-359
                     const f3 wo = -d;
                     if (!is_delta(mat.type)) {                                                  // :925-995
                         float u = rng_next(rng);

@@ -61,6 +61,31 @@ __device__ __forceinline__ int prim_test(const float4 q0, const float4 q1, const
         if (tt < tmin || tt > tmax) return 0;
         t_out = tt; b1_out = b1; b2_out = b2;
         return 1;
+    } else if (__float_as_int(q2.y) == 2) {      // hair segment, Line::Intersect (src/line.h:33-86)
+        f3 p0 = mk3(q0.x, q0.y, q0.z), p1 = mk3(q0.w, q1.x, q1.y);
+        float width0 = q1.z, width1 = q1.w;
+        f3 u = d;
+        f3 v = p1 - p0;
+        f3 w = o - p0;
+        float a = dot(u, u);
+        float b = dot(u, v);
+        float c = dot(v, v);
+        float dd = dot(u, w);
+        float e = dot(v, w);
+        float det = a * c - b * b;
+        if (det == 0) return 0;
+        float t = (b * e - c * dd) / det;
+        float s = (a * e - b * dd) / det;
+        if (t < tmin || t > tmax) return 0;
+        s = clampf(s, 0.f, 1.f);
+        f3 pr = o + d * t;
+        f3 pl = p0 + (p1 - p0) * s;
+        f3 prl = pr - pl;
+        float d2 = dot(prl, prl);
+        float r = width0 * (1 - s) + width1 * s;
+        if (d2 > r * r) return 0;
+        t_out = t; b1_out = s; b2_out = sqrtf(d2) / r;          // (b1, b2) carry the segment uv (src/line.h:77)
+        return 1;
     } else {                                     // sphere: q0 = centre.xyz, radius
         f3 op = o - mk3(q0.x, q0.y, q0.z);
         float radius = q0.w;

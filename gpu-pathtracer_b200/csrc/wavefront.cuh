@@ -23,8 +23,11 @@ static_assert(sizeof(WNode) == 64, "WNode");
 constexpr int kEmptyChild = 0x7fffffff;
 
 // Intersection record per primitive (leaf order), 48 B: v0, e1 = v1-v0, e2 = v2-v0 for Moeller-Trumbore
-// (src/mesh.h:45-66 recomputes the edges per test from a 176-B Primitive), or centre+radius for a sphere.
-//   q0 = v0.xyz, e1.x   q1 = e1.yz, e2.xy   q2 = e2.z, type(bits), last-in-leaf(bits), -
+// (src/mesh.h:45-66 recomputes the edges per test from a 176-B Primitive), or centre+radius for a sphere, or the
+// end points and radii of a hair segment (src/line.h:8).
+//   triangle: q0 = v0.xyz, e1.x   q1 = e1.yz, e2.xy   q2 = e2.z, type(bits) = 0, last-in-leaf(bits), -
+//   sphere:   q0 = centre.xyz, radius                 q2 = -, type = 1, last, -
+//   line:     q0 = p0.xyz, p1.x   q1 = p1.yz, width0, width1   q2 = -, type = 2, last, -
 struct WPrim { float4 q0, q1, q2; };
 static_assert(sizeof(WPrim) == 48, "WPrim");
 
@@ -60,6 +63,8 @@ struct WInfinite {                  // src/infinite.h:6 with a device texel poin
 struct SceneDev {
     const WNode* nodes; const WPrim* prims; const WShade* shade; const WLight* lights;
     const Material* mats; const WMedium* mediums; const float* cdf;
+    const unsigned char* texels;    // all uchar4 textures back to back (src/texture.h:9)
+    const int4* tex_info;           // per texture: {first texel, width, height, -}
     WInfinite inf;
     float root_min[3], root_max[3];
     int32_t n_nodes, n_prims, n_lights, n_cdf, n_mats, n_mediums;

@@ -38,6 +38,7 @@ class SceneArrays:
     infinite: np.ndarray = None        # 1 x Infinite or None
     infinite_texels: np.ndarray = None  # (h, w, 3) float32, kept alive for infinite.data
     root_box: np.ndarray = None
+    textures: list = field(default_factory=list)   # (h, w, 4) uint8 arrays — Texture::data (src/texture.h:9)
     name: str = ""
     meta: dict = field(default_factory=dict)
 
@@ -166,13 +167,26 @@ def make_homogeneous_medium(sigmaA, sigmaS, g=0.0, scale=1.0):
 
 
 # ------------------------------------------------------------------------------------------------ assembly
+def line_prims(p0, p1, width0, width1, mat_idx):
+    """Hair segments (src/line.h:8): arrays of end points (n, 3) and radii (n,)."""
+    n = len(p0)
+    p = np.zeros(n, L.PrimitiveLine)
+    p["type"] = L.GT_LINES
+    ln = p["line"]
+    ln["p0"] = np.asarray(p0, F); ln["p1"] = np.asarray(p1, F)
+    ln["width0"] = np.asarray(width0, F); ln["width1"] = np.asarray(width1, F)
+    ln["matIdx"] = mat_idx
+    p["line"] = ln
+    return p.view(L.Primitive)
+
+
 def _default_prep():
     from . import _lib
     return _lib.HostPrep()
 
 
 def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials, mediums, prims, lights,
-             infinite=None, infinite_texels=None, prep=None, meta=None):
+             infinite=None, infinite_texels=None, prep=None, meta=None, textures=None):
     """Scene::Init (src/scene.h:50-82): BVH over all primitives, infinite.Init(root_box), light CDF; plus the
     camera construction of src/main.cpp:268-270."""
     prep = prep or _default_prep()
@@ -187,7 +201,8 @@ def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials
                        camera=camera, prims=prims_o, nodes=nodes,
                        materials=np.ascontiguousarray(materials), mediums=np.ascontiguousarray(mediums),
                        lights=lights, light_distribution=lightdist, infinite=infinite,
-                       infinite_texels=infinite_texels, root_box=root_box, name=name, meta=meta or {})
+                       infinite_texels=infinite_texels, root_box=root_box, name=name, meta=meta or {},
+                       textures=[np.ascontiguousarray(t, np.uint8) for t in (textures or [])])
 
 
 def load_scene_json(path, prep=None, overrides=None):
@@ -421,3 +436,44 @@ def random_triangles(n_tris=1_000_000, width=2048, height=2048, max_depth=8, see
     return assemble(f"random_tris_{n_tris}", width, height, 0.001, "pt", max_depth, cam, mats, np.zeros(0, L.Medium),
                     prims, np.zeros(0, L.Area), infinite=inf, infinite_texels=tex, prep=prep,
                     meta={"seed": seed, "n_tris": n_tris})
+
+
+def checker_texture(w=64, h=32, seed=7):
+    """A seeded uchar4 test texture: coloured checker with per-texel noise (exercises the bilinear footprint)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.where(((xx // 8 + yy // 8) % 2)[..., None] == 0, np.array([230, 60, 40]), np.array([40, 90, 220]))
+    t = np.zeros((h, w, 4), np.uint8)
+    t[..., :3] = np.clip(base + rng.randint(-30, 30, (h, w, 3)), 0, 255)
+    t[..., 3] = 255
+    return t
+
+
+def cornell_textured_hair(width=256, height=256, max_depth=6, n_hair=400, seed=11, prep=None):
+    """SURVEY 8(f).2 widening case: the C1 Cornell box with textured floor / back wall (bilinear uchar4 GetTexel,
+    src/pathtracer.cu:324-359), a textured substrate box, and a tuft of `Line` hair segments (src/line.h:33) on the
+    short box.  Built from the same OBJ files; uv come from their `vt` records."""
+    base = cornell_pt(width, height, max_depth, prep=prep)
+    prims = base.prims.copy()
+    mats = np.concatenate([base.materials, make_material("lambertian", diffuse=(1, 1, 1)),
+                           make_material("substrate", diffuse=(1, 1, 1), specular=(0.04, 0.04, 0.04), alphaU=0.2, alphaV=0.2),
+                           make_material("lambertian", diffuse=(0.35, 0.25, 0.12))])
+    i_tex_l, i_tex_s, i_hair = len(base.materials), len(base.materials) + 1, len(base.materials) + 2
+    mats["textureIdx"][i_tex_l] = 0
+    mats["textureIdx"][i_tex_s] = 1
+    t = prims["triangle"]
+    v = np.stack([t["v1"]["v"], t["v2"]["v"], t["v3"]["v"]], 1)
+    is_tri = prims["type"] == L.GT_TRIANGLE
+    floor = is_tri & (np.abs(v[..., 1]).max(1) < 1e-6)
+    back = is_tri & (np.abs(v[..., 2] + 1.0).max(1) < 1e-6)
+    tall = is_tri & (v[..., 1].max(1) > 0.9) & (v[..., 1].max(1) < 1.5) & (t["lightIdx"] == -1) & ~back
+    t["matIdx"] = np.where(floor | back, i_tex_l, np.where(tall, i_tex_s, t["matIdx"]))
+    prims["triangle"] = t
+    rng = np.random.RandomState(seed)
+    root = np.stack([rng.uniform(-0.1, 0.55, n_hair), np.full(n_hair, 0.6), rng.uniform(-0.1, 0.6, n_hair)], 1)
+    tip = root + np.stack([rng.normal(0, 0.05, n_hair), rng.uniform(0.15, 0.35, n_hair), rng.normal(0, 0.05, n_hair)], 1)
+    hair = line_prims(root, tip, np.full(n_hair, 0.006), np.full(n_hair, 0.001), i_hair)
+    cam = {"position": [0, 1.0, 6.8], "lookat": [0, 1.0, 0], "up": [0, 1, 0], "fov": 19.5}
+    return assemble("cornell_textured_hair", width, height, base.epsilon, "pt", max_depth, cam, mats, base.mediums,
+                    L.cat([prims, hair], L.Primitive), base.lights, prep=prep,
+                    textures=[checker_texture(64, 32, 7), checker_texture(16, 48, 8)])

@@ -41,7 +41,7 @@ extern "C" {
 #define B200PT_EINVAL       -1   /* bad argument / unsupported scene feature */
 #define B200PT_ECUDA        -2   /* CUDA runtime error (message in b200pt_last_error) */
 #define B200PT_ENOMEM       -3
-#define B200PT_EUNSUPPORTED -4   /* integrator / primitive / medium type outside the hot path */
+#define B200PT_EUNSUPPORTED -4   /* integrator / medium type outside the hot path (heterogeneous media, lines under vpt) */
 
 /* One uchar4 texture (src/texture.h:9, uploaded at src/pathtracer.cu:2646-2661). */
 typedef struct b200pt_texture {

@@ -62,6 +62,7 @@ def main():
         "vol_caustic_64": lambda: pt.scenes.cornell_vol_caustic(64, 64, 17, prep=prep),
         "veach_standin_64x48": lambda: pt.scenes.veach_standin(64, 48, 17, prep=prep),
         "random_tris_20k_64": lambda: pt.scenes.random_triangles(20000, 64, 64, 8, prep=prep),
+        "cornell_textured_hair_64": lambda: pt.scenes.cornell_textured_hair(64, 64, 6, prep=prep),
     }
     for name, mk in scenes.items():
         s = mk()

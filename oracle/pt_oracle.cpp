@@ -38,6 +38,8 @@ struct SceneO {
     RefInfinite inf; bool has_inf = false;
     std::vector<float> inf_texels;
     std::vector<float> cdf;
+    struct Tex { std::vector<unsigned char> rgba; int w, h; };
+    std::vector<Tex> textures;
     int integrator = 1, max_depth = 5;
     float eps = 0.001f;
     unsigned w = 0, h = 0;
@@ -154,10 +156,48 @@ bool sphere_intersect(const RefSphere& S, Ray& ray, Isect* isect) {
     return true;
 }
 
+// Line::Intersect, src/line.h:33-86 (hair segment: closest approach of ray and segment against the lerped radius)
+bool line_intersect(const RefLine& L, Ray& ray, Isect* isect) {
+    f3 u = ray.d;
+    f3 v = ld3(L.p1) - ld3(L.p0);
+    f3 w = ray.o - ld3(L.p0);
+    float a = dot(u, u);
+    float b = dot(u, v);
+    float c = dot(v, v);
+    float d = dot(u, w);
+    float e = dot(v, w);
+    float det = a * c - b * b;
+    if (det == 0) return false;
+    float t = (b * e - c * d) / det;
+    float s = (a * e - b * d) / det;
+    if (t < ray.tmin || t > ray.tmax) return false;
+    s = clampf(s, 0.f, 1.f);
+    f3 pr = ray.o + ray.d * t;
+    f3 pl = ld3(L.p0) + (ld3(L.p1) - ld3(L.p0)) * s;
+    f3 prl = pr - pl;
+    float d2 = dot(prl, prl);
+    float r = L.width0 * (1 - s) + L.width1 * s;
+    if (d2 > r * r) return false;
+    ray.tmax = t;
+    if (isect) {
+        isect->pos = at(ray, t);
+        isect->nor = -ray.d;
+        isect->uv = mk2(s, sqrtf(d2) / r);
+        f3 dpdu, dpdv;
+        make_coordinate(isect->nor, dpdu, dpdv);
+        isect->dpdu = dpdu;
+        isect->matIdx = L.matIdx;
+        isect->lightIdx = -1;
+        isect->bssrdf = -1;
+        // mediumInside / mediumOutside are left untouched by the reference (only `pt` scenes use lines)
+    }
+    return true;
+}
+
 bool prim_intersect(const RefPrimitive& p, Ray& ray, Isect* isect) {
     if (p.type == REF_GT_TRIANGLE) return triangle_intersect(p.u.triangle, ray, isect);
     if (p.type == REF_GT_SPHERE) return sphere_intersect(p.u.sphere, ray, isect);
-    return false;   // GT_LINES: outside the hot path's configs
+    return line_intersect(p.u.line, ray, isect);
 }
 
 // Intersect (closest hit), src/pathtracer.cu:214-255: fixed left-then-right DFS over LinearBVHNode[]
@@ -347,7 +387,33 @@ f3 transmittance(Ray ray) {
 }
 
 const RefMaterial& material(int idx) { return g->mats[idx]; }
-f3 albedo_of(const RefMaterial& m) { return ld3(m.diffuse); }    // GetTexel with textureIdx == -1, src/pathtracer.cu:341-343
+// getTexel / GetTexel, src/pathtracer.cu:324-359: constant colour, or wrap+clamp bilinear lookup of a uchar4 texture
+f3 texel_at(const SceneO::Tex& T, int x, int y) {
+    const float inv = 1.f / 255.f;
+    const int w = T.w, h = T.h;
+    float rx = x - (x / w) * w;
+    float ry = y - (y / h) * h;
+    x = (rx < 0) ? rx + w : rx;
+    y = (ry < 0) ? ry + h : ry;
+    if (x < 0) x = 0;
+    if (x > w - 1) x = w - 1;
+    if (y < 0) y = 0;
+    if (y > h - 1) y = h - 1;
+    const unsigned char* c = &T.rgba[4 * ((size_t)y * w + x)];
+    return mk3(c[0] * inv, c[1] * inv, c[2] * inv);
+}
+f3 albedo_of(const RefMaterial& m, f2 uv) {
+    if (m.textureIdx == -1) return ld3(m.diffuse);
+    const SceneO::Tex& T = g->textures[m.textureIdx];
+    float xx = T.w * uv.x;
+    float yy = T.h * uv.y;
+    int x = floorf(xx);
+    int y = floorf(yy);
+    float dx = fabsf(xx - x);
+    float dy = fabsf(yy - y);
+    f3 c00 = texel_at(T, x, y), c10 = texel_at(T, x + 1, y), c01 = texel_at(T, x, y + 1), c11 = texel_at(T, x + 1, y + 1);
+    return (1 - dy) * ((1 - dx) * c00 + dx * c10) + dy * ((1 - dx) * c01 + dx * c11);
+}
 const Material& M(const RefMaterial& m) { return *reinterpret_cast<const Material*>(&m); }
 const Camera& C(const RefCamera& c) { return *reinterpret_cast<const Camera*>(&c); }
 
@@ -376,7 +442,7 @@ f3 direct_light(const Ray& r, const Isect& isect, const RefMaterial& mat, uint32
             Ray sr = shadowRay;
             if (!intersect_p(sr)) {
                 f3 fr; float samplePdf;
-                eval_bsdf(M(mat), albedo_of(mat), wo, shadowRay.d, nor, dpdu, fr, samplePdf);
+                eval_bsdf(M(mat), albedo_of(mat, isect.uv), wo, shadowRay.d, nor, dpdu, fr, samplePdf);
                 float weight = power_heuristic(1, lightPdf * choicePdf, 1, samplePdf);
                 Ld += weight * fr * radiance * fabsf(dot(nor, shadowRay.d)) / (lightPdf * choicePdf);
             }
@@ -384,7 +450,7 @@ f3 direct_light(const Ray& r, const Isect& isect, const RefMaterial& mat, uint32
     } else {
         if (!is_black(radiance)) {
             f3 fr; float samplePdf;
-            eval_bsdf(M(mat), albedo_of(mat), wo, shadowRay.d, nor, dpdu, fr, samplePdf);
+            eval_bsdf(M(mat), albedo_of(mat, isect.uv), wo, shadowRay.d, nor, dpdu, fr, samplePdf);
             f3 tr = transmittance(shadowRay);
             float weight = power_heuristic(1, lightPdf * choicePdf, 1, samplePdf);
             Ld += weight * tr * fr * radiance * fabsf(dot(nor, shadowRay.d)) / (lightPdf * choicePdf);
@@ -393,7 +459,7 @@ f3 direct_light(const Ray& r, const Isect& isect, const RefMaterial& mat, uint32
     float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);   // device evaluates the argument list left to right
     f3 us = mk3(s0, s1, s2);
     f3 out, fr; float pdf;
-    sample_bsdf(M(mat), albedo_of(mat), wo, nor, dpdu, us, out, fr, pdf);
+    sample_bsdf(M(mat), albedo_of(mat, isect.uv), wo, nor, dpdu, us, out, fr, pdf);
     if (!(is_black(fr) || pdf == 0)) {
         Isect lightIsect; lightIsect.lightIdx = -1;
         Ray lightRay = mk_ray(pos, out, r.medium, g->eps);
@@ -467,7 +533,7 @@ bool path_sample(unsigned x, unsigned y, unsigned pixel, unsigned iter, f3& Li_o
         }
         float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);
         f3 out, fr; float pdf;
-        sample_bsdf(M(mat), albedo_of(mat), -r.d, nor, dpdu, mk3(c0, c1, c2), out, fr, pdf);
+        sample_bsdf(M(mat), albedo_of(mat, isect.uv), -r.d, nor, dpdu, mk3(c0, c1, c2), out, fr, pdf);
         if (is_black(fr)) break;
         beta *= fr * fabsf(dot(nor, out)) / pdf;
         specular = is_delta(mat.type);
@@ -547,7 +613,7 @@ bool volpath_sample(unsigned x, unsigned y, unsigned pixel, unsigned iter, f3& L
             }
             float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);
             f3 out, fr; float pdf;
-            sample_bsdf(M(mat), albedo_of(mat), -r.d, nor, dpdu, mk3(c0, c1, c2), out, fr, pdf);
+            sample_bsdf(M(mat), albedo_of(mat, isect.uv), -r.d, nor, dpdu, mk3(c0, c1, c2), out, fr, pdf);
             if (is_black(fr)) break;
             beta *= fr * fabsf(dot(nor, out)) / pdf;
             specular = is_delta(mat.type);
@@ -583,6 +649,12 @@ extern "C" int oracle_begin(const b200pt_scene_view* v, unsigned w, unsigned h, 
         if (g->inf.isvalid) g->inf_texels.assign(g->inf.data, g->inf.data + 3 * (size_t)g->inf.width * g->inf.height);
     }
     g->cdf.assign(v->light_distribution, v->light_distribution + v->n_light_distribution);
+    for (int i = 0; i < v->n_textures; ++i) {
+        SceneO::Tex T; T.w = v->textures[i].width; T.h = v->textures[i].height;
+        const unsigned char* src = (const unsigned char*)v->textures[i].texels;
+        T.rgba.assign(src, src + 4 * (size_t)T.w * T.h);
+        g->textures.push_back(T);
+    }
     g->integrator = v->integrator_type; g->max_depth = v->max_depth; g->eps = eps; g->w = w; g->h = h;
     g->acc.assign((size_t)w * h, mk3(0, 0, 0));
     g->color.assign((size_t)w * h, mk3(0, 0, 0));
@@ -639,14 +711,14 @@ extern "C" void oracle_sample_bsdf(const void* mat72, const float* in3, const fl
                                    const float* u3, float* out3, float* fr3, float* pdf) {
     RefMaterial m; std::memcpy(&m, mat72, sizeof(m));
     f3 out = mk3(0, 0, 0), fr = mk3(0, 0, 0); float p = 0;
-    sample_bsdf(M(m), albedo_of(m), ld3(in3), ld3(nor3), ld3(dpdu3), ld3(u3), out, fr, p);
+    sample_bsdf(M(m), albedo_of(m, mk2(uv2[0], uv2[1])), ld3(in3), ld3(nor3), ld3(dpdu3), ld3(u3), out, fr, p);
     out3[0] = out.x; out3[1] = out.y; out3[2] = out.z; fr3[0] = fr.x; fr3[1] = fr.y; fr3[2] = fr.z; *pdf = p;
 }
 extern "C" void oracle_fr(const void* mat72, const float* in3, const float* out3, const float* nor3, const float* uv2,
                           const float* dpdu3, float* fr3, float* pdf) {
     RefMaterial m; std::memcpy(&m, mat72, sizeof(m));
     f3 fr = mk3(0, 0, 0); float p = 0;
-    eval_bsdf(M(m), albedo_of(m), ld3(in3), ld3(out3), ld3(nor3), ld3(dpdu3), fr, p);
+    eval_bsdf(M(m), albedo_of(m, mk2(uv2[0], uv2[1])), ld3(in3), ld3(out3), ld3(nor3), ld3(dpdu3), fr, p);
     fr3[0] = fr.x; fr3[1] = fr.y; fr3[2] = fr.z; *pdf = p;
 }
 extern "C" void oracle_camera_ray(const void* cam104, float x, float y, float ax, float ay, float* o3, float* d3) {

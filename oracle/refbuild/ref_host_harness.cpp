@@ -39,8 +39,15 @@ extern "C" int refhost_begin(const b200pt_scene_view* v, unsigned w, unsigned h,
     kernel_lights = s.lights.data();
     g_inf = s.infinite;
     kernel_infinite = &g_inf;
-    kernel_textures = nullptr;   // textured materials are a "next" row; host harness covers constant colour
-    kernel_texture_size = nullptr;
+    // what BeginRender uploads for textures (src/pathtracer.cu:2646-2661): per-texture texel pointers + (w, h) pairs
+    static std::vector<uchar4*> tex_ptrs; static std::vector<int> tex_sizes;
+    tex_ptrs.clear(); tex_sizes.clear();
+    for (size_t i = 0; i < s.textures.size(); ++i) {
+        tex_ptrs.push_back(s.textures[i].data.data());
+        tex_sizes.push_back(s.textures[i].width); tex_sizes.push_back(s.textures[i].height);
+    }
+    kernel_textures = tex_ptrs.empty() ? nullptr : tex_ptrs.data();
+    kernel_texture_size = tex_sizes.empty() ? nullptr : tex_sizes.data();
     kernel_light_distribution = s.lightDistribution.data();
     kernel_light_size = (int)s.lights.size();
     kernel_light_distribution_size = (int)s.lightDistribution.size();

@@ -19,6 +19,7 @@ SCENES = {
     "veach_c3": (lambda: pt.scenes.veach_standin(256, 192, 17), 32),
     "random_tris_c4": (lambda: pt.scenes.random_triangles(50000, 256, 256, 8), 16),
     "vol_caustic_c5": (lambda: pt.scenes.cornell_vol_caustic(256, 256, 17), 32),
+    "textured_hair": (lambda: pt.scenes.cornell_textured_hair(256, 256, 6), 32),     # textures + lines
 }
 
 
@@ -60,7 +61,7 @@ def test_matches_reference_cuda_integrator(name):
     assert (_rmse(tone, ref_tone) <= TOL).all()
 
 
-@pytest.mark.parametrize("name", ["cornell_c1", "veach_c3", "vol_caustic_c5", "random_tris_c4"])
+@pytest.mark.parametrize("name", ["cornell_c1", "veach_c3", "vol_caustic_c5", "random_tris_c4", "textured_hair"])
 def test_matches_cpu_oracle(name, oracle):
     mk, _ = SCENES[name]
     s = mk()

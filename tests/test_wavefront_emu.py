@@ -29,6 +29,7 @@ SCENES = {
     "vol_caustic": lambda: pt.scenes.cornell_vol_caustic(64, 64, 17),
     "veach": lambda: pt.scenes.veach_standin(64, 48, 17),
     "random_tris": lambda: pt.scenes.random_triangles(5000, 64, 64, 8),
+    "textured_hair": lambda: pt.scenes.cornell_textured_hair(64, 64, 6),            # textures + lines
 }
 
 
