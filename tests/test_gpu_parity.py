@@ -181,7 +181,7 @@ def test_full_config_c2_1024spp_matches_reference_cuda():
 @pytest.mark.parametrize("name,mk,spp", [
     ("veach_c3_full", lambda: pt.scenes.veach_standin(768, 576, 17), 64),
     ("vol_caustic_c5_full", lambda: pt.scenes.cornell_vol_caustic(512, 512, 17), 256),
-    ("random_tris_c4_200k", lambda: pt.scenes.random_triangles(200_000, 512, 512, 8), 64),
+    ("random_tris_c4_200k", lambda: pt.scenes.random_triangles(200_000, 512, 512, 8), 256),   # configs[3] is quoted at 256 spp
 ])
 def test_full_size_configs_match_reference_cuda(name, mk, spp):
     s = mk()
