@@ -53,7 +53,7 @@ __device__ __forceinline__ f3 material_albedo(const SceneDev& sc, const Material
     float dx = fabsf(xx - x);
     float dy = fabsf(yy - y);
     f3 c00 = tex_texel(sc, info, x, y), c10 = tex_texel(sc, info, x + 1, y), c01 = tex_texel(sc, info, x, y + 1), c11 = tex_texel(sc, info, x + 1, y + 1);
-    return (1 - dy) * ((1 - dx) * c00 + dx * c10) + dy * ((1 - dx) * c01 + dx * c11);
+    return lin2(1 - dy, lin2(1 - dx, c00, dx, c10), dy, lin2(1 - dx, c01, dx, c11));
 }
 
 // Epilogue of Triangle::Intersect (src/mesh.h:68-95) / Sphere::Intersect (src/sphere.h:74-91), evaluated once
@@ -62,7 +62,7 @@ __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, 
     const WShade& s = sc.shade[prim];
     h.pos = o + t * d;
     if (s.type == 0) {
-        h.nor = normalize(ld3(s.n1) * (1.f - b1 - b2) + ld3(s.n2) * b1 + ld3(s.n3) * b2);
+                h.nor = normalize(lin3(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
         h.uv = mk2(s.uv1[0], s.uv1[1]) * (1.f - b1 - b2) + mk2(s.uv2[0], s.uv2[1]) * b1 + mk2(s.uv3[0], s.uv3[1]) * b2;
         h.dpdu = normalize(cross(h.nor, ld3(s.ndpdv)));
     } else if (s.type == 2) {                                            // hair segment, src/line.h:74-83
@@ -86,7 +86,7 @@ __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, 
 // shading normal only (MIS hit, :962)
 __device__ __forceinline__ f3 hit_normal(const SceneDev& sc, f3 pos, int prim, float b1, float b2) {
     const WShade& s = sc.shade[prim];
-    if (s.type == 0) return normalize(ld3(s.n1) * (1.f - b1 - b2) + ld3(s.n2) * b1 + ld3(s.n3) * b2);
+    if (s.type == 0) return normalize(lin3(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
     return normalize(pos - ld3(s.n1));     // sphere (hair segments never carry a light, so their normal is not needed here)
 }
 
@@ -112,7 +112,7 @@ __device__ __forceinline__ f3 inf_bilinear(const WInfinite& I, f2 uv) {
     float dx = fabsf(xx - x);
     float dy = fabsf(yy - y);
     f3 c00 = inf_texel(I, x, y), c10 = inf_texel(I, x + 1, y), c01 = inf_texel(I, x, y + 1), c11 = inf_texel(I, x + 1, y + 1);
-    return (1 - dy) * ((1 - dx) * c00 + dx * c10) + dy * ((1 - dx) * c01 + dx * c11);
+    return lin2(1 - dy, lin2(1 - dx, c00, dx, c10), dy, lin2(1 - dx, c01, dx, c11));
 }
 // direction -> lat-long uv, shared by Infinite::Le (:47) and Infinite::SampleLight (:17)
 __device__ __forceinline__ f2 inf_dir_to_uv(const WInfinite& I, f3 dir) {
@@ -153,8 +153,8 @@ struct LightSample { f3 radiance, dir; float tmax, pdf; };
 // Area::SampleLight (src/area.h:14) -> Triangle::SampleShape (src/mesh.h:100)
 __device__ __forceinline__ void area_sample(const WLight& L, f3 pos, float ux, float uy, float eps, LightSample& ls) {
     f2 uv = uniform_triangle(ux, uy);
-    f3 p = uv.x * ld3(L.v1) + uv.y * ld3(L.v2) + (1 - uv.x - uv.y) * ld3(L.v3);
-    f3 normal = normalize(uv.x * ld3(L.n1) + uv.y * ld3(L.n2) + (1 - uv.x - uv.y) * ld3(L.n3));
+    f3 p = lin3(uv.x, ld3(L.v1), uv.y, ld3(L.v2), 1 - uv.x - uv.y, ld3(L.v3));
+    f3 normal = normalize(lin3(uv.x, ld3(L.n1), uv.y, ld3(L.n2), 1 - uv.x - uv.y, ld3(L.n3)));
     f3 dir = p - pos;
     float pdf = 1.f / (L.area * fabsf(dot(normal, normalize(dir)))) * dot(dir, dir);
     if (dot(normal, dir) >= 0.f) pdf = 0.f;

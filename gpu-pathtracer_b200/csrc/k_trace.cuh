@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                             if (invisible) {
                                 const WShade& s = a.sc.shade[hprim];
                                 f3 nor;
-                                if (s.type == 0) nor = normalize(ld3(s.n1) * (1.f - hb1 - hb2) + ld3(s.n2) * hb1 + ld3(s.n3) * hb2);
+                                if (s.type == 0) nor = normalize(lin3(1.f - hb1 - hb2, ld3(s.n1), hb1, ld3(s.n2), hb2, ld3(s.n3)));
                                 else nor = normalize((o + seg * d) - ld3(s.n1));
                                 medium = dot(d, nor) > 0 ? s.mediumOutside : s.mediumInside;
                                 remain -= seg;
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
             if (!invisible) break;
             const WShade& sh = a.sc.shade[hprim];
             f3 nor;
-            if (sh.type == 0) nor = normalize(ld3(sh.n1) * (1.f - hb1 - hb2) + ld3(sh.n2) * hb1 + ld3(sh.n3) * hb2);
+            if (sh.type == 0) nor = normalize(lin3(1.f - hb1 - hb2, ld3(sh.n1), hb1, ld3(sh.n2), hb2, ld3(sh.n3)));
             else nor = normalize((o + seg * d) - ld3(sh.n1));
             medium = dot(d, nor) > 0 ? sh.mediumOutside : sh.mediumInside;
             remain -= seg;

@@ -38,7 +38,11 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--dump", default="")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to b200pt_set_option")
+    ap.add_argument("--lib", default="", help="alternative libb200pt build to load (A/B experiments)")
     a = ap.parse_args()
+    if a.lib:
+        from gpu_pathtracer_b200 import _lib
+        _lib.load(a.lib)
     t0 = time.time()
     s = make(a.scene, a.size)
     print(f"scene {s.name}: {len(s.prims)} prims, {len(s.nodes)} nodes, {s.width}x{s.height}, depth {s.max_depth}, built in {time.time() - t0:.1f}s", flush=True)
