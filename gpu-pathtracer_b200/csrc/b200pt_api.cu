@@ -495,8 +495,11 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     // persistent traversal grid: resident CTAs per SM x SM count
     int per_sm = 0;
     size_t smem = (size_t)c->stage_nodes + c->stage_prims + kTraceStackBytes;
-    if (c->small_scene) smem = (size_t)c->small_prim_bytes + (size_t)c->n_leaves * 32;
-    if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
+    if (c->small_scene) {
+        smem = (size_t)c->small_prim_bytes + (size_t)c->n_leaves * 32;
+        if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_small<true>, kTraceThreads, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_small<false>, kTraceThreads, smem);
+    } else if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
     if (per_sm <= 0) per_sm = 1;
     c->trace_blocks = c->num_sms * per_sm;

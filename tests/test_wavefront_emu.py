@@ -128,3 +128,39 @@ def test_error_codes(emu):
     bad = s.prims.copy(); bad["triangle"]["matIdx"][0] = 99
     view.prims = bad.ctypes.data
     assert lib.b200pt_create(C.byref(view), 64, 64, 0.001, 0, None, C.byref(ctx)) == -1
+
+
+@pytest.mark.parametrize("lanes", ["1", "3"])
+def test_lane_count_does_not_change_the_image(lanes, emu, monkeypatch):
+    """A context splits its tiles over B200PT_LANES independent wavefronts (default 2); any lane count must give
+    the bits of the default."""
+    s = pt.scenes.cornell_pt(128, 64, 6)
+    with pt.PathTracer(s) as r:
+        tone = r.render(3, reset=True, spp=3); acc = r.accum()
+    monkeypatch.setenv("B200PT_LANES", lanes)
+    with pt.PathTracer(s) as r:
+        tone2 = r.render(3, reset=True, spp=3); acc2 = r.accum()
+        assert r.stats()["samples"] == 3 * 128 * 64
+    assert np.array_equal(_bits(acc), _bits(acc2))
+    assert np.array_equal(_bits(tone), _bits(tone2))
+
+
+def test_scene_validation_errors(emu):
+    """Unsupported / malformed scene content is rejected at create, never approximated."""
+    s = pt.scenes.cornell_textured_hair(64, 64, 4, n_hair=20)
+    lib = _lib.load()
+    view, keep = _lib.make_view(s)
+    ctx = C.c_void_p()
+    assert lib.b200pt_create(C.byref(view), 64, 64, 0.001, 0, None, C.byref(ctx)) == 0
+    assert lib.b200pt_destroy(ctx) == 0
+    view.integrator_type = 2                                   # lines are only defined for `pt`
+    assert lib.b200pt_create(C.byref(view), 64, 64, 0.001, 0, None, C.byref(ctx)) == -4
+    assert b"line" in lib.b200pt_last_error()
+    view.integrator_type = 1
+    mats = s.materials.copy(); mats["textureIdx"][0] = 7       # texture index out of range
+    view.materials = mats.ctypes.data
+    assert lib.b200pt_create(C.byref(view), 64, 64, 0.001, 0, None, C.byref(ctx)) == -1
+    v2, keep2 = _lib.make_view(pt.scenes.cornell_vol_caustic(64, 64, 4))
+    med = pt.scenes.cornell_vol_caustic(64, 64, 4).mediums.copy(); med["type"][0] = 1      # heterogeneous medium
+    v2.mediums = med.ctypes.data
+    assert lib.b200pt_create(C.byref(v2), 64, 64, 0.001, 0, None, C.byref(ctx)) == -4
