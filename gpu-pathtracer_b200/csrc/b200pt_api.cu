@@ -459,19 +459,9 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     }
     fill_map(c->map, width, height, sh, nsh, tw, th);
 
-    // lanes: local tile j of this context goes to lane j % kLanes, i.e. lane k is shard (sh + nsh * k) of nsh * kLanes
-    int n_lanes = 2;
-    if (const char* env = getenv("B200PT_LANES")) n_lanes = std::max(1, std::min(8, atoi(env)));
-    if (width % tw || height % th || c->map.n_local_tiles < n_lanes) n_lanes = 1;
-    c->lanes.resize(n_lanes);
-    for (int k = 0; k < n_lanes; ++k) {
-        Lane& L = c->lanes[k];
-        if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B200PT_ECUDA, "stream create failed"));
-        cudaEventCreateWithFlags(&L.ev_poll[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&L.ev_poll[1], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming);
-        if (n_lanes == 1) L.map = c->map;
-        else fill_map(L.map, width, height, sh + nsh * k, nsh * n_lanes, tw, th);
-    }
+    // lane 0's stream carries the scene upload
+    c->lanes.resize(1);
+    if (cudaStreamCreateWithFlags(&c->lanes[0].stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B200PT_ECUDA, "stream create failed"));
     c->stream = c->lanes[0].stream;
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -480,6 +470,21 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     c->sc.eps = epsilon;
     int rc = build_scene(c, scene);
     if (rc) return bail(rc);
+
+    // lanes: local tile j of this context goes to lane j % n_lanes, i.e. lane k is shard (sh + nsh * k) of nsh * n_lanes.
+    // Measured (profiles/r01q_lanes.txt): 3 lanes are best when the flat small-scene kernel traces (C2 +5 %), 2 otherwise.
+    int n_lanes = c->small_scene ? 3 : 2;
+    if (const char* env = getenv("B200PT_LANES")) n_lanes = std::max(1, std::min(8, atoi(env)));
+    if (width % tw || height % th || c->map.n_local_tiles < n_lanes) n_lanes = 1;
+    c->lanes.resize(n_lanes);
+    for (int k = 0; k < n_lanes; ++k) {
+        Lane& L = c->lanes[k];
+        if (k && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B200PT_ECUDA, "stream create failed"));
+        cudaEventCreateWithFlags(&L.ev_poll[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&L.ev_poll[1], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming);
+        if (n_lanes == 1) L.map = c->map;
+        else fill_map(L.map, width, height, sh + nsh * k, nsh * n_lanes, tw, th);
+    }
 
     size_t npix = (size_t)width * height;
     if ((rc = dev_alloc(c, &c->acc, 3 * npix, true))) return bail(rc);
