@@ -41,7 +41,7 @@ struct Lane {
     unsigned long long counter_init[2] = {0, 0};
     std::vector<void*> pool_allocs;       // cudaMalloc'ed pool/queue planes (re-allocated by the "pool" option)
     ShadeArgs sa; TraceArgs ta;
-    int chunk = 0; bool done = false;
+    int chunk = 0; bool done = false, exact_pending = false;
 };
 
 struct b200pt_ctx {
@@ -422,6 +422,8 @@ static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
 // Pool slots per lane: the context total split evenly, never more than 4 slots per pixel of the lane.
 static int lane_pool_size(const b200pt_ctx* c, const Lane& L) {
     int pool = std::max(1024, c->pool_total / (int)c->lanes.size());
+    // a lane whose pixels almost fit gets one slot per pixel: a 1-spp Render call then runs in exact-step mode
+    if (L.map.n_local_pixels > pool && (double)L.map.n_local_pixels <= 1.1 * pool) pool = L.map.n_local_pixels;
     if ((size_t)pool > (size_t)L.map.n_local_pixels * 4) pool = std::max(1024, L.map.n_local_pixels * 4);
     return pool;
 }
@@ -571,7 +573,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (size_t k = 0; k < c->lanes.size(); ++k) {
         Lane& L = c->lanes[k];
-        L.done = L.map.n_local_pixels == 0; L.chunk = 0;
+        L.done = L.map.n_local_pixels == 0; L.chunk = 0; L.exact_pending = false;
         if (L.done) continue;
         if (k) CK(cudaStreamWaitEvent(L.stream, c->ev_fork, 0));
         const size_t need = (size_t)n_iters * L.map.n_local_pixels;
@@ -600,15 +602,24 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         for (Lane& L : c->lanes) {
             if (L.done) continue;
             all_done = false;
-            for (int s = 0; s < c->steps_per_poll; ++s) {
+            // `pt` with every sample of the batch in flight at once (the reference's one-Render-per-frame usage): a path
+            // needs at most max_depth bounces, so exactly max_depth + 1 steps retire everything — launch those and
+            // check once, instead of polling in chunks of steps_per_poll
+            // (`vpt` has no such bound — medium boundaries do not count as bounces — so a single-pass `vpt` batch is
+            // checked synchronously after 8 steps and then every 4)
+            const bool single_pass = L.sa.batch.total <= (unsigned long long)L.pool.n;
+            const bool exact = single_pass && (!c->vol ? L.chunk == 0 : true);
+            const int n_steps = !exact ? c->steps_per_poll : (!c->vol ? c->sc.max_depth + 1 : (L.chunk == 0 ? 8 : 4));
+            for (int s = 0; s < n_steps; ++s) {
                 launch_trace(c, L, L.ta); L.ta.parity ^= 1u;
                 L.sa.parity ^= 1u; launch_shade(c, L, L.sa);
             }
-            *launches += 2.0 * c->steps_per_poll; *steps += c->steps_per_poll;
+            *launches += 2.0 * n_steps; *steps += n_steps;
             const int slot = L.chunk & 1;
             CK(cudaMemcpyAsync(&L.h_counters[slot], L.counters, sizeof(Counters), cudaMemcpyDeviceToHost, L.stream));
             CK(cudaEventRecord(L.ev_poll[slot], L.stream));
-            if (L.chunk >= 1) {
+            if (exact) L.exact_pending = true;
+            else if (L.chunk >= 1) {
                 const int prev = (L.chunk - 1) & 1;
                 CK(cudaEventSynchronize(L.ev_poll[prev]));
                 if (L.h_counters[prev].done_samples >= L.sa.batch.total) L.done = true;
@@ -616,6 +627,13 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
             if (++L.chunk > (1 << 22)) return fail(B200PT_ECUDA, "wavefront did not converge (internal error)");
         }
         if (all_done) break;
+        // exact-step lanes: all lanes have been launched; now wait for their verdicts (normally "done")
+        for (Lane& L : c->lanes) {
+            if (!L.exact_pending) continue;
+            L.exact_pending = false;
+            CK(cudaEventSynchronize(L.ev_poll[(L.chunk - 1) & 1]));
+            if (L.h_counters[(L.chunk - 1) & 1].done_samples >= L.sa.batch.total) L.done = true;
+        }
     }
     for (size_t k = 0; k < c->lanes.size(); ++k) {
         Lane& L = c->lanes[k];
