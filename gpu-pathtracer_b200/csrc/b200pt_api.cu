@@ -383,7 +383,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     if (v->n_light_distribution != expect)
         return fail(B200PT_EINVAL, "light distribution has " + std::to_string(v->n_light_distribution) + " entries, expected " + std::to_string(expect));
     sc.integrator = v->integrator_type; sc.max_depth = v->max_depth;
-    if (v->max_depth < 0 || v->max_depth > 255) return fail(B200PT_EINVAL, "maxDepth must be in [0, 255]");
+    if (v->max_depth < 0 || v->max_depth > 127) return fail(B200PT_EINVAL, "maxDepth must be in [0, 127]");
     c->vol = v->integrator_type == B200PT_IT_VPT;
 
     // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
@@ -406,7 +406,7 @@ static void free_pool(Lane& L) {
 static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
     free_pool(L);
     Pool& p = L.pool;
-    float4** arrs[] = {&p.o_rng, &p.d_flags, &p.beta_s, &p.li_t, &p.shd, &p.misd, &p.ldl, &p.misf, &p.beta_old, &p.hit0, &p.hit1, &p.vis, &p.aux};
+    float4** arrs[] = {&p.o_rng, &p.d_flags, &p.beta_s, &p.li_t, &p.shd, &p.misd, &p.ldl, &p.misf, &p.beta_old, &p.hit0, &p.hit1, &p.vis, &p.aux, &p.pend_o, &p.carry};
     n = (n + 255) & ~255;
     auto grab = [&](void** q, size_t bytes) -> int {
         cudaError_t e = cudaMalloc(q, bytes);

@@ -201,15 +201,15 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
 
     // ---------------------------------------------------------------- loads: the CTA's 128 pool records, all arrays,
     // staged into shared memory by TMA bulk copies (one elected thread issues them, everyone waits on the mbarrier)
-    constexpr int kArrays = VOL ? 12 : 11;
+    constexpr int kArrays = VOL ? 14 : 13;
 #ifndef B200PT_EMULATE
     __shared__ __align__(128) float4 s_rec[kArrays][128];
     __shared__ uint64_t bar;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const float4* src[12] = {a.pool.d_flags, a.pool.o_rng, a.pool.beta_s, a.pool.li_t, a.pool.hit0, a.pool.beta_old,
-                                 a.pool.vis, a.pool.ldl, a.pool.misd, a.pool.misf, a.pool.hit1, a.pool.aux};
+        const float4* src[14] = {a.pool.d_flags, a.pool.o_rng, a.pool.beta_s, a.pool.li_t, a.pool.hit0, a.pool.beta_old,
+                                 a.pool.vis, a.pool.ldl, a.pool.misd, a.pool.misf, a.pool.hit1, a.pool.pend_o, a.pool.carry, a.pool.aux};
         mbar_expect_tx(&bar, (uint32_t)(kArrays * 128 * sizeof(float4)));
 #pragma unroll
         for (int k = 0; k < kArrays; ++k) tma_bulk_g2s(&s_rec[k][0], src[k] + (size_t)blockIdx.x * 128, 128 * sizeof(float4), &bar);
@@ -219,11 +219,13 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     const float4 df = s_rec[0][threadIdx.x], orng = s_rec[1][threadIdx.x], bs = s_rec[2][threadIdx.x], lt4 = s_rec[3][threadIdx.x];
     const float4 h0 = s_rec[4][threadIdx.x], bo = s_rec[5][threadIdx.x], pv = s_rec[6][threadIdx.x], pl = s_rec[7][threadIdx.x];
     const float4 pmd = s_rec[8][threadIdx.x], pmf = s_rec[9][threadIdx.x], h1 = s_rec[10][threadIdx.x];
+    const float4 po = s_rec[11][threadIdx.x], cy = s_rec[12][threadIdx.x];
     const float4 pax = VOL ? s_rec[kArrays - 1][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
 #else
     const float4 df = a.pool.d_flags[slot], orng = a.pool.o_rng[slot], bs = a.pool.beta_s[slot], lt4 = a.pool.li_t[slot];
     const float4 h0 = a.pool.hit0[slot], bo = a.pool.beta_old[slot], pv = a.pool.vis[slot], pl = a.pool.ldl[slot];
     const float4 pmd = a.pool.misd[slot], pmf = a.pool.misf[slot], h1 = a.pool.hit1[slot];
+    const float4 po = a.pool.pend_o[slot], cy = a.pool.carry[slot];
     const float4 pax = VOL ? a.pool.aux[slot] : make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
     const unsigned long long next_snapshot = a.counters->next_sample;
@@ -241,19 +243,23 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     // of it is exact enough, see below)
     bool finished = !alive && (kdone < a.batch.k_static || next_snapshot < a.batch.total);
     const bool idle_dead = !alive && !finished;
-    int bounces = (int)((flags >> kBounceShift) & 0xffu);
+    int bounces = (int)((flags >> kBounceShift) & 0x7fu);
     int medium = (int)((flags >> kMediumShift) & 0xffu) - 1;      // medium of the continuation ray (vpt)
+    bool retire_carry = false;                                     // the slot's previous sample is completed by section A
 
     // ---------------------------------------------------------------- A. pending direct light of the previous bounce
     if (alive && (flags & F_PENDING)) {
         const f3 beta_old = mk3(bo.x, bo.y, bo.z);
+        const f3 po3 = mk3(po.x, po.y, po.z);                          // where the shadow / MIS rays started
+        const bool carried = (flags & F_CARRY) != 0;
+        f3 Lacc = carried ? mk3(cy.x, cy.y, cy.z) : Li;                // the radiance this direct light belongs to
         const int medium2 = (int)((flags >> kMedium2Shift) & 0xffu) - 1;
         if (VOL && (flags & F_MEDSCATTER)) {
             // Li += tr*beta*phase*radiance / (lightPdf*choicePdf)   (src/pathtracer.cu:1092-1093)
             if (flags & F_SHADOW) {
                 const float4 v = pv; const float4 l = pl; const float4 mf = pmf;
                 f3 tr = mk3(v.x, v.y, v.z), radiance = mk3(l.x, l.y, l.z);
-                Li += tr * beta_old * mf.x * radiance / mf.y;
+                Lacc += tr * beta_old * mf.x * radiance / mf.y;
             }
         } else {
             f3 Ld = mk3(0.f, 0.f, 0.f);
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                 if (h1.x >= 0.f) {
                     const int prim = __float_as_int(h1.y);
                     const int lightIdx = sc.shade[prim].lightIdx;
-                    f3 p = o + h1.x * out;
+                    f3 p = po3 + h1.x * out;
                     f3 n = hit_normal(sc, p, prim, h1.z, h1.w);
                     f3 radiance = mk3(0.f, 0.f, 0.f);
                     if (lightIdx != -1) {
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                         if (!is_black(radiance)) {
                             float pdfA = 1.f / L.area;                                          // Area::Pdf, src/area.h:28
                             float choicePdf = sc.cdf[lightIdx + 1] - sc.cdf[lightIdx];
-                            float lenSquare = dot(p - o, p - o);
+                            float lenSquare = dot(p - po3, p - po3);
                             float costheta = fabsf(dot(n, out));
                             float lPdf = pdfA * lenSquare / (costheta);
                             float weight = power_heuristic(1, pdf, 1, lPdf * choicePdf);
@@ -310,14 +316,21 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                     }
                 }
             }
-            Li += beta_old * Ld;                                                                // :994
+            Lacc += beta_old * Ld;                                                                // :994
         }
-        if (flags & F_TERMINATE) finished = true;
+        if (carried) {
+            st_pool(a.samples + __float_as_uint(po.w), make_float4(Lacc.x, Lacc.y, Lacc.z, 1.f));
+            retire_carry = true;
+        } else {
+            Li = Lacc;
+            if (flags & F_TERMINATE) finished = true;
+        }
     }
 
     // ---------------------------------------------------------------- B. shade the continuation hit
     uint32_t nf = F_ALIVE;          // flags of the next step
     f3 new_o = o, new_d = d;
+    f3 pend_origin = o;             // origin of the shadow / MIS rays emitted by this step
     bool specular = (flags & F_SPECULAR) != 0;
     if (alive && !finished) {
         if (h0.x < 0.f) {                                                                       // miss, :905-909
@@ -360,6 +373,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                         phase = kInvFourPi * (1.f - M.g * M.g) / sqrtf(cubicTerm * cubicTerm * cubicTerm);
                     }
                     nf |= F_PENDING | F_MEDSCATTER;
+                    pend_origin = samplePos;
                     st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, 0.f));
                     if (!is_black(ls.radiance)) {                                               // Tr() is side-effect free otherwise
                         nf |= F_SHADOW;
@@ -428,6 +442,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                         if (idx != sc.n_lights) area_sample(sc.lights[idx], h.pos, ua, ub, sc.eps, ls);
                         else inf_sample(sc.inf, ua, ub, sc.eps, ls);
                         nf |= F_PENDING;
+                        pend_origin = h.pos;
                         st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
                         float mis_absdot = 0.f;
                         f3 ldl = mk3(0, 0, 0);
@@ -495,13 +510,21 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     // ---------------------------------------------------------------- C. retire + regenerate
     // One aggregated atomic per warp hands out the next samples; the ray-queue reservation is issued right behind
     // it (a regenerated slot always emits exactly one continuation ray), so both round trips overlap.
+    // A path that ends with direct light still pending does not idle for a step: if samples are left, the slot starts
+    // its next sample now and carries the old one (F_CARRY) until the next pass has added the pending light.
+    const bool have_more = kdone < a.batch.k_static || next_snapshot < a.batch.total;
+    const bool emitted_pending = alive && !finished && (nf & F_PENDING) != 0u;
+    const bool carry_now = emitted_pending && (nf & F_TERMINATE) != 0u && have_more;
+    const bool want_new = finished || carry_now;
     if (finished && alive) {
         st_pool(a.samples + sample, make_float4(Li.x, Li.y, Li.z, 1.f));
     }
-    const bool take_static = finished && kdone < a.batch.k_static;
-    const uint32_t m_fin = __ballot_sync(kFullMask, finished && !take_static);      // lanes that need the global counter
+    const bool take_static = want_new && kdone < a.batch.k_static;
+    const uint32_t m_fin = __ballot_sync(kFullMask, want_new && !take_static);      // lanes that need the global counter
     const uint32_t m_ret = __ballot_sync(kFullMask, finished && alive);
-    uint32_t rays = finished ? F_CONT : (idle_dead ? 0u : (nf & (F_CONT | F_SHADOW | F_MIS)));
+    const uint32_t m_ret2 = __ballot_sync(kFullMask, retire_carry);
+    uint32_t rays = want_new ? (F_CONT | (carry_now ? (nf & (F_SHADOW | F_MIS)) : 0u))
+                             : (idle_dead ? 0u : (nf & (F_CONT | F_SHADOW | F_MIS)));
     const uint32_t mc = __ballot_sync(kFullMask, (rays & F_CONT) != 0u);
     const uint32_t ms = __ballot_sync(kFullMask, (rays & F_SHADOW) != 0u);
     const uint32_t mm = __ballot_sync(kFullMask, (rays & F_MIS) != 0u);
@@ -511,7 +534,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     if (lane == 0u) {
         if (m_fin) sbase = atomicAdd(&a.counters->next_sample, (unsigned long long)__popc(m_fin));
         if (nc + ns + nm) qbase = atomicAdd(&a.q.ctl->tail[a.parity & 1u], nc + ns + nm);
-        if (m_ret) atomicAdd(&a.counters->done_samples, (unsigned long long)__popc(m_ret));
+        if (m_ret | m_ret2) atomicAdd(&a.counters->done_samples, (unsigned long long)(__popc(m_ret) + __popc(m_ret2)));
     }
     sbase = __shfl_sync(kFullMask, sbase, 0);
     qbase = __shfl_sync(kFullMask, qbase, 0);
@@ -520,37 +543,50 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     if (rays & F_MIS) a.q.entries[qbase + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
     if (idle_dead) return;
 
-    if (finished) {
+    uint32_t carried_sample = 0u;
+    if (want_new) {
         unsigned long long s;
         if (take_static) { s = (unsigned long long)slot + (unsigned long long)kdone * (unsigned long long)a.pool.n; ++kdone; }
         else s = sbase + (unsigned long long)__popc(m_fin & lt);
         if (s >= a.batch.total) {
-            // the batch ran out between the snapshot and the atomic: the slot dies; its queue entry stays and
-            // traces one harmless ray (this happens in at most one step per batch)
-            st_pool(a.pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
-            st_pool(a.pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
-            return;
+            // the batch ran out between the snapshot and the atomic (at most one step per batch); the reserved queue
+            // entry stays and traces one harmless ray
+            if (finished) {                                   // the slot dies
+                st_pool(a.pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
+                st_pool(a.pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
+                return;
+            }
+            // carry_now: fall back to the idle step — the state computed by section B (TERMINATE | PENDING) is kept
+        } else {
+            uint32_t pending_bits = 0u;
+            if (carry_now) {
+                st_pool(a.pool.carry + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
+                carried_sample = sample;
+                pending_bits = F_CARRY | (nf & (F_PENDING | F_SHADOW | F_MIS | F_MEDSCATTER)) | (nf & (0xffu << kMedium2Shift));
+            }
+            sample = (uint32_t)s;
+            const uint32_t npix = (uint32_t)a.map.n_local_pixels;
+            const uint32_t it_local = sample / npix, local = sample - it_local * npix;
+            uint32_t x, y;
+            local_to_xy(a.map, local, x, y);
+            const uint32_t pixel = x + y * (uint32_t)a.map.width;                               // :883
+            rng = rng_seed(pixel, a.batch.first_iter + it_local);                               // :888
+            float offsetx = rng_next(rng) - 0.5f;                                               // :892-897
+            float offsety = rng_next(rng) - 0.5f;
+            float a0 = rng_next(rng), a1 = rng_next(rng);
+            f2 aperture = mk2(0.f, 0.f);
+            if (a.cam.apertureRadius > 0.00001f) aperture = uniform_disk(a0, a1);                // unused otherwise (camera.h:63)
+            camera_ray(a.cam, x + offsetx, y + offsety, aperture, new_o, new_d);
+            beta = mk3(1.f, 1.f, 1.f); Li = mk3(0.f, 0.f, 0.f);
+            bounces = 0; specular = false;
+            int m = VOL ? a.cam.medium : -1;                                                    // :1043
+            nf = F_ALIVE | F_CONT | ((uint32_t)(m + 1) << kMediumShift) | pending_bits;
         }
-        sample = (uint32_t)s;
-        const uint32_t npix = (uint32_t)a.map.n_local_pixels;
-        const uint32_t it_local = sample / npix, local = sample - it_local * npix;
-        uint32_t x, y;
-        local_to_xy(a.map, local, x, y);
-        const uint32_t pixel = x + y * (uint32_t)a.map.width;                                   // :883
-        rng = rng_seed(pixel, a.batch.first_iter + it_local);                                   // :888
-        float offsetx = rng_next(rng) - 0.5f;                                                   // :892-897
-        float offsety = rng_next(rng) - 0.5f;
-        float a0 = rng_next(rng), a1 = rng_next(rng);
-        f2 aperture = mk2(0.f, 0.f);
-        if (a.cam.apertureRadius > 0.00001f) aperture = uniform_disk(a0, a1);                    // unused otherwise (camera.h:63)
-        camera_ray(a.cam, x + offsetx, y + offsety, aperture, new_o, new_d);
-        beta = mk3(1.f, 1.f, 1.f); Li = mk3(0.f, 0.f, 0.f);
-        bounces = 0; specular = false;
-        int m = VOL ? a.cam.medium : -1;                                                        // :1043
-        nf = F_ALIVE | F_CONT | ((uint32_t)(m + 1) << kMediumShift);
     }
+    if (emitted_pending)
+        st_pool(a.pool.pend_o + slot, make_float4(pend_origin.x, pend_origin.y, pend_origin.z, __uint_as_float(carried_sample)));
     if (specular) nf |= F_SPECULAR;
-    nf |= ((uint32_t)bounces & 0xffu) << kBounceShift;
+    nf |= ((uint32_t)bounces & 0x7fu) << kBounceShift;
     st_pool(a.pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
     st_pool(a.pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
     st_pool(a.pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));

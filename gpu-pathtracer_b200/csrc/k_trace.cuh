@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
             if (!active && idx < tail) {
                 entry = a.q.entries[idx];
                 const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
-                const float4 orng = a.pool.o_rng[slot];
+                const float4 orng = kind == 0u ? a.pool.o_rng[slot] : a.pool.pend_o[slot];     // shadow / MIS rays keep their own origin
                 o = mk3(orng.x, orng.y, orng.z);
                 float4 dv;
                 if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tail; idx += stride) {
         const uint32_t entry = a.q.entries[idx];
         const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
-        const float4 orng = a.pool.o_rng[slot];
+        const float4 orng = kind == 0u ? a.pool.o_rng[slot] : a.pool.pend_o[slot];             // shadow / MIS rays keep their own origin
         f3 o = mk3(orng.x, orng.y, orng.z);
         float4 dv;
         if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }

@@ -83,7 +83,8 @@ constexpr uint32_t F_PENDING = 1u << 4;      // previous bounce's direct light s
 constexpr uint32_t F_TERMINATE = 1u << 5;    // retire after the pending direct light is added
 constexpr uint32_t F_SPECULAR = 1u << 6;     // last bounce was a delta BSDF
 constexpr uint32_t F_MEDSCATTER = 1u << 7;   // pending contribution is a medium in-scatter (vpt)
-constexpr int kBounceShift = 8;              // bits 8..15: bounce counter
+constexpr uint32_t F_CARRY = 1u << 15;       // the pending direct light belongs to the slot's PREVIOUS sample (see Pool::carry)
+constexpr int kBounceShift = 8;              // bits 8..14: bounce counter
 constexpr int kMediumShift = 16;             // bits 16..23: continuation ray's medium index + 1 (0 = none)
 constexpr int kMedium2Shift = 24;            // bits 24..31: medium of the shadow / MIS rays + 1
 
@@ -101,6 +102,11 @@ struct Pool {
     float4* hit1;         // MIS hit
     float4* vis;          // shadow result: transmittance xyz (0 = occluded; 1 for `pt`), -
     float4* aux;          // vpt only: emitter radiance xyz, MIS weight of the light sample
+    // A path that ends with direct light still pending (Russian roulette, depth limit, black BSDF) does not idle for a
+    // step: its slot is regenerated at once and CARRIES the old sample along — the shadow / MIS rays keep their own
+    // origin, and the next shade pass adds their result to the carried radiance and retires the old sample.
+    float4* pend_o;       // origin of the shadow / MIS rays xyz, carried sample index (bits)
+    float4* carry;        // radiance of the carried sample so far xyz, -
     int32_t n;
 };
 
