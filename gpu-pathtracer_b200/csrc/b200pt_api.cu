@@ -41,7 +41,7 @@ struct Lane {
     unsigned long long counter_init[2] = {0, 0};
     std::vector<void*> pool_allocs;       // cudaMalloc'ed pool/queue planes (re-allocated by the "pool" option)
     ShadeArgs sa; TraceArgs ta;
-    int chunk = 0; bool done = false, exact_pending = false;
+    int chunk = 0; bool done = false, exact_pending = false, nearly_done = false;
 };
 
 struct b200pt_ctx {
@@ -573,7 +573,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (size_t k = 0; k < c->lanes.size(); ++k) {
         Lane& L = c->lanes[k];
-        L.done = L.map.n_local_pixels == 0; L.chunk = 0; L.exact_pending = false;
+        L.done = L.map.n_local_pixels == 0; L.chunk = 0; L.exact_pending = false; L.nearly_done = false;
         if (L.done) continue;
         if (k) CK(cudaStreamWaitEvent(L.stream, c->ev_fork, 0));
         const size_t need = (size_t)n_iters * L.map.n_local_pixels;
@@ -609,7 +609,8 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
             // checked synchronously after 8 steps and then every 4)
             const bool single_pass = L.sa.batch.total <= (unsigned long long)L.pool.n;
             const bool exact = single_pass && (!c->vol ? L.chunk == 0 : true);
-            const int n_steps = !exact ? c->steps_per_poll : (!c->vol ? c->sc.max_depth + 1 : (L.chunk == 0 ? 8 : 4));
+            // (a lane that was almost finished at the last poll is launched in short chunks: fewer empty tail steps)
+            const int n_steps = !exact ? (L.nearly_done ? 2 : c->steps_per_poll) : (!c->vol ? c->sc.max_depth + 1 : (L.chunk == 0 ? 8 : 4));
             for (int s = 0; s < n_steps; ++s) {
                 launch_trace(c, L, L.ta); L.ta.parity ^= 1u;
                 L.sa.parity ^= 1u; launch_shade(c, L, L.sa);
@@ -623,6 +624,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
                 const int prev = (L.chunk - 1) & 1;
                 CK(cudaEventSynchronize(L.ev_poll[prev]));
                 if (L.h_counters[prev].done_samples >= L.sa.batch.total) L.done = true;
+                else if ((double)L.h_counters[prev].done_samples >= 0.97 * (double)L.sa.batch.total) L.nearly_done = true;
             }
             if (++L.chunk > (1 << 22)) return fail(B200PT_ECUDA, "wavefront did not converge (internal error)");
         }

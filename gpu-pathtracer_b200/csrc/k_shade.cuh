@@ -203,6 +203,17 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
     // staged into shared memory by TMA bulk copies (one elected thread issues them, everyone waits on the mbarrier)
     constexpr int kArrays = VOL ? 14 : 13;
 #ifndef B200PT_EMULATE
+    // drain phase (no sample left to hand out): a tile whose slots are all dead has nothing to do — find that out
+    // with one 16-byte load per thread instead of staging 13 planes
+    // (the counter moves while the kernel runs: one thread reads it, so the whole CTA takes the same branch)
+    __shared__ int s_drain;
+    if (threadIdx.x == 0) s_drain = a.counters->next_sample >= a.batch.total ? 1 : 0;
+    __syncthreads();
+    if (s_drain) {
+        const uint32_t f = __float_as_uint(a.pool.d_flags[slot].w);
+        const uint32_t k = __float_as_uint(a.pool.li_t[slot].w);
+        if (!__syncthreads_or((f & F_ALIVE) != 0u || k < a.batch.k_static)) return;
+    }
     __shared__ __align__(128) float4 s_rec[kArrays][128];
     __shared__ uint64_t bar;
     if (threadIdx.x == 0) {
