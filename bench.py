@@ -39,7 +39,7 @@ ALGO = {
 
 
 # ncu-measured DRAM traffic per sample, whole wavefront (see profiles/); filled in from the capture of the round
-DRAM_BYTES_PER_SAMPLE = {"c2": 2017.0}     # profiles/r01j_launches_summary.txt: 25.4 GB over 12.6 Msamples
+DRAM_BYTES_PER_SAMPLE = {"c2": 1684.0}     # profiles/r01s_launches_summary.txt: 21.2 GB over 12.6 Msamples
 
 
 def algo_bytes_per_sample(w):
