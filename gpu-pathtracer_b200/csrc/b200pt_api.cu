@@ -59,6 +59,7 @@ struct b200pt_ctx {
     size_t stage_top_bytes = 20 * 1024;    // top-of-tree nodes staged per CTA when the scene does not fit
     int refill_below = 24;
     bool lambert_only = false;             // every referenced material is lambertian -> specialised shade kernel
+    uint32_t mats_used = 0;                // MaterialTypes referenced by primitives (picks the k_shade instantiation)
     float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
     bool small_scene = false;              // use k_trace_small
     uint32_t small_prim_bytes = 0;
@@ -322,11 +323,12 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     if ((rc = dev_upload(c, &d_mats, (const Material*)v->materials, (size_t)v->n_materials))) return rc;
     sc.mats = d_mats; sc.n_mats = v->n_materials;
     // material set actually referenced by primitives (scene files often define materials they do not use)
-    c->lambert_only = true;
+    c->mats_used = 0u;
     for (int i = 0; i < v->n_prims; ++i) {
         const int m = ws[i].matIdx;
-        if (m >= 0 && mats[m].type != MT_LAMBERTIAN) { c->lambert_only = false; break; }
+        if (m >= 0) c->mats_used |= 1u << (mats[m].type & 31);
     }
+    c->lambert_only = (c->mats_used & ~kMatsLambertOnly) == 0u;
     std::vector<WMedium> wm(std::max(v->n_mediums, 1));
     std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
     const RefMedium* med = (const RefMedium*)v->mediums;
@@ -540,11 +542,14 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
 
 static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
     const int blocks = L.pool.n / 128;
+    const bool ldc = (c->mats_used & ~kMatsLDC) == 0u;
     if (c->vol) {
         if (c->lambert_only) PT_LAUNCH((k_shade<true, kMatsLambertOnly>), blocks, 128, 0, L.stream, sa);
+        else if (ldc) PT_LAUNCH((k_shade<true, kMatsLDC>), blocks, 128, 0, L.stream, sa);
         else PT_LAUNCH((k_shade<true, kMatsAll>), blocks, 128, 0, L.stream, sa);
     } else {
         if (c->lambert_only) PT_LAUNCH((k_shade<false, kMatsLambertOnly>), blocks, 128, 0, L.stream, sa);
+        else if (ldc) PT_LAUNCH((k_shade<false, kMatsLDC>), blocks, 128, 0, L.stream, sa);
         else PT_LAUNCH((k_shade<false, kMatsAll>), blocks, 128, 0, L.stream, sa);
     }
 }

@@ -191,7 +191,25 @@ static inline void st_pool(float4* p, float4 v) { *p = v; }
 // Material specialisation: a scene whose materials are all lambertian gets a kernel without the GGX / dielectric
 // code (a quarter of the instructions and registers of the general one); MATS is the set of MaterialTypes present.
 constexpr uint32_t kMatsLambertOnly = 1u << MT_LAMBERTIAN;
-constexpr uint32_t kMatsAll = 0xffffffffu;
+constexpr uint32_t kMatsLDC = (1u << MT_LAMBERTIAN) | (1u << MT_DIELECTRIC) | (1u << MT_ROUGHCONDUCTOR);   // e.g. veach_bidir
+constexpr uint32_t kMatsAll = 0x3fu;
+
+// SampleBSDF / Fr restricted to the material types in MATS: each enabled type is dispatched with a compile-time
+// constant, so the switch inside sample_bsdf / eval_bsdf folds to that one case and the others are never emitted.
+template <uint32_t MATS>
+__device__ __forceinline__ void sample_bsdf_m(const Material& m, f3 albedo, f3 in, f3 nor, f3 dpdu, f3 u, f3& out, f3& fr, float& pdf) {
+#define PT_CASE(T) if (((MATS >> (T)) & 1u) && m.type == (T)) { Material mm = m; mm.type = (T); sample_bsdf(mm, albedo, in, nor, dpdu, u, out, fr, pdf); return; }
+    PT_CASE(MT_LAMBERTIAN) PT_CASE(MT_MIRROR) PT_CASE(MT_DIELECTRIC) PT_CASE(MT_ROUGHDIELECTRIC) PT_CASE(MT_ROUGHCONDUCTOR) PT_CASE(MT_SUBSTRATE)
+#undef PT_CASE
+    fr = mk3(0, 0, 0); pdf = 0.f; out = mk3(0, 0, 0);
+}
+template <uint32_t MATS>
+__device__ __forceinline__ void eval_bsdf_m(const Material& m, f3 albedo, f3 in, f3 out, f3 nor, f3 dpdu, f3& fr, float& pdf) {
+#define PT_CASE(T) if (((MATS >> (T)) & 1u) && m.type == (T)) { Material mm = m; mm.type = (T); eval_bsdf(mm, albedo, in, out, nor, dpdu, fr, pdf); return; }
+    PT_CASE(MT_LAMBERTIAN) PT_CASE(MT_MIRROR) PT_CASE(MT_DIELECTRIC) PT_CASE(MT_ROUGHDIELECTRIC) PT_CASE(MT_ROUGHCONDUCTOR) PT_CASE(MT_SUBSTRATE)
+#undef PT_CASE
+    fr = mk3(0, 0, 0); pdf = 0.f;
+}
 
 template <bool VOL, uint32_t MATS>
 __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
@@ -439,8 +457,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                     nf |= F_CONT | ((uint32_t)(m + 1) << kMediumShift);
                     // bounces unchanged, no Russian roulette (the reference `continue`s)
                 } else {
-                    Material mat = sc.mats[h.matIdx];
-                    if (MATS == kMatsLambertOnly) mat.type = MT_LAMBERTIAN;    // scene-level fact: drops the other BSDFs
+                    const Material mat = sc.mats[h.matIdx];
                     const f3 albedo = material_albedo(sc, mat, h.uv);                          // GetTexel, :341-359
                     const f3 wo = -d;
                     if (!is_delta(mat.type)) {                                                  // :925-995
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                         f3 ldl = mk3(0, 0, 0);
                         if (!is_black(ls.radiance)) {
                             f3 fr; float samplePdf;
-                            eval_bsdf(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
+                            eval_bsdf_m<MATS>(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
                             float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
                             nf |= F_SHADOW;
                             st_pool(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
@@ -471,7 +488,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                         }
                         float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
                         f3 out, fr; float pdf;
-                        sample_bsdf(mat, albedo, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
+                        sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
                         float denom = ls.pdf * choicePdf;
                         if (!(is_black(fr) || pdf == 0)) {
                             nf |= F_MIS;
@@ -486,7 +503,7 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                     }
                     float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :997-1003
                     f3 out, fr; float pdf;
-                    sample_bsdf(mat, albedo, wo, h.nor, h.dpdu, mk3(c0, c1, c2), out, fr, pdf);
+                    sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(c0, c1, c2), out, fr, pdf);
                     if (is_black(fr)) {
                         nf |= F_TERMINATE;
                     } else {
