@@ -188,7 +188,7 @@ def main():
             __cuda_array_interface__ = {"shape": (npix * 3,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         acc_t = torch.as_tensor(_Holder(), device=f"cuda:{local}")
     out_dev = torch.empty(npix * 3, dtype=torch.float32, device=f"cuda:{local}")
-    out_host = np.empty((H, W, 3), np.float32)
+    out_host = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()    # pinned host image for the e2e arm
 
     def barrier():
         if world > 1:

@@ -392,6 +392,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     // (TMA bulk copy): everything when the scene is small, else the top of the breadth-first node array
     size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
     // (k_trace also keeps 24 KB of traversal stack in shared memory; 20 KB of structure keeps 5 CTAs per SM resident)
+    if (const char* env = getenv("B200PT_STAGE_BYTES")) c->stage_top_bytes = (size_t)std::max(0, atoi(env));
     if (nb + pb <= c->stage_top_bytes) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; }
     else { c->stage_nodes = (uint32_t)std::min<size_t>(nb, c->stage_top_bytes); c->stage_prims = 0; }
     c->small_prim_bytes = (uint32_t)pb;

@@ -7,7 +7,9 @@ sys.path.insert(0, ROOT)
 import gpu_pathtracer_b200 as pt
 from tests import refhost
 import torch
-for name, s in [("cornell 1024^2 d8", pt.scenes.cornell_pt(1024, 1024, 8)), ("vol 512^2", pt.scenes.cornell_vol_caustic(512, 512, 17))]:
+for name, s in [("cornell 1024^2 d8", pt.scenes.cornell_pt(1024, 1024, 8)), ("cornell 512^2 d5", pt.scenes.cornell_pt(512, 512, 5)),
+                ("cornell 256^2 d5", pt.scenes.cornell_pt(256, 256, 5)), ("vol 512^2", pt.scenes.cornell_vol_caustic(512, 512, 17)),
+                ("veach 768x576", pt.scenes.veach_standin(768, 576, 17))]:
     n = 64
     out = torch.empty(s.width * s.height * 3, dtype=torch.float32, device="cuda")
     with pt.PathTracer(s) as r:
