@@ -38,7 +38,7 @@ struct Lane {
     Counters* counters = nullptr;
     Counters* h_counters = nullptr;       // pinned, 2 polling slots
     float4* samples = nullptr; size_t samples_cap = 0;   // in float4
-    unsigned long long counter_init[2] = {0, 0};
+    unsigned long long* h_init = nullptr; // pinned: initial {next_sample, done_samples} of a batch
     std::vector<void*> pool_allocs;       // cudaMalloc'ed pool/queue planes (re-allocated by the "pool" option)
     ShadeArgs sa; TraceArgs ta;
     int chunk = 0; bool done = false, exact_pending = false, nearly_done = false;
@@ -70,6 +70,15 @@ struct b200pt_ctx {
     double total_ms = 0;
     bool vol = false;
     int last_filmic = 1;
+    // captured frame (CUDA graph) for the one-Render-per-frame usage: `pt`, spp == 1, every lane single-pass
+    FrameParams* d_frame = nullptr;        // device copy read by the captured kernels
+    FrameParams* h_frame = nullptr;        // pinned staging, refreshed before every graph launch
+    bool use_graph = true;
+#ifndef B200PT_EMULATE
+    cudaGraphExec_t graph_exec = nullptr;
+#endif
+    double graph_launches = 0, graph_steps = 0;
+    unsigned long long rays_seen = 0;      // device ray counters at the end of the previous render call
 };
 
 template <class T> static int dev_alloc(b200pt_ctx* c, T** p, size_t n, bool zero = false) {
@@ -495,10 +504,14 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     if ((rc = dev_alloc(c, &c->acc, 3 * npix, true))) return bail(rc);
     if ((rc = dev_alloc(c, &c->color, 3 * npix, true))) return bail(rc);
     if ((rc = dev_alloc(c, &c->out, 3 * npix, true))) return bail(rc);
+    if ((rc = dev_alloc(c, &c->d_frame, 1, true))) return bail(rc);
+    if (cudaMallocHost((void**)&c->h_frame, sizeof(FrameParams)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
+    if (const char* env = getenv("B200PT_GRAPH")) c->use_graph = atoi(env) != 0;
     for (Lane& L : c->lanes) {
         if ((rc = dev_alloc(c, &L.counters, 1, true))) return bail(rc);
         if ((rc = dev_alloc(c, &L.q.ctl, 1, true))) return bail(rc);
         if (cudaMallocHost((void**)&L.h_counters, 2 * sizeof(Counters)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
+        if (cudaMallocHost((void**)&L.h_init, 2 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
         if ((rc = alloc_pool(c, L, lane_pool_size(c, L)))) return bail(rc);
     }
 
@@ -521,6 +534,10 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
 extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return fail(B200PT_EINVAL, "null argument");
     std::string n(name);
+#ifndef B200PT_EMULATE
+    if (c->graph_exec) { cudaSetDevice(c->device); cudaDeviceSynchronize(); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // kernel arguments are baked in
+#endif
+    if (n == "graph") { c->use_graph = value != 0; return 0; }
     if (n == "pool") {
         if (value < 256 || value > (1 << 26)) return fail(B200PT_EINVAL, "pool must be in [256, 2^26]");
         CK(cudaSetDevice(c->device));
@@ -567,15 +584,17 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
-    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp;
+    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
     ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
 }
 
 // One batch = n_iters iterations of every local pixel through the wavefronts of all lanes, then the ordered resolve.
 // Lane streams are forked from / joined into lane 0's stream with events, so the caller sees one ordered stream.
+// `capture`: the call is being recorded into a CUDA graph (exact-step mode only: no allocation, no host polling, and
+// the per-call inputs are read from c->d_frame).
 static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint32_t n_iters, int reset, float* out_dev, int write_out,
-                     double* launches, double* steps) {
+                     double* launches, double* steps, bool capture = false) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (size_t k = 0; k < c->lanes.size(); ++k) {
         Lane& L = c->lanes[k];
@@ -584,6 +603,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         if (k) CK(cudaStreamWaitEvent(L.stream, c->ev_fork, 0));
         const size_t need = (size_t)n_iters * L.map.n_local_pixels;
         if (need > L.samples_cap) {
+            if (capture) return fail(B200PT_ECUDA, "internal: sample planes must be allocated before capture");
             if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
             cudaError_t e = cudaMalloc((void**)&L.samples, need * sizeof(float4));
             if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc of the sample planes: ") + cudaGetErrorString(e));
@@ -592,13 +612,14 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
         bp.k_static = (uint32_t)((need - need / 4) / (unsigned long long)L.pool.n);      // ~3/4 of the batch by static assignment
         // next_sample starts behind the statically assigned range; done_samples at 0 (rays keeps counting)
-        L.counter_init[0] = (unsigned long long)bp.k_static * (unsigned long long)L.pool.n; L.counter_init[1] = 0ull;
-        CK(cudaMemcpyAsync(L.counters, L.counter_init, sizeof(L.counter_init), cudaMemcpyHostToDevice, L.stream));
+        L.h_init[0] = (unsigned long long)bp.k_static * (unsigned long long)L.pool.n; L.h_init[1] = 0ull;
+        CK(cudaMemcpyAsync(L.counters, L.h_init, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, L.stream));
         CK(cudaMemsetAsync(L.pool.li_t, 0, sizeof(float4) * (size_t)L.pool.n, L.stream));   // no static samples consumed yet
         CK(cudaMemsetAsync(L.q.ctl, 0, sizeof(QueueCtl), L.stream));
         // all slots start dead: the first shade pass only regenerates
         CK(cudaMemsetAsync(L.pool.d_flags, 0, sizeof(float4) * (size_t)L.pool.n, L.stream));
         fill_args(c, L, cam, bp);
+        L.sa.frame = capture ? c->d_frame : nullptr;
         L.sa.parity = 0; launch_shade(c, L, L.sa); *launches += 1;
     }
     // Launch in chunks, lanes interleaved, and poll each lane's retired-sample counter one chunk behind, so the GPU
@@ -624,6 +645,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
             *launches += 2.0 * n_steps; *steps += n_steps;
             const int slot = L.chunk & 1;
             CK(cudaMemcpyAsync(&L.h_counters[slot], L.counters, sizeof(Counters), cudaMemcpyDeviceToHost, L.stream));
+            if (capture) { L.done = true; ++L.chunk; continue; }      // verdict is read by the caller after the graph has run
             CK(cudaEventRecord(L.ev_poll[slot], L.stream));
             if (exact) L.exact_pending = true;
             else if (L.chunk >= 1) {
@@ -648,6 +670,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         if (L.map.n_local_pixels == 0) continue;
         ResolveArgs ra; ra.samples = L.samples; ra.acc = c->acc; ra.color = c->color; ra.out = out_dev ? out_dev : c->out;
         ra.map = L.map; ra.batch = L.sa.batch; ra.reset = reset; ra.filmic = cam.filmic; ra.write_out = write_out;
+        ra.frame = capture ? c->d_frame : nullptr;
         PT_LAUNCH(k_resolve, (L.map.n_local_pixels + 255) / 256, 256, 0, L.stream, ra);
         *launches += 1;
         if (k) { CK(cudaEventRecord(L.ev_done, L.stream)); CK(cudaStreamWaitEvent(c->stream, L.ev_done, 0)); }
@@ -656,14 +679,12 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
     return 0;
 }
 
+// Rays traced so far (statistics): one asynchronous read-back per lane on the context stream, one wait.
 static int read_rays(b200pt_ctx* c, unsigned long long* total) {
+    for (Lane& L : c->lanes) CK(cudaMemcpyAsync(&L.h_counters[1].rays, &L.counters->rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     *total = 0;
-    for (Lane& L : c->lanes) {
-        unsigned long long r = 0;
-        CK(cudaMemcpyAsync(&r, &L.counters->rays, sizeof(r), cudaMemcpyDeviceToHost, L.stream));
-        CK(cudaStreamSynchronize(L.stream));
-        *total += r;
-    }
+    for (Lane& L : c->lanes) *total += L.h_counters[1].rays;
     return 0;
 }
 
@@ -678,9 +699,9 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     c->last_filmic = cam.filmic;
     float* out_dev = (output && output_is_device) ? output : c->out;
     const size_t npix = (size_t)c->width * c->height;
-    unsigned long long rays0 = 0, rays1 = 0;
-    int rc = read_rays(c, &rays0);
-    if (rc) return rc;
+    const unsigned long long rays0 = c->rays_seen;
+    unsigned long long rays1 = 0;
+    int rc = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (reset && c->map.n_shards > 1) CK(cudaMemsetAsync(c->acc, 0, 3 * npix * sizeof(float), c->stream));
     if (c->map.n_shards > 1 && out_dev) CK(cudaMemsetAsync(out_dev, 0, 3 * npix * sizeof(float), c->stream));
@@ -689,6 +710,40 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     uint32_t max_iters = (uint32_t)std::max<size_t>(1, c->max_batch_bytes / per_iter);
     double launches = 0, steps = 0;
     uint32_t done = 0;
+#ifndef B200PT_EMULATE
+    // one Render per frame (`pt`, 1 spp, every lane single-pass): the whole frame — uploads, shade / trace steps of all
+    // lanes, resolves — is ONE captured CUDA graph, replayed with the per-call inputs refreshed through c->d_frame
+    bool graph_frame = c->use_graph && !c->vol && spp == 1;
+    for (Lane& L : c->lanes) if (L.map.n_local_pixels > L.pool.n) graph_frame = false;
+    if (graph_frame) {
+        for (Lane& L : c->lanes) {
+            const size_t need = (size_t)L.map.n_local_pixels;
+            if (need > L.samples_cap) {
+                if (c->graph_exec) { CK(cudaDeviceSynchronize()); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+                if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
+                if (cudaMalloc((void**)&L.samples, std::max<size_t>(need, 1) * sizeof(float4)) != cudaSuccess) return fail(B200PT_ENOMEM, "cudaMalloc of the sample planes");
+                L.samples_cap = need;
+            }
+        }
+        if (!c->graph_exec) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            cudaMemcpyAsync(c->d_frame, c->h_frame, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream);
+            c->graph_launches = 0; c->graph_steps = 0;
+            int rc2 = run_batch(c, cam, first_iter, 1, reset, out_dev, 1, &c->graph_launches, &c->graph_steps, true);
+            cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
+            if (rc2 || e2 != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return rc2 ? rc2 : fail(B200PT_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(e2)); }
+            e2 = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) { c->graph_exec = nullptr; return fail(B200PT_ECUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e2)); }
+        }
+        c->h_frame->cam = cam; c->h_frame->first_iter = first_iter; c->h_frame->reset = reset ? 1 : 0;
+        c->h_frame->filmic = cam.filmic; c->h_frame->out = out_dev;
+        CK(cudaGraphLaunch(c->graph_exec, c->stream));
+        launches = c->graph_launches; steps = c->graph_steps;
+        done = spp;
+    }
+#endif
     while (done < spp) {
         uint32_t n = std::min(max_iters, spp - done);
         bool last = done + n == spp;
@@ -699,7 +754,14 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     CK(cudaEventRecord(c->ev1, c->stream));
     if (output && !output_is_device) CK(cudaMemcpyAsync(output, out_dev, 3 * npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+#ifndef B200PT_EMULATE
+    if (graph_frame)
+        for (Lane& L : c->lanes)
+            if (L.map.n_local_pixels && L.h_counters[0].done_samples < (unsigned long long)L.map.n_local_pixels)
+                return fail(B200PT_ECUDA, "captured frame did not retire every sample (internal error)");
+#endif
     if ((rc = read_rays(c, &rays1))) return rc;
+    c->rays_seen = rays1;
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats[0] = (double)spp * c->map.n_local_pixels; c->stats[1] = launches; c->stats[2] = (double)(rays1 - rays0);
@@ -799,10 +861,15 @@ extern "C" int b200pt_destroy(b200pt_ctx* c) {
         free_pool(L);
         if (L.samples) cudaFree(L.samples);
         if (L.h_counters) cudaFreeHost(L.h_counters);
+        if (L.h_init) cudaFreeHost(L.h_init);
         for (auto& e : L.ev_poll) if (e) cudaEventDestroy(e);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
+#ifndef B200PT_EMULATE
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+#endif
+    if (c->h_frame) cudaFreeHost(c->h_frame);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);

@@ -24,6 +24,7 @@ struct ShadeArgs {
     Camera cam;
     ShardMap map;
     BatchParams batch;
+    const FrameParams* frame;  // non-null inside a captured frame: camera and first_iter come from here
 };
 
 struct SurfaceHit { f3 pos, nor, dpdu; f2 uv; int matIdx, lightIdx, mediumInside, mediumOutside; };
@@ -598,16 +599,17 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
             uint32_t x, y;
             local_to_xy(a.map, local, x, y);
             const uint32_t pixel = x + y * (uint32_t)a.map.width;                               // :883
-            rng = rng_seed(pixel, a.batch.first_iter + it_local);                               // :888
+            const Camera& cam = a.frame ? a.frame->cam : a.cam;
+            rng = rng_seed(pixel, (a.frame ? a.frame->first_iter : a.batch.first_iter) + it_local);   // :888
             float offsetx = rng_next(rng) - 0.5f;                                               // :892-897
             float offsety = rng_next(rng) - 0.5f;
             float a0 = rng_next(rng), a1 = rng_next(rng);
             f2 aperture = mk2(0.f, 0.f);
-            if (a.cam.apertureRadius > 0.00001f) aperture = uniform_disk(a0, a1);                // unused otherwise (camera.h:63)
-            camera_ray(a.cam, x + offsetx, y + offsety, aperture, new_o, new_d);
+            if (cam.apertureRadius > 0.00001f) aperture = uniform_disk(a0, a1);                  // unused otherwise (camera.h:63)
+            camera_ray(cam, x + offsetx, y + offsety, aperture, new_o, new_d);
             beta = mk3(1.f, 1.f, 1.f); Li = mk3(0.f, 0.f, 0.f);
             bounces = 0; specular = false;
-            int m = VOL ? a.cam.medium : -1;                                                    // :1043
+            int m = VOL ? cam.medium : -1;                                                      // :1043
             nf = F_ALIVE | F_CONT | ((uint32_t)(m + 1) << kMediumShift) | pending_bits;
         }
     }
@@ -628,6 +630,7 @@ struct ResolveArgs {
     const float4* samples; float* acc; float* color; float* out;
     ShardMap map; BatchParams batch;
     int reset; int filmic; int write_out;
+    const FrameParams* frame;  // non-null inside a captured frame: reset / filmic / out / first_iter come from here
 };
 __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
@@ -637,7 +640,10 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     local_to_xy(a.map, local, x, y);
     const size_t pixel = (size_t)x + (size_t)y * (size_t)a.map.width;
     f3 color = mk3(a.color[3 * pixel], a.color[3 * pixel + 1], a.color[3 * pixel + 2]);
-    f3 acc = a.reset ? mk3(0.f, 0.f, 0.f) : mk3(a.acc[3 * pixel], a.acc[3 * pixel + 1], a.acc[3 * pixel + 2]);
+    const int reset = a.frame ? a.frame->reset : a.reset, filmic = a.frame ? a.frame->filmic : a.filmic;
+    const uint32_t first_iter = a.frame ? a.frame->first_iter : a.batch.first_iter;
+    float* const out = a.frame ? a.frame->out : a.out;
+    f3 acc = reset ? mk3(0.f, 0.f, 0.f) : mk3(a.acc[3 * pixel], a.acc[3 * pixel + 1], a.acc[3 * pixel + 2]);
     for (uint32_t k = 0; k < a.batch.n_iters; ++k) {
         const float4 s = a.samples[(size_t)k * npix + local];
         const f3 L = mk3(s.x, s.y, s.z);
@@ -647,10 +653,10 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     a.color[3 * pixel] = color.x; a.color[3 * pixel + 1] = color.y; a.color[3 * pixel + 2] = color.z;
     a.acc[3 * pixel] = acc.x; a.acc[3 * pixel + 1] = acc.y; a.acc[3 * pixel + 2] = acc.z;
     if (a.write_out) {
-        const uint32_t iter = a.batch.first_iter + a.batch.n_iters - 1;
+        const uint32_t iter = first_iter + a.batch.n_iters - 1;
         f3 c = acc / (float)(int)iter;
-        c = a.filmic ? filmic_tonemap(c) : gamma_correct(c);
-        a.out[3 * pixel] = c.x; a.out[3 * pixel + 1] = c.y; a.out[3 * pixel + 2] = c.z;
+        c = filmic ? filmic_tonemap(c) : gamma_correct(c);
+        out[3 * pixel] = c.x; out[3 * pixel + 1] = c.y; out[3 * pixel + 2] = c.z;
     }
 }
 

@@ -182,6 +182,10 @@ __device__ __forceinline__ void local_to_xy(const ShardMap& m, uint32_t local, u
     x = tx * (uint32_t)m.tile_w + ix; y = ty * (uint32_t)m.tile_h + iy;
 }
 
+// Per-call inputs of a captured (CUDA graph) frame: read through a pointer so that the graph's kernel arguments stay
+// constant from frame to frame; a memcpy node refreshes it from pinned host memory at the head of the graph.
+struct FrameParams { Camera cam; uint32_t first_iter; int32_t reset, filmic, _pad; float* out; };
+
 struct BatchParams {
     uint32_t first_iter;     // iteration number of sample plane 0 (1-based, part of the RNG seed)
     uint32_t n_iters;        // iterations in this batch
