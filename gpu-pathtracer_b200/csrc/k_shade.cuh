@@ -61,7 +61,11 @@ __device__ __forceinline__ f3 material_albedo(const SceneDev& sc, const Material
 // for the final hit from (t, prim, b1, b2).
 __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, float t, int prim, float b1, float b2, SurfaceHit& h) {
     const WShade& s = sc.shade[prim];
+#if defined(__CUDA_ARCH__)
+    h.pos = mk3(__fmaf_rn(t, d.x, o.x), __fmaf_rn(t, d.y, o.y), __fmaf_rn(t, d.z, o.z));     // Ray::operator(), fused (as the reference build does)
+#else
     h.pos = o + t * d;
+#endif
     if (s.type == 0) {
                 h.nor = normalize(lin3(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
         h.uv = mk2(s.uv1[0], s.uv1[1]) * (1.f - b1 - b2) + mk2(s.uv2[0], s.uv2[1]) * b1 + mk2(s.uv3[0], s.uv3[1]) * b2;
@@ -346,7 +350,11 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
                     }
                 }
             }
+#if defined(__CUDA_ARCH__)
+            Lacc = mk3(__fmaf_rn(beta_old.x, Ld.x, Lacc.x), __fmaf_rn(beta_old.y, Ld.y, Lacc.y), __fmaf_rn(beta_old.z, Ld.z, Lacc.z));   // :994, fused
+#else
             Lacc += beta_old * Ld;                                                                // :994
+#endif
         }
         if (carried) {
             st_pool(a.samples + __float_as_uint(po.w), make_float4(Lacc.x, Lacc.y, Lacc.z, 1.f));

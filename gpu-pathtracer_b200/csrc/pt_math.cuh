@@ -349,7 +349,11 @@ PT_HD f3 schlick_fresnel(f3 rs, float costheta) {                               
 }
 PT_HD float power_heuristic(int nf, float fPdf, int ng, float gPdf) {                                       // pathtracer.cu:166
     float f = nf * fPdf, g = ng * gPdf;
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(__fmul_rn(f, f), __fmaf_rn(g, g, __fmul_rn(f, f)));      // f*f is shared, g*g is fused (reference build)
+#else
     return (f * f) / (f * f + g * g);
+#endif
 }
 PT_HD bool same_hemisphere(f3 in, f3 out, f3 nor) { return dot(in, nor) * dot(out, nor) > 0 ? true : false; }  // :210
 
