@@ -188,26 +188,41 @@ def main():
             __cuda_array_interface__ = {"shape": (npix * 3,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         acc_t = torch.as_tensor(_Holder(), device=f"cuda:{local}")
     out_dev = torch.empty(npix * 3, dtype=torch.float32, device=f"cuda:{local}")
-    out_host = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()    # pinned host image for the e2e arm
+    out_host_t = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)              # pinned host image for the e2e arm
+    out_host = out_host_t.numpy()
+    full_acc = torch.empty(npix * 3, dtype=torch.float32, device=f"cuda:{local}") if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_and_tonemap(last_iter):
+        """N > 1: ONE NCCL reduce of the float3 accumulation framebuffer per spp batch (tiles are disjoint, so the sum has
+        one non-zero contributor per pixel), then Output's tonemap of the full image on rank 0."""
+        full_acc.copy_(acc_t)                     # keep the context's own buffer shard-only for the next batch
+        dist.reduce(full_acc, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            torch.cuda.current_stream().synchronize()       # the tonemap runs on the library's stream
+            r.tonemap_device(full_acc.data_ptr(), last_iter, out_dev.data_ptr())
+
     def step_device(i):
         """inputs resident: camera struct is the only host->device traffic (104 B, like the reference's Render)."""
         r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_dev.data_ptr(), output_is_device=True)
         if world > 1:
-            dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
+            reduce_and_tonemap((i + 1) * spp)
         return r.stats()
 
     def step_e2e(i):
-        """public call with HOST buffers: camera from host, tonemapped float3 image back to host every step."""
-        img = r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_host)
-        if world > 1:
-            dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
-        return img
+        """public call with HOST buffers: camera from host, tonemapped float3 image back to (pinned) host memory every step."""
+        if world == 1:
+            return r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_host)
+        r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_dev.data_ptr(), output_is_device=True)
+        reduce_and_tonemap((i + 1) * spp)
+        if rank == 0:
+            out_host_t.view(-1).copy_(out_dev)
+            torch.cuda.synchronize()
+        return out_host
 
     # ---- device-timed arm
     for i in range(a.warmup):
