@@ -584,7 +584,7 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
-    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr;
+    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
     ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
 }
@@ -653,6 +653,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
                 CK(cudaEventSynchronize(L.ev_poll[prev]));
                 if (L.h_counters[prev].done_samples >= L.sa.batch.total) L.done = true;
                 else if ((double)L.h_counters[prev].done_samples >= 0.97 * (double)L.sa.batch.total) L.nearly_done = true;
+                if (L.h_counters[prev].next_sample >= L.sa.batch.total) L.sa.drain_hint = 1;
             }
             if (++L.chunk > (1 << 22)) return fail(B200PT_ECUDA, "wavefront did not converge (internal error)");
         }

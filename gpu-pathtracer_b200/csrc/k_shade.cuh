@@ -25,6 +25,7 @@ struct ShadeArgs {
     ShardMap map;
     BatchParams batch;
     const FrameParams* frame;  // non-null inside a captured frame: camera and first_iter come from here
+    int32_t drain_hint;        // the host saw the sample counter exhausted: dead tiles may leave early
 };
 
 struct SurfaceHit { f3 pos, nor, dpdu; f2 uv; int matIdx, lightIdx, mediumInside, mediumOutside; };
@@ -228,11 +229,8 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
 #ifndef B200PT_EMULATE
     // drain phase (no sample left to hand out): a tile whose slots are all dead has nothing to do — find that out
     // with one 16-byte load per thread instead of staging 13 planes
-    // (the counter moves while the kernel runs: one thread reads it, so the whole CTA takes the same branch)
-    __shared__ int s_drain;
-    if (threadIdx.x == 0) s_drain = a.counters->next_sample >= a.batch.total ? 1 : 0;
-    __syncthreads();
-    if (s_drain) {
+    // (drain_hint comes from the host's last poll of the sample counter, so steps before the drain phase pay nothing)
+    if (a.drain_hint) {
         const uint32_t f = __float_as_uint(a.pool.d_flags[slot].w);
         const uint32_t k = __float_as_uint(a.pool.li_t[slot].w);
         if (!__syncthreads_or((f & F_ALIVE) != 0u || k < a.batch.k_static)) return;
