@@ -512,6 +512,7 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
         if ((rc = dev_alloc(c, &L.q.ctl, 1, true))) return bail(rc);
         if (cudaMallocHost((void**)&L.h_counters, 2 * sizeof(Counters)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
         if (cudaMallocHost((void**)&L.h_init, 2 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(B200PT_ENOMEM, "pinned alloc failed"));
+        std::memset(L.h_counters, 0, 2 * sizeof(Counters));
         if ((rc = alloc_pool(c, L, lane_pool_size(c, L)))) return bail(rc);
     }
 
@@ -621,6 +622,8 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         fill_args(c, L, cam, bp);
         L.sa.frame = capture ? c->d_frame : nullptr;
         L.sa.parity = 0; launch_shade(c, L, L.sa); *launches += 1;
+        // single-pass batch: that first pass handed out every sample, so from now on dead tiles may leave early
+        if (bp.total <= (unsigned long long)L.pool.n) L.sa.drain_hint = 1;
     }
     // Launch in chunks, lanes interleaved, and poll each lane's retired-sample counter one chunk behind, so the GPU
     // never waits on the host.  Step i of a lane: trace consumes queue set (i & 1), the shade after it fills the other.
@@ -760,6 +763,10 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
         for (Lane& L : c->lanes)
             if (L.map.n_local_pixels && L.h_counters[0].done_samples < (unsigned long long)L.map.n_local_pixels)
                 return fail(B200PT_ECUDA, "captured frame did not retire every sample (internal error)");
+#endif
+#ifndef B200PT_EMULATE
+    if (graph_frame) { for (Lane& L : c->lanes) rays1 += L.map.n_local_pixels ? L.h_counters[0].rays : L.h_counters[1].rays; }   // read back by the graph itself
+    else
 #endif
     if ((rc = read_rays(c, &rays1))) return rc;
     c->rays_seen = rays1;
