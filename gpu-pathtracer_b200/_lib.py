@@ -33,7 +33,7 @@ class Shard(C.Structure):
 EXPORTS = [
     "b200pt_create", "b200pt_render", "b200pt_get_accum",
     "b200pt_accum_device_ptr", "b200pt_get_color", "b200pt_tonemap", "b200pt_trace_primary", "b200pt_stats",
-    "b200pt_set_option", "b200pt_destroy", "b200pt_last_error", "b200pt_version", "b200pt_bvh_build",
+    "b200pt_set_option", "b200pt_get_info", "b200pt_destroy", "b200pt_last_error", "b200pt_version", "b200pt_bvh_build",
     "b200pt_camera_init", "b200pt_light_distribution", "b200pt_infinite_init",
 ]
 
@@ -60,6 +60,7 @@ def load(path=None):
     lib.b200pt_trace_primary.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.b200pt_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.b200pt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.b200pt_get_info.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
     lib.b200pt_destroy.argtypes = [C.c_void_p]
     lib.b200pt_bvh_build.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]
     lib.b200pt_camera_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 6 + [C.c_int] * 3

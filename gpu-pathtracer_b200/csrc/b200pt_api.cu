@@ -532,6 +532,18 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     return B200PT_OK;
 }
 
+extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_value) {
+    if (!c || !name || !out_value) return fail(B200PT_EINVAL, "null argument");
+    const std::string n(name);
+    if (n == "lanes") *out_value = (int64_t)c->lanes.size();
+    else if (n == "pool_per_lane") *out_value = c->lanes.empty() ? 0 : (int64_t)c->lanes[0].pool.n;
+    else if (n == "groups") *out_value = c->small_scene ? c->n_leaves : 0;
+    else if (n == "small_kernel") *out_value = c->small_scene ? 1 : 0;
+    else if (n == "lambert_only") *out_value = c->lambert_only ? 1 : 0;
+    else return fail(B200PT_EINVAL, "unknown info " + n);
+    return 0;
+}
+
 extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return fail(B200PT_EINVAL, "null argument");
     std::string n(name);

@@ -80,6 +80,12 @@ class PathTracer:
         _lib.check(self.lib.b200pt_stats(self._ctx, s), "stats")
         return {"samples": s[0], "launches": s[1], "rays": s[2], "steps": s[3], "device_ms": s[4]}
 
+    def info(self, name):
+        """Read-only facts: 'lanes', 'pool_per_lane', 'groups', 'small_kernel', 'lambert_only'."""
+        v = C.c_int64(0)
+        _lib.check(self.lib.b200pt_get_info(self._ctx, name.encode(), C.byref(v)), f"get_info({name})")
+        return int(v.value)
+
     def set_option(self, name, value):
         _lib.check(self.lib.b200pt_set_option(self._ctx, name.encode(), int(value)), f"set_option({name})")
 

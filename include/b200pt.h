@@ -109,6 +109,10 @@ int b200pt_trace_primary(b200pt_ctx* ctx, const void* camera, uint32_t iter, flo
  * [4]=device ms of the call (CUDA events on the context's stream around all kernels of the call). */
 int b200pt_stats(b200pt_ctx* ctx, double* out5);
 
+/* Read-only facts about a context: "lanes" (independent wavefronts), "pool_per_lane" (path slots of one lane),
+ * "groups" (primitive groups of the small-scene kernel, 0 if the tree kernel is used), "small_kernel", "lambert_only". */
+int b200pt_get_info(b200pt_ctx* ctx, const char* name, int64_t* out_value);
+
 /* Tunables (pool = number of path slots in flight; 0 keeps default). */
 int b200pt_set_option(b200pt_ctx* ctx, const char* name, int64_t value);
 
