@@ -34,6 +34,7 @@ EXPORTS = [
     "b200pt_create", "b200pt_render", "b200pt_get_accum",
     "b200pt_accum_device_ptr", "b200pt_get_color", "b200pt_tonemap", "b200pt_trace_primary", "b200pt_stats",
     "b200pt_set_option", "b200pt_get_info", "b200pt_destroy", "b200pt_last_error", "b200pt_version", "b200pt_bvh_build",
+    "b200pt_bvh_build_gpu",
     "b200pt_camera_init", "b200pt_light_distribution", "b200pt_infinite_init",
 ]
 
@@ -63,6 +64,8 @@ def load(path=None):
     lib.b200pt_get_info.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
     lib.b200pt_destroy.argtypes = [C.c_void_p]
     lib.b200pt_bvh_build.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]
+    lib.b200pt_bvh_build_gpu.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                         C.c_int32, C.c_void_p]
     lib.b200pt_camera_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 6 + [C.c_int] * 3
     lib.b200pt_light_distribution.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     lib.b200pt_infinite_init.argtypes = [C.c_void_p, C.c_void_p]
@@ -105,21 +108,38 @@ def make_view(s):
     return v, keep
 
 
-class HostPrep:
-    """Scene preparation through the product's host-side C ABI."""
+def bvh_build(prims, gpu=False, device=0):
+    """BVH::Build through the C ABI: host builder (b200pt_bvh_build) or the GPU one (b200pt_bvh_build_gpu).
+    Returns (prims in leaf order, LinearBVHNode[], root box, timing_ms4 or None)."""
+    lib = load()
+    prims = np.ascontiguousarray(prims)
+    n = len(prims)
+    prims_o = np.zeros(n, L.Primitive)
+    nodes = np.zeros(2 * n + 1, L.LinearBVHNode)
+    nn = C.c_int32(0)
+    box = np.zeros(6, np.float32)
+    timing = None
+    if gpu:
+        timing = np.zeros(4, np.float64)
+        check(lib.b200pt_bvh_build_gpu(prims.ctypes.data, n, prims_o.ctypes.data, nodes.ctypes.data, len(nodes),
+                                       C.byref(nn), box.ctypes.data, device, timing.ctypes.data), "bvh_build_gpu")
+    else:
+        check(lib.b200pt_bvh_build(prims.ctypes.data, n, prims_o.ctypes.data, nodes.ctypes.data, len(nodes),
+                                   C.byref(nn), box.ctypes.data), "bvh_build")
+    return prims_o, nodes[:nn.value].copy(), box, timing
 
-    def __init__(self):
+
+class HostPrep:
+    """Scene preparation through the product's C ABI; gpu_bvh=True builds the tree with b200pt_bvh_build_gpu."""
+
+    def __init__(self, gpu_bvh=False, device=0):
         self.lib = load()
+        self.gpu_bvh = gpu_bvh
+        self.device = device
+        self.bvh_timing = None
 
     def scene_init(self, prims, lights, infinite, infinite_texels):
-        n = len(prims)
-        prims_o = np.zeros(n, L.Primitive)
-        nodes = np.zeros(2 * n + 1, L.LinearBVHNode)
-        nn = C.c_int32(0)
-        box = np.zeros(6, np.float32)
-        check(self.lib.b200pt_bvh_build(prims.ctypes.data, n, prims_o.ctypes.data, nodes.ctypes.data, len(nodes),
-                                        C.byref(nn), box.ctypes.data), "bvh_build")
-        nodes = nodes[:nn.value].copy()
+        prims_o, nodes, box, self.bvh_timing = bvh_build(prims, self.gpu_bvh, self.device)
         if infinite is not None:
             infinite = infinite.copy()
             check(self.lib.b200pt_infinite_init(infinite.ctypes.data, box.ctypes.data), "infinite_init")

@@ -18,6 +18,7 @@ using namespace pt;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int b200pt_internal_fail(int code, const char* msg) { return fail(code, msg); }   // for bvh_build.cu
 #define CK(call)                                                                                              \
     do {                                                                                                      \
         cudaError_t e_ = (call);                                                                              \

@@ -130,6 +130,16 @@ int b200pt_version(void);
 int b200pt_bvh_build(const void* prims_in, int32_t n_prims, void* prims_out, void* nodes_out,
                      int32_t nodes_capacity, int32_t* n_nodes, float* root_box6);
 
+/* The same tree built on the GPU: level-synchronous binned SAH — every node of a level is
+ * split at once (bucket histograms with integer atomics, stable segmented partition by prefix sum), then
+ * flattened into the reference's pre-order LinearBVHNode layout.  Same arguments and same output as
+ * b200pt_bvh_build (byte-identical, except that a zero box coordinate is always +0), host pointers in and
+ * out.  timing_ms4 (optional): [0] upload, [1] device build, [2] download (CUDA events), [3] wall clock of the
+ * call including allocation. */
+int b200pt_bvh_build_gpu(const void* prims_in, int32_t n_prims, void* prims_out, void* nodes_out,
+                         int32_t nodes_capacity, int32_t* n_nodes, float* root_box6, int32_t device,
+                         double* timing_ms4);
+
 /* Camera constructor arithmetic (src/camera.h:31-47 + Lookat :124-129): fills a 104-B reference Camera. */
 int b200pt_camera_init(void* camera104, const float* position3, const float* lookat3, const float* up3,
                        float res_x, float res_y, float distance, float fov, float aperture_radius,
