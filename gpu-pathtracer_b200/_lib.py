@@ -87,7 +87,7 @@ def make_view(s):
     """b200pt_scene_view over a SceneArrays; returns (view, keepalive list)."""
     v = SceneView()
     keep = [s.camera, s.prims, s.nodes, s.materials, s.mediums, s.lights, s.light_distribution, s.infinite,
-            s.infinite_texels]
+            s.infinite_texels] + list(getattr(s, "densities", None) or [])
     v.camera = _ptr(s.camera); v.prims = _ptr(s.prims); v.nodes = _ptr(s.nodes)
     v.materials = _ptr(s.materials); v.mediums = _ptr(s.mediums); v.lights = _ptr(s.lights)
     v.infinite = _ptr(s.infinite) if s.infinite is not None else None

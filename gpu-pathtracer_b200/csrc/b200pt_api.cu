@@ -403,6 +403,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
     // (k_trace also keeps 24 KB of traversal stack in shared memory; 20 KB of structure keeps 5 CTAs per SM resident)
     if (const char* env = getenv("B200PT_STAGE_BYTES")) c->stage_top_bytes = (size_t)std::max(0, atoi(env));
+    c->stage_top_bytes = std::min<size_t>(c->stage_top_bytes, 200 * 1024 - kTraceStackBytes) & ~(size_t)63;   // 227 KB per CTA on sm_100
     if (nb + pb <= c->stage_top_bytes) { c->stage_nodes = (uint32_t)nb; c->stage_prims = (uint32_t)pb; }
     else { c->stage_nodes = (uint32_t)std::min<size_t>(nb, c->stage_top_bytes); c->stage_prims = 0; }
     c->small_prim_bytes = (uint32_t)pb;
@@ -526,6 +527,15 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_small<false>, kTraceThreads, smem);
     } else if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
+#ifndef B200PT_EMULATE
+    if (smem > 48 * 1024) {      // above the default dynamic shared-memory limit: opt in, then ask again
+        cudaError_t e = c->vol ? cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("shared-memory opt-in failed: ") + cudaGetErrorString(e)));
+        if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
+    }
+#endif
     if (per_sm <= 0) per_sm = 1;
     c->trace_blocks = c->num_sms * per_sm;
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));

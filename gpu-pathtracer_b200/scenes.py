@@ -39,6 +39,7 @@ class SceneArrays:
     infinite_texels: np.ndarray = None  # (h, w, 3) float32, kept alive for infinite.data
     root_box: np.ndarray = None
     textures: list = field(default_factory=list)   # (h, w, 4) uint8 arrays — Texture::data (src/texture.h:9)
+    densities: list = field(default_factory=list)  # float32 (nz, ny, nx) grids the heterogeneous Medium records point to
     name: str = ""
     meta: dict = field(default_factory=dict)
 
@@ -166,6 +167,32 @@ def make_homogeneous_medium(sigmaA, sigmaS, g=0.0, scale=1.0):
     return m
 
 
+def make_heterogeneous_medium(sigmaA, sigmaS, grid, p0, p1, g=0.0, scale=1.0, iter_max=1000, eval_transmittance_type=1):
+    """Medium record of src/parsescene.cpp:98-132 for a density grid (nz, ny, nx) float32 in the box p0..p1.
+    Returns (record, grid): the record holds the grid's ADDRESS, so the caller keeps the array alive
+    (SceneArrays.densities)."""
+    grid = np.ascontiguousarray(grid, F)
+    m = np.zeros(1, L.Medium)
+    a = (np.asarray(sigmaA, F) * F(scale)).astype(F)
+    s = (np.asarray(sigmaS, F) * F(scale)).astype(F)
+    t = (a + s).astype(F)
+    if not (t[0] == t[1] == t[2]):
+        raise ValueError("sigmaA and sigmaS requires uniform attenuation coefficient")      # src/parsescene.cpp:102
+    m["type"] = L.MT_HETEROGENEOUS; m["g"] = F(g)
+    m["sigmaA"] = a; m["sigmaS"] = s; m["sigmaT"] = t
+    m["nx"] = grid.shape[2]; m["ny"] = grid.shape[1]; m["nz"] = grid.shape[0]
+    m["density"] = grid.ctypes.data
+    mx = F(0)
+    gm = grid.max()
+    if gm > mx:
+        mx = gm
+    with np.errstate(divide="ignore"):
+        m["invMaxDensity"] = F(1) / F(mx)
+    m["p0"] = np.asarray(p0, F); m["p1"] = np.asarray(p1, F)
+    m["iterMax"] = iter_max; m["evalTransmittanceType"] = eval_transmittance_type
+    return m, grid
+
+
 # ------------------------------------------------------------------------------------------------ assembly
 def line_prims(p0, p1, width0, width1, mat_idx):
     """Hair segments (src/line.h:8): arrays of end points (n, 3) and radii (n,)."""
@@ -186,7 +213,7 @@ def _default_prep():
 
 
 def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials, mediums, prims, lights,
-             infinite=None, infinite_texels=None, prep=None, meta=None, textures=None):
+             infinite=None, infinite_texels=None, prep=None, meta=None, textures=None, densities=None):
     """Scene::Init (src/scene.h:50-82): BVH over all primitives, infinite.Init(root_box), light CDF; plus the
     camera construction of src/main.cpp:268-270."""
     prep = prep or _default_prep()
@@ -202,7 +229,8 @@ def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials
                        materials=np.ascontiguousarray(materials), mediums=np.ascontiguousarray(mediums),
                        lights=lights, light_distribution=lightdist, infinite=infinite,
                        infinite_texels=infinite_texels, root_box=root_box, name=name, meta=meta or {},
-                       textures=[np.ascontiguousarray(t, np.uint8) for t in (textures or [])])
+                       textures=[np.ascontiguousarray(t, np.uint8) for t in (textures or [])],
+                       densities=list(densities or []))
 
 
 def load_scene_json(path, prep=None, overrides=None):
@@ -477,3 +505,30 @@ def cornell_textured_hair(width=256, height=256, max_depth=6, n_hair=400, seed=1
     return assemble("cornell_textured_hair", width, height, base.epsilon, "pt", max_depth, cam, mats, base.mediums,
                     L.cat([prims, hair], L.Primitive), base.lights, prep=prep,
                     textures=[checker_texture(64, 32, 7), checker_texture(16, 48, 8)])
+
+
+def smoke_grid(nx=20, ny=24, nz=12, seed=3):
+    """Procedural density grid (nz, ny, nx): a few soft blobs plus a plume, zero towards the box faces."""
+    z, y, x = np.meshgrid((np.arange(nz) + 0.5) / nz, (np.arange(ny) + 0.5) / ny, (np.arange(nx) + 0.5) / nx, indexing="ij")
+    rng = np.random.RandomState(seed)
+    d = np.zeros((nz, ny, nx), np.float64)
+    for _ in range(6):
+        c = rng.uniform(0.25, 0.75, 3); r = rng.uniform(0.12, 0.28)
+        d += rng.uniform(0.4, 1.0) * np.exp(-(((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (r * r)))
+    d += 0.6 * np.exp(-(((x - 0.5) ** 2 + (z - 0.5) ** 2) / 0.03)) * y
+    d[d < 0.08] = 0.0
+    return d.astype(F)
+
+
+def cornell_smoke(width=256, height=256, max_depth=8, eval_transmittance_type=1, sigma=(2.0, 18.0), prep=None):
+    """SURVEY 8(f).3 widening case, the shape of the reference's shipped scenes/cornell_box/scene.json: the Cornell
+    box rendered with `vpt`, and a box of HETEROGENEOUS smoke (density grid, src/medium.h:52) behind an invisible
+    boundary mesh (matIdx -1, inside = the medium).  The grid is procedural (smoke_grid)."""
+    base = cornell_pt(width, height, max_depth, prep=prep)
+    lo, hi = (-0.55, 0.25, -0.35), (0.45, 1.45, 0.25)
+    med, grid = make_heterogeneous_medium([sigma[0]] * 3, [sigma[1]] * 3, smoke_grid(), lo, hi, g=0.0, iter_max=2000,
+                                          eval_transmittance_type=eval_transmittance_type)
+    boundary = triangles_to_prims(*_box_tris(lo, hi), -1, medium_inside=0, medium_outside=-1)
+    cam = {"position": [0, 1.0, 6.8], "lookat": [0, 1.0, 0], "up": [0, 1, 0], "fov": 19.5, "medium": -1}
+    return assemble("cornell_smoke", width, height, base.epsilon, "vpt", max_depth, cam, base.materials, med,
+                    L.cat([base.prims, boundary], L.Primitive), base.lights, prep=prep, densities=[grid])

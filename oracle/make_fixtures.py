@@ -63,8 +63,15 @@ def main():
         "veach_standin_64x48": lambda: pt.scenes.veach_standin(64, 48, 17, prep=prep),
         "random_tris_20k_64": lambda: pt.scenes.random_triangles(20000, 64, 64, 8, prep=prep),
         "cornell_textured_hair_64": lambda: pt.scenes.cornell_textured_hair(64, 64, 6, prep=prep),
+        # heterogeneous smoke, one fixture per Heterogeneous::Tr estimator (src/medium.h:64-135)
+        "cornell_smoke_ratio_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 1, prep=prep),
+        "cornell_smoke_delta_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 0, prep=prep),
+        "cornell_smoke_residual_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 2, prep=prep),
     }
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]          # optional: regenerate just these fixtures
     for name, mk in scenes.items():
+        if only and name not in only:
+            continue
         s = mk()
         out = {"camera": s.camera.view(np.uint8), "nodes": s.nodes.view(np.uint8), "prims_order_hash": prim_hash(s.prims),
                "light_distribution": s.light_distribution, "root_box": s.root_box}
@@ -77,6 +84,8 @@ def main():
         out["spp"] = np.int32(spp)
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
         print(name, "nodes", len(s.nodes), "prims", len(s.prims), "mean", acc.reshape(-1, 3).mean(0) / spp)
+    if only:
+        return
     kat = ref.known_answers(pt.scenes.cornell_pt(64, 64, 4, prep=prep), pt.scenes.veach_standin(64, 48, 17, prep=prep))
     np.savez_compressed(os.path.join(GOLD, "kat.npz"), **kat)
     print("kat:", {k: v.shape for k, v in kat.items()})

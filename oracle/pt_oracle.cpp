@@ -34,6 +34,7 @@ struct SceneO {
     std::vector<RefLinearBVHNode> nodes;
     std::vector<RefMaterial> mats;
     std::vector<RefMedium> mediums;
+    std::vector<std::vector<float>> densities;   // heterogeneous media: private copies of the nx*ny*nz grids
     std::vector<RefArea> lights;
     RefInfinite inf; bool has_inf = false;
     std::vector<float> inf_texels;
@@ -344,6 +345,106 @@ f3 homogeneous_sample(const RefMedium& m, const Ray& ray, uint32_t& rng, float& 
     t = dist;
     return sampledMedium ? (Tr * sigmaS / pdf) : sigmaT * Tr / pdf;
 }
+// ---- Heterogeneous (src/medium.h:52-179): a density grid in the box p0..p1, sigmaT uniform across channels ----
+float het_d(const RefMedium& m, f3 p) {                           // Heterogeneous::d, src/medium.h:173-178
+    int x = p.x, y = p.y, z = p.z;
+    if (x < 0 || x > m.nx - 1 || y < 0 || y > m.ny - 1 || z < 0 || z > m.nz - 1) return 0.f;
+    int idx = z * m.ny * m.nx + y * m.nx + x;
+    return m.density[idx];
+}
+float lerpf(float a, float b, float t) { return a + t * (b - a); }   // src/cutil_math.h:1008
+float het_density(const RefMedium& m, f3 p) {                     // Heterogeneous::getDensity, src/medium.h:159-171
+    f3 ps = mk3(p.x * m.nx, p.y * m.ny, p.z * m.nz);
+    f3 psi = mk3(floorf(ps.x), floorf(ps.y), floorf(ps.z));
+    f3 delta = ps - psi;
+    float d00 = lerpf(het_d(m, psi), het_d(m, psi + mk3(1, 0, 0)), delta.x);
+    float d10 = lerpf(het_d(m, psi + mk3(0, 1, 0)), het_d(m, psi + mk3(1, 1, 0)), delta.x);
+    float d01 = lerpf(het_d(m, psi + mk3(0, 0, 1)), het_d(m, psi + mk3(1, 0, 1)), delta.x);
+    float d11 = lerpf(het_d(m, psi + mk3(0, 1, 1)), het_d(m, psi + mk3(1, 1, 1)), delta.x);
+    float d0 = lerpf(d00, d10, delta.y);
+    float d1 = lerpf(d01, d11, delta.y);
+    return lerpf(d0, d1, delta.z);
+}
+// Heterogeneous::Tr, src/medium.h:64-135: delta (0), ratio (1) or residual-ratio (2) tracking; draws from the path's RNG
+f3 heterogeneous_tr(const RefMedium& m, const Ray& ray, uint32_t& rng) {
+    float sigma = dot(ld3(m.sigmaT), mk3(0.212671f, 0.715160f, 0.072169f));
+    f3 d = ld3(m.p1) - ld3(m.p0);
+    float tr = 1.f;
+    float dist = 0.f;
+    int iter = m.iterMax;
+    if (m.evalTransmittanceType == 0) {
+        while (true) {
+            dist += -logf(rng_next(rng)) * m.invMaxDensity / sigma;
+            if (dist >= ray.tmax) break;
+            f3 p = at(ray, dist);
+            p = (p - ld3(m.p0)) / d;
+            if (het_density(m, p) * m.invMaxDensity > rng_next(rng)) { tr = 0; break; }
+            if (--iter == 0) { tr = 0; break; }
+        }
+    } else if (m.evalTransmittanceType == 1) {
+        while (true) {
+            dist += -logf(rng_next(rng)) * m.invMaxDensity / sigma;
+            if (dist >= ray.tmax) break;
+            f3 p = at(ray, dist);
+            p = (p - ld3(m.p0)) / d;
+            tr *= 1.f - het_density(m, p) * m.invMaxDensity;
+            if (tr < 0.1f) {
+                float q = 1.f - tr;
+                if (rng_next(rng) < q) return mk3(0.f, 0.f, 0.f);
+                tr = 1;
+            }
+            if (--iter == 0) break;
+        }
+    } else {
+        float maxDensity = 1 / m.invMaxDensity;
+        float ce = 0.5 * maxDensity;
+        float tc = expf(-ray.tmax * ce * sigma);
+        while (true) {
+            dist += -logf(rng_next(rng)) * (1 / (maxDensity - ce) / sigma);
+            if (dist >= ray.tmax) break;
+            f3 p = at(ray, dist);
+            p = (p - ld3(m.p0)) / d;
+            tr *= 1.f - (het_density(m, p) - ce) / (maxDensity - ce);
+            if (tr < 0.1f) {
+                float q = 1.f - tr;
+                if (rng_next(rng) < q) return mk3(0.f, 0.f, 0.f);
+                tr /= (1.f - q);
+            }
+            if (--iter == 0) break;
+        }
+        tr *= tc;
+    }
+    return mk3(tr, tr, tr);
+}
+// Heterogeneous::Sample, src/medium.h:137-157: delta tracking; a real collision scatters with weight sigmaS / sigmaT
+f3 heterogeneous_sample(const RefMedium& m, const Ray& ray, uint32_t& rng, float& t, bool& sampled) {
+    float sigma = dot(ld3(m.sigmaT), mk3(0.212671f, 0.715160f, 0.072169f));
+    f3 d = ld3(m.p1) - ld3(m.p0);
+    float dist = 0.f;
+    int iter = m.iterMax;
+    while (true) {
+        dist += -logf(rng_next(rng)) * m.invMaxDensity / sigma;
+        if (dist >= ray.tmax) break;
+        f3 p = at(ray, dist);
+        p = (p - ld3(m.p0)) / d;
+        if (het_density(m, p) * m.invMaxDensity > rng_next(rng)) {
+            t = dist;
+            sampled = true;
+            return ld3(m.sigmaS) / ld3(m.sigmaT);
+        }
+        if (--iter == 0) break;
+    }
+    t = dist;
+    sampled = false;
+    return mk3(1.f, 1.f, 1.f);
+}
+// the type dispatch at every call site (src/pathtracer.cu:308-311, :1065-1068, :1107-1110, :1180-1183, :1200-1203)
+f3 medium_tr(const RefMedium& m, const Ray& ray, uint32_t& rng) {
+    return m.type == REF_MEDIUM_HOMOGENEOUS ? homogeneous_tr(m, ray) : heterogeneous_tr(m, ray, rng);
+}
+f3 medium_sample(const RefMedium& m, const Ray& ray, uint32_t& rng, float& t, bool& sampled) {
+    return m.type == REF_MEDIUM_HOMOGENEOUS ? homogeneous_sample(m, ray, rng, t, sampled) : heterogeneous_sample(m, ray, rng, t, sampled);
+}
 void medium_phase(const RefMedium& m, f3 in, f3 out, float& phase, float& pdf) {   // Medium::Phase, src/medium.h:222
     float gg = m.g;
     if (gg == 0) { phase = kInvFourPi; pdf = phase; return; }
@@ -369,15 +470,15 @@ void medium_sample_phase(const RefMedium& m, f2 u, f3& dir, float& phase, float&
     phase = kInvFourPi * (1.f - gg * gg) / sqrtf(cubicTerm * cubicTerm * cubicTerm);
     pdf = phase;
 }
-// Tr, src/pathtracer.cu:298-322 (homogeneous media only; heterogeneous is a "next" row)
-f3 transmittance(Ray ray) {
+// Tr, src/pathtracer.cu:298-322
+f3 transmittance(Ray ray, uint32_t& rng) {
     f3 tr = mk3(1, 1, 1);
     float tmax = ray.tmax;
     while (true) {
         Isect isect; isect.lightIdx = -1; isect.matIdx = 0;
         bool invisible = intersect(ray, &isect);
         if (invisible && isect.matIdx != -1) return mk3(0, 0, 0);
-        if (ray.medium >= 0) tr *= homogeneous_tr(g->mediums[ray.medium], ray);
+        if (ray.medium >= 0) tr *= medium_tr(g->mediums[ray.medium], ray, rng);
         if (!invisible) break;
         int m = dot(ray.d, isect.nor) > 0 ? isect.mediumOutside : isect.mediumInside;
         tmax -= ray.tmax;
@@ -451,7 +552,7 @@ f3 direct_light(const Ray& r, const Isect& isect, const RefMaterial& mat, uint32
         if (!is_black(radiance)) {
             f3 fr; float samplePdf;
             eval_bsdf(M(mat), albedo_of(mat, isect.uv), wo, shadowRay.d, nor, dpdu, fr, samplePdf);
-            f3 tr = transmittance(shadowRay);
+            f3 tr = transmittance(shadowRay, rng);
             float weight = power_heuristic(1, lightPdf * choicePdf, 1, samplePdf);
             Ld += weight * tr * fr * radiance * fabsf(dot(nor, shadowRay.d)) / (lightPdf * choicePdf);
         }
@@ -478,7 +579,7 @@ f3 direct_light(const Ray& r, const Isect& isect, const RefMaterial& mat, uint32
                 if (!vol) Ld += weight * fr * rad * fabsf(dot(out, nor)) / pdf;
                 else {
                     f3 tr = mk3(1.f, 1.f, 1.f);
-                    if (lightRay.medium >= 0) tr = homogeneous_tr(g->mediums[lightRay.medium], lightRay);
+                    if (lightRay.medium >= 0) tr = medium_tr(g->mediums[lightRay.medium], lightRay, rng);
                     Ld += weight * tr * fr * rad * fabsf(dot(out, nor)) / pdf;
                 }
             }
@@ -490,7 +591,7 @@ f3 direct_light(const Ray& r, const Isect& isect, const RefMaterial& mat, uint32
             if (!vol) Ld += weight * fr * rad * fabsf(dot(out, nor)) / pdf;
             else {
                 f3 tr = mk3(1.f, 1.f, 1.f);
-                if (lightRay.medium >= 0) tr = homogeneous_tr(g->mediums[lightRay.medium], lightRay);
+                if (lightRay.medium >= 0) tr = medium_tr(g->mediums[lightRay.medium], lightRay, rng);
                 Ld += weight * tr * fr * rad * fabsf(dot(out, nor)) / pdf;
             }
         }
@@ -566,7 +667,7 @@ bool volpath_sample(unsigned x, unsigned y, unsigned pixel, unsigned iter, f3& L
         f3 pos = isect.pos, nor = isect.nor, dpdu = isect.dpdu;
         float sampledDist = 0.f;
         bool sampledMedium = false;
-        if (r.medium >= 0) beta *= homogeneous_sample(g->mediums[r.medium], r, rng, sampledDist, sampledMedium);
+        if (r.medium >= 0) beta *= medium_sample(g->mediums[r.medium], r, rng, sampledDist, sampledMedium);
         if (is_black(beta)) break;
         if (sampledMedium) {
             const RefMedium& med = g->mediums[r.medium];
@@ -581,7 +682,7 @@ bool volpath_sample(unsigned x, unsigned y, unsigned pixel, unsigned iter, f3& L
             if (!inf) area_sample_light(g->lights[idx], samplePos, mk2(ua, ub), radiance, shadowRay, lightNor, lightPdf, g->eps);
             else inf_sample_light(samplePos, mk2(ua, ub), radiance, shadowRay, lightNor, lightPdf, g->eps);
             shadowRay.medium = r.medium;
-            f3 tr = transmittance(shadowRay);
+            f3 tr = transmittance(shadowRay, rng);
             float phase, unuse;
             medium_phase(med, -r.d, shadowRay.d, phase, unuse);
             if (!is_black(radiance)) Li += tr * beta * phase * radiance / (lightPdf * choicePdf);
@@ -595,7 +696,7 @@ bool volpath_sample(unsigned x, unsigned y, unsigned pixel, unsigned iter, f3& L
             if (bounces == 0 || specular) {
                 if (isect.lightIdx != -1) {
                     f3 tr = mk3(1.f, 1.f, 1.f);
-                    if (r.medium >= 0) tr = homogeneous_tr(g->mediums[r.medium], r);
+                    if (r.medium >= 0) tr = medium_tr(g->mediums[r.medium], r, rng);
                     Li += tr * beta * area_le(g->lights[isect.lightIdx], nor, -r.d);
                     break;
                 }
@@ -642,6 +743,13 @@ extern "C" int oracle_begin(const b200pt_scene_view* v, unsigned w, unsigned h, 
     g->nodes.assign((const RefLinearBVHNode*)v->nodes, (const RefLinearBVHNode*)v->nodes + v->n_nodes);
     g->mats.assign((const RefMaterial*)v->materials, (const RefMaterial*)v->materials + v->n_materials);
     if (v->n_mediums) g->mediums.assign((const RefMedium*)v->mediums, (const RefMedium*)v->mediums + v->n_mediums);
+    g->densities.resize(g->mediums.size());
+    for (size_t i = 0; i < g->mediums.size(); ++i) {
+        RefMedium& m = g->mediums[i];
+        if (m.type != REF_MEDIUM_HETEROGENEOUS) continue;
+        g->densities[i].assign(m.density, m.density + (size_t)m.nx * m.ny * m.nz);
+        m.density = g->densities[i].data();
+    }
     if (v->n_lights) g->lights.assign((const RefArea*)v->lights, (const RefArea*)v->lights + v->n_lights);
     if (v->infinite) {
         std::memcpy(&g->inf, v->infinite, sizeof(RefInfinite));
