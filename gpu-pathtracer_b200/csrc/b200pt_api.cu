@@ -5,6 +5,7 @@
 #include "ref_layouts.h"
 #include "k_shade.cuh"
 #include "k_trace.cuh"
+#include "k_volpath_seq.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -70,6 +71,8 @@ struct b200pt_ctx {
     double stats[5] = {0, 0, 0, 0, 0};
     double total_ms = 0;
     bool vol = false;
+    bool het = false;                      // `vpt` with a heterogeneous medium: k_volpath_seq renders (k_volpath_seq.cuh)
+    int seq_blocks = 0;
     int last_filmic = 1;
     // captured frame (CUDA graph) for the one-Render-per-frame usage: `pt`, spp == 1, every lane single-pass
     FrameParams* d_frame = nullptr;        // device copy read by the captured kernels
@@ -342,10 +345,34 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     std::vector<WMedium> wm(std::max(v->n_mediums, 1));
     std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
     const RefMedium* med = (const RefMedium*)v->mediums;
+    std::vector<WHetero> wh(std::max(v->n_mediums, 1));
+    std::memset(wh.data(), 0, wh.size() * sizeof(WHetero));
+    bool any_het = false;
     for (int i = 0; i < v->n_mediums; ++i) {
-        if (med[i].type != REF_MEDIUM_HOMOGENEOUS) return fail(B200PT_EUNSUPPORTED, "heterogeneous media are not implemented yet (SURVEY 8(f).3)");
         std::memcpy(wm[i].sigmaA, med[i].sigmaA, 12); std::memcpy(wm[i].sigmaS, med[i].sigmaS, 12); std::memcpy(wm[i].sigmaT, med[i].sigmaT, 12);
         wm[i].g = med[i].g; wm[i].type = 0;
+        if (med[i].type == REF_MEDIUM_HOMOGENEOUS) continue;
+        if (med[i].type != REF_MEDIUM_HETEROGENEOUS) return fail(B200PT_EINVAL, "unknown medium type");
+        // Heterogeneous (src/medium.h:52): the density grid is deep-copied to the device (src/pathtracer.cu:2612-2622
+        // copies it and delete[]s the caller's array; this library never touches caller memory)
+        if (med[i].nx <= 0 || med[i].ny <= 0 || med[i].nz <= 0 || !med[i].density) return fail(B200PT_EINVAL, "heterogeneous medium without a density grid");
+        if (med[i].evalTransmittanceType < 0 || med[i].evalTransmittanceType > 2) return fail(B200PT_EINVAL, "evalTransmittanceType must be 0, 1 or 2");
+        float* d_density;
+        if ((rc = dev_upload(c, &d_density, med[i].density, (size_t)med[i].nx * med[i].ny * med[i].nz))) return rc;
+        wm[i].type = 1;
+        wh[i].density = d_density; wh[i].nx = med[i].nx; wh[i].ny = med[i].ny; wh[i].nz = med[i].nz;
+        wh[i].invMaxDensity = med[i].invMaxDensity;
+        std::memcpy(wh[i].p0, med[i].p0, 12); std::memcpy(wh[i].p1, med[i].p1, 12);
+        wh[i].iterMax = med[i].iterMax; wh[i].evalTransmittanceType = med[i].evalTransmittanceType;
+        any_het = true;
+    }
+    sc.het = nullptr;
+    // (`pt` never looks at media — Path, src/pathtracer.cu:880-1021 — so only `vpt` needs the sequential kernel)
+    if (any_het && v->integrator_type == B200PT_IT_VPT) {
+        WHetero* d_het;
+        if ((rc = dev_upload(c, &d_het, wh.data(), wh.size()))) return rc;
+        sc.het = d_het;
+        c->het = true;
     }
     WMedium* d_med;
     if ((rc = dev_upload(c, &d_med, wm.data(), wm.size()))) return rc;
@@ -538,6 +565,12 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
 #endif
     if (per_sm <= 0) per_sm = 1;
     c->trace_blocks = c->num_sms * per_sm;
+    if (c->het) {
+        int seq_per_sm = 0;
+        if (c->lambert_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&seq_per_sm, k_volpath_seq<kMatsLambertOnly>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&seq_per_sm, k_volpath_seq<kMatsAll>, 128, 0);
+        c->seq_blocks = c->num_sms * std::max(seq_per_sm, 1);
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));
     *out_ctx = c;
     return B200PT_OK;
@@ -595,6 +628,10 @@ static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
         else PT_LAUNCH((k_shade<false, kMatsAll>), blocks, 128, 0, L.stream, sa);
     }
 }
+static void launch_seq(b200pt_ctx* c, const Lane& L, const SeqArgs& qa) {
+    if (c->lambert_only) PT_LAUNCH((k_volpath_seq<kMatsLambertOnly>), c->seq_blocks, 128, 0, L.stream, qa);
+    else PT_LAUNCH((k_volpath_seq<kMatsAll>), c->seq_blocks, 128, 0, L.stream, qa);
+}
 static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
     if (c->small_scene) {
         const size_t smem = (size_t)c->small_prim_bytes + (size_t)c->n_leaves * 32;
@@ -634,6 +671,18 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
             L.samples_cap = need;
         }
         BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
+        if (c->het) {
+            // heterogeneous media: every sample of the batch runs start to finish in one launch of the sequential kernel
+            bp.k_static = 0;
+            L.h_init[0] = 0ull; L.h_init[1] = 0ull;
+            CK(cudaMemcpyAsync(L.counters, L.h_init, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, L.stream));
+            SeqArgs qa; qa.sc = c->sc; qa.samples = L.samples; qa.counters = L.counters; qa.cam = cam; qa.map = L.map; qa.batch = bp;
+            launch_seq(c, L, qa);
+            L.sa.batch = bp;
+            *launches += 1; *steps += 1;
+            L.done = true;
+            continue;
+        }
         bp.k_static = (uint32_t)((need - need / 4) / (unsigned long long)L.pool.n);      // ~3/4 of the batch by static assignment
         // next_sample starts behind the statically assigned range; done_samples at 0 (rays keeps counting)
         L.h_init[0] = (unsigned long long)bp.k_static * (unsigned long long)L.pool.n; L.h_init[1] = 0ull;

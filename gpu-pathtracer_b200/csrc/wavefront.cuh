@@ -52,7 +52,14 @@ struct WLight {
 };
 static_assert(sizeof(WLight) == 96, "WLight");
 
-struct WMedium { float sigmaA[3], sigmaS[3], sigmaT[3]; float g; int32_t type; int32_t _pad; };   // homogeneous (src/medium.h:9)
+struct WMedium { float sigmaA[3], sigmaS[3], sigmaT[3]; float g; int32_t type; int32_t _pad; };   // type 0 homogeneous (src/medium.h:9), 1 heterogeneous (+ WHetero)
+
+// Heterogeneous medium (src/medium.h:52): density grid in the box p0..p1 (device pointer), indexed like WMedium.
+struct WHetero {
+    const float* density; int32_t nx, ny, nz;
+    float invMaxDensity, p0[3], p1[3];
+    int32_t iterMax, evalTransmittanceType;
+};
 
 struct WInfinite {                  // src/infinite.h:6 with a device texel pointer
     const float* data; int32_t width, height;
@@ -71,6 +78,7 @@ struct SceneDev {
     int32_t root_leaf_count;        // > 0 when the whole scene is a single leaf (no inner node)
     int32_t integrator, max_depth;
     float eps;
+    const WHetero* het;             // non-null when some medium is heterogeneous (then k_volpath_seq renders the scene)
 };
 
 // ---- path pool -------------------------------------------------------------------------------------------

@@ -234,19 +234,29 @@ def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials
 
 
 def load_scene_json(path, prep=None, overrides=None):
-    """The subset of LoadScene (src/parsescene.cpp:45) the hot path's configs use: homogeneous media, constant
+    """The subset of LoadScene (src/parsescene.cpp:45) the hot path's configs use: homogeneous and heterogeneous media, constant
     colour materials, OBJ meshes with TRS, spheres, mesh area lights.  Raises on anything else."""
     with open(path) as f:
         doc = json.load(f)
     if overrides:
         doc.update(overrides)
     base = os.path.dirname(os.path.abspath(path))
-    medium_names, mediums = [], []
+    medium_names, mediums, densities = [], [], []
     for m in doc.get("medium", []):
-        if m.get("type", "homogeneous") != "homogeneous":
-            raise ValueError("heterogeneous media are outside the hot path (SURVEY §8(f).3)")
-        mediums.append(make_homogeneous_medium(m.get("sigmaA", [1, 1, 1]), m.get("sigmaS", [1, 1, 1]),
-                                               m.get("g", 0.0), m.get("scale", 1.0)))
+        if m.get("type", "homogeneous") == "homogeneous":
+            mediums.append(make_homogeneous_medium(m.get("sigmaA", [1, 1, 1]), m.get("sigmaS", [1, 1, 1]),
+                                                   m.get("g", 0.0), m.get("scale", 1.0)))
+        else:                                   # src/parsescene.cpp:98-132; density file: nx*ny*nz floats, x fastest (medium.h:237)
+            nx, ny, nz = int(m["nx"]), int(m["ny"]), int(m["nz"])
+            dpath = os.path.join(base, m["density"])
+            if dpath.endswith(".npz"):
+                grid = np.load(dpath)["density"].astype(F).reshape(nz, ny, nx)
+            else:
+                grid = np.loadtxt(dpath, dtype=F, max_rows=nx * ny * nz).reshape(nz, ny, nx)
+            rec, grid = make_heterogeneous_medium(m.get("sigmaA", [1, 1, 1]), m.get("sigmaS", [1, 1, 1]), grid, m["p0"], m["p1"],
+                                                  m.get("g", 0.0), m.get("scale", 1.0), int(m.get("iterMax", 1000)),
+                                                  int(m.get("evalTransmittanceType", 1)))
+            mediums.append(rec); densities.append(grid)
         medium_names.append(m["name"])
     mediums = L.cat(mediums, L.Medium)
 
@@ -325,7 +335,7 @@ def load_scene_json(path, prep=None, overrides=None):
     prims = L.cat(prims, L.Primitive)
     lights = L.cat(lights, L.Area)
     return assemble(os.path.basename(path), width, height, epsilon, integrator, max_depth, cam, materials, mediums,
-                    prims, lights, prep=prep, meta={"json": path})
+                    prims, lights, prep=prep, meta={"json": path}, densities=densities)
 
 
 # ------------------------------------------------------------------------------------------------ configs
@@ -336,6 +346,13 @@ def golden_dir():
 def cornell_pt(width=256, height=256, max_depth=4, prep=None):
     """C1/C2: shipped Cornell materials/camera/light as `pt`, with short+tall boxes."""
     return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "cornell_pt.json"), prep=prep,
+                           overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
+
+
+def cornell_shipped_smoke(width=512, height=512, max_depth=17, prep=None):
+    """scenes/cornell_box/scene.json as shipped — `vpt`, the 100 x 100 x 40 smoke grid `hhh` (ratio
+    tracking) inside the invisible boundary mesh density_render.obj; what result/heterogeneous.png shows."""
+    return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "scene_smoke_vpt.json"), prep=prep,
                            overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
 
 

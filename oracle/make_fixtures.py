@@ -42,6 +42,20 @@ def stage_scene_files():
     doc["scene"] += [{"mesh": "geometry/short.obj", "material": "General"}, {"mesh": "geometry/tall.obj", "material": "General"}]
     with open(os.path.join(dst, "cornell_pt.json"), "w") as f:
         json.dump(doc, f, indent=1)
+    # the shipped scene.json as it is (`vpt`, heterogeneous smoke `hhh` inside density_render.obj), with
+    # Right.obj lower-cased and the 3.6 MB text grid density.d (nx*ny*nz floats, src/medium.h:237) stored as float32 npz
+    with open(os.path.join(src, "scene.json")) as f:
+        doc = json.load(f)
+    for u in doc["scene"]:
+        u["mesh"] = u["mesh"].replace("Right.obj", "right.obj")
+    for m in doc["medium"]:
+        if m["type"] == "heterogeneous":
+            grid = np.loadtxt(os.path.join(src, m["density"]), dtype=np.float32, max_rows=m["nx"] * m["ny"] * m["nz"])
+            np.savez_compressed(os.path.join(dst, "geometry", "density.npz"), density=grid.reshape(m["nz"], m["ny"], m["nx"]))
+            m["density"] = "geometry/density.npz"
+    shutil.copy(os.path.join(src, "geometry", "density_render.obj"), os.path.join(dst, "geometry", "density_render.obj"))
+    with open(os.path.join(dst, "scene_smoke_vpt.json"), "w") as f:
+        json.dump(doc, f, indent=1)
     with open(os.path.join(src, "vol_caustic.json")) as f:
         doc = json.load(f)
     # C5: `vpt`, emitter swapped to the regular Cornell light (mesh_6 is 0.005 x 0.004: image mean 2.5e-5)
@@ -67,6 +81,7 @@ def main():
         "cornell_smoke_ratio_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 1, prep=prep),
         "cornell_smoke_delta_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 0, prep=prep),
         "cornell_smoke_residual_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 2, prep=prep),
+        "shipped_smoke_64": lambda: pt.scenes.cornell_shipped_smoke(64, 64, 17, prep=prep),      # the reference's own scene.json
     }
     only = [a for a in sys.argv[1:] if not a.startswith("-")]          # optional: regenerate just these fixtures
     for name, mk in scenes.items():

@@ -24,6 +24,10 @@ def make(name, size):
         return pt.scenes.veach_standin(size, size * 3 // 4, 17)
     if name == "vol":
         return pt.scenes.cornell_vol_caustic(size, size, 17)
+    if name == "shipped":                             # the reference's scenes/cornell_box/scene.json (heterogeneous smoke)
+        return pt.scenes.cornell_shipped_smoke(size, size, 17)
+    if name.startswith("smoke"):                      # smoke / smoke0 / smoke2: heterogeneous medium, Tr estimator 1 / 0 / 2
+        return pt.scenes.cornell_smoke(size, size, 8, int(name[5:] or 1))
     if name.startswith("tris"):
         return pt.scenes.random_triangles(int(name[4:] or 1000000), size, size, 8)
     raise SystemExit(name)

@@ -20,6 +20,11 @@ SCENES = {
     "random_tris_c4": (lambda: pt.scenes.random_triangles(50000, 256, 256, 8), 16),
     "vol_caustic_c5": (lambda: pt.scenes.cornell_vol_caustic(256, 256, 17), 32),
     "textured_hair": (lambda: pt.scenes.cornell_textured_hair(256, 256, 6), 32),     # textures + lines
+    # heterogeneous smoke (the shape of the reference's shipped scene.json), one per Tr estimator
+    "smoke_ratio": (lambda: pt.scenes.cornell_smoke(256, 256, 8, 1), 32),
+    "smoke_delta": (lambda: pt.scenes.cornell_smoke(256, 256, 8, 0), 32),
+    "smoke_residual": (lambda: pt.scenes.cornell_smoke(256, 256, 8, 2), 32),
+    "smoke_shipped": (lambda: pt.scenes.cornell_shipped_smoke(256, 256, 17), 16),    # the reference's own scene.json + grid
 }
 
 
@@ -87,7 +92,8 @@ def test_matches_reference_cuda_integrator(name):
     assert np.median(np.abs(tone - ref_tone)) <= 1e-6                   # tonemapped output of the last iteration
 
 
-@pytest.mark.parametrize("name", ["cornell_c1", "veach_c3", "vol_caustic_c5", "random_tris_c4", "textured_hair"])
+@pytest.mark.parametrize("name", ["cornell_c1", "veach_c3", "vol_caustic_c5", "random_tris_c4", "textured_hair", "smoke_ratio",
+                                  "smoke_delta", "smoke_residual", "smoke_shipped"])
 def test_matches_cpu_oracle(name, oracle):
     mk, _ = SCENES[name]
     s = mk()
@@ -102,7 +108,13 @@ def test_matches_cpu_oracle(name, oracle):
     # The 50k-random-triangle scene has ~1000x more silhouette edges per ray and a bright sun, so there the
     # CPU-vs-GPU check is on the FRACTION of visibly different pixels (the reference's own CUDA build is the
     # oracle of record for that scene: test_matches_reference_cuda_integrator, <= 1e-4).
-    if name == "random_tris_c4":
+    if name.startswith("smoke"):
+        # delta / ratio tracking takes a discrete decision (density / max > u) at every step of every free flight, each
+        # behind a logf: device-vs-libm last-ulp differences flip ~100x more decisions than in the surface-only scenes.
+        # The CPU oracle bounds gross errors here; parity proper is vs the reference CUDA build (above, <= 1e-4).
+        assert (rmse <= 1e-3).all(), rmse
+        assert np.allclose(acc.mean((0, 1)), ref_acc.mean((0, 1)), rtol=2e-3)
+    elif name == "random_tris_c4":
         d = np.abs(acc - ref_acc).max(-1) / spp
         assert (d > 1e-2).mean() < 2e-3, (d > 1e-2).mean()
         assert (rmse <= 1e-2).all(), rmse
