@@ -34,7 +34,7 @@ EXPORTS = [
     "b200pt_create", "b200pt_render", "b200pt_get_accum",
     "b200pt_accum_device_ptr", "b200pt_get_color", "b200pt_tonemap", "b200pt_trace_primary", "b200pt_stats",
     "b200pt_set_option", "b200pt_get_info", "b200pt_destroy", "b200pt_last_error", "b200pt_version", "b200pt_bvh_build",
-    "b200pt_bvh_build_gpu",
+    "b200pt_bvh_build_gpu", "b200pt_bvh_cache_save", "b200pt_bvh_cache_info", "b200pt_bvh_cache_load", "b200pt_bvh_load_or_build",
     "b200pt_camera_init", "b200pt_light_distribution", "b200pt_infinite_init",
 ]
 
@@ -127,6 +127,47 @@ def bvh_build(prims, gpu=False, device=0):
         check(lib.b200pt_bvh_build(prims.ctypes.data, n, prims_o.ctypes.data, nodes.ctypes.data, len(nodes),
                                    C.byref(nn), box.ctypes.data), "bvh_build")
     return prims_o, nodes[:nn.value].copy(), box, timing
+
+
+def bvh_cache_save(path, prims, nodes, box):
+    """Write the reference's bvh.cache byte stream (BVH::LoadOrBuildBVH, src/bvh.cpp:202-215)."""
+    lib = load()
+    prims = np.ascontiguousarray(prims); nodes = np.ascontiguousarray(nodes); box = np.ascontiguousarray(box, np.float32)
+    check(lib.b200pt_bvh_cache_save(os.fsencode(path), C.c_void_p(prims.ctypes.data), C.c_int32(len(prims)),
+                                    C.c_void_p(nodes.ctypes.data), C.c_int32(len(nodes)), C.c_void_p(box.ctypes.data)), "bvh_cache_save")
+
+
+def bvh_cache_info(path):
+    """(n_prims, n_nodes, root box) from the header, after checking it against the file size."""
+    lib = load()
+    npr = C.c_int32(0); nn = C.c_int32(0); box = np.zeros(6, np.float32)
+    check(lib.b200pt_bvh_cache_info(os.fsencode(path), C.byref(npr), C.byref(nn), C.c_void_p(box.ctypes.data)), "bvh_cache_info")
+    return npr.value, nn.value, box
+
+
+def bvh_cache_load(path):
+    """Read a bvh.cache (src/bvh.cpp:193-200) -> (prims in leaf order, LinearBVHNode[], root box)."""
+    lib = load()
+    n, m, _ = bvh_cache_info(path)
+    prims = np.zeros(n, L.Primitive); nodes = np.zeros(m, L.LinearBVHNode); box = np.zeros(6, np.float32)
+    npr = C.c_int32(0); nn = C.c_int32(0)
+    check(lib.b200pt_bvh_cache_load(os.fsencode(path), C.c_void_p(prims.ctypes.data), C.c_int32(n), C.c_void_p(nodes.ctypes.data),
+                                    C.c_int32(m), C.byref(npr), C.byref(nn), C.c_void_p(box.ctypes.data)), "bvh_cache_load")
+    return prims, nodes, box
+
+
+def bvh_load_or_build(path, prims, device=-1):
+    """BVH::LoadOrBuildBVH: load `path` when it holds len(prims) primitives, else build (GPU builder when device >= 0)
+    and write it.  Returns (prims in leaf order, nodes, root box, was_loaded)."""
+    lib = load()
+    prims = np.ascontiguousarray(prims)
+    n = len(prims)
+    prims_o = np.zeros(n, L.Primitive); nodes = np.zeros(2 * n + 1, L.LinearBVHNode); box = np.zeros(6, np.float32)
+    nn = C.c_int32(0); loaded = C.c_int32(0)
+    check(lib.b200pt_bvh_load_or_build(os.fsencode(path), C.c_void_p(prims.ctypes.data), C.c_int32(n), C.c_void_p(prims_o.ctypes.data),
+                                       C.c_void_p(nodes.ctypes.data), C.c_int32(len(nodes)), C.byref(nn), C.c_void_p(box.ctypes.data),
+                                       C.c_int32(device), C.byref(loaded)), "bvh_load_or_build")
+    return prims_o, nodes[:nn.value].copy(), box, bool(loaded.value)
 
 
 class HostPrep:

@@ -9,7 +9,9 @@
 #include "ref_layouts.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace {
@@ -242,4 +244,107 @@ extern "C" int b200pt_infinite_init(void* infinite72, const float* root_box6) {
     inf.radius = sqrtf(v3dot(d, d));
     std::memcpy(infinite72, &inf, sizeof(inf));
     return B200PT_OK;
+}
+
+// ---- bvh.cache (BVH::LoadOrBuildBVH, src/bvh.cpp:189-217) -------------------------------------------------------------
+// Byte stream: int total_nodes | int n_prims | float[3] root min | float[3] root max | Primitive[n_prims] |
+// LinearBVHNode[total_nodes].  The reference reads it without any validation; here the header is checked against
+// the file size before anything is copied.
+namespace {
+struct CacheHeader { int32_t n_nodes; int32_t n_prims; float box[6]; };
+static_assert(sizeof(CacheHeader) == 32, "bvh.cache header is 32 bytes");
+
+struct File {
+    FILE* fp = nullptr;
+    explicit File(const char* path, const char* mode) { fp = path ? std::fopen(path, mode) : nullptr; }
+    ~File() { if (fp) std::fclose(fp); }
+};
+
+int cache_read_header(FILE* fp, CacheHeader& h) {
+    if (std::fread(&h, sizeof(h), 1, fp) != 1) return B200PT_EINVAL;
+    if (h.n_nodes <= 0 || h.n_prims <= 0 || (int64_t)h.n_nodes > 2 * (int64_t)h.n_prims + 1) return B200PT_EINVAL;
+    if (std::fseek(fp, 0, SEEK_END) != 0) return B200PT_EINVAL;
+    const long long size = std::ftell(fp);
+    const long long want = (long long)sizeof(h) + (long long)h.n_prims * (long long)sizeof(RefPrimitive) +
+                           (long long)h.n_nodes * (long long)sizeof(RefLinearBVHNode);
+    if (size != want) return B200PT_EINVAL;
+    if (std::fseek(fp, (long)sizeof(h), SEEK_SET) != 0) return B200PT_EINVAL;
+    return B200PT_OK;
+}
+}  // namespace
+
+extern "C" int b200pt_bvh_cache_save(const char* path, const void* prims, int32_t n_prims, const void* nodes,
+                                     int32_t n_nodes, const float* root_box6) {
+    if (!path || !prims || !nodes || !root_box6 || n_prims <= 0 || n_nodes <= 0) return B200PT_EINVAL;
+    const std::string tmp = std::string(path) + ".tmp";
+    {
+        File f(tmp.c_str(), "wb");
+        if (!f.fp) return B200PT_EINVAL;
+        CacheHeader h; h.n_nodes = n_nodes; h.n_prims = n_prims; std::memcpy(h.box, root_box6, sizeof(h.box));
+        bool ok = std::fwrite(&h, sizeof(h), 1, f.fp) == 1;
+        ok = ok && std::fwrite(prims, sizeof(RefPrimitive), (size_t)n_prims, f.fp) == (size_t)n_prims;
+        ok = ok && std::fwrite(nodes, sizeof(RefLinearBVHNode), (size_t)n_nodes, f.fp) == (size_t)n_nodes;
+        ok = ok && std::fflush(f.fp) == 0;
+        if (!ok) { std::remove(tmp.c_str()); return B200PT_EINVAL; }
+    }
+    if (std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return B200PT_EINVAL; }
+    return B200PT_OK;
+}
+
+extern "C" int b200pt_bvh_cache_info(const char* path, int32_t* n_prims, int32_t* n_nodes, float* root_box6) {
+    File f(path, "rb");
+    if (!f.fp) return B200PT_EINVAL;
+    CacheHeader h;
+    const int rc = cache_read_header(f.fp, h);
+    if (rc != B200PT_OK) return rc;
+    if (n_prims) *n_prims = h.n_prims;
+    if (n_nodes) *n_nodes = h.n_nodes;
+    if (root_box6) std::memcpy(root_box6, h.box, sizeof(h.box));
+    return B200PT_OK;
+}
+
+extern "C" int b200pt_bvh_cache_load(const char* path, void* prims_out, int32_t prims_capacity, void* nodes_out,
+                                     int32_t nodes_capacity, int32_t* n_prims, int32_t* n_nodes, float* root_box6) {
+    if (!prims_out || !nodes_out || !n_prims || !n_nodes) return B200PT_EINVAL;
+    File f(path, "rb");
+    if (!f.fp) return B200PT_EINVAL;
+    CacheHeader h;
+    const int rc = cache_read_header(f.fp, h);
+    if (rc != B200PT_OK) return rc;
+    if (h.n_prims > prims_capacity || h.n_nodes > nodes_capacity) return B200PT_ENOMEM;
+    if (std::fread(prims_out, sizeof(RefPrimitive), (size_t)h.n_prims, f.fp) != (size_t)h.n_prims) return B200PT_EINVAL;
+    if (std::fread(nodes_out, sizeof(RefLinearBVHNode), (size_t)h.n_nodes, f.fp) != (size_t)h.n_nodes) return B200PT_EINVAL;
+    // Structural check of what the traversal will index with (the reference trusts the file blindly).
+    const RefLinearBVHNode* nd = (const RefLinearBVHNode*)nodes_out;
+    for (int i = 0; i < h.n_nodes; ++i) {
+        if (nd[i].is_leaf) {
+            if (nd[i].start < 0 || nd[i].end < nd[i].start || nd[i].end >= h.n_prims) return B200PT_EINVAL;
+        } else if (nd[i].second_child_offset <= i + 1 || nd[i].second_child_offset >= h.n_nodes) {
+            return B200PT_EINVAL;
+        }
+    }
+    *n_prims = h.n_prims; *n_nodes = h.n_nodes;
+    if (root_box6) std::memcpy(root_box6, h.box, sizeof(h.box));
+    return B200PT_OK;
+}
+
+extern "C" int b200pt_bvh_load_or_build(const char* path, const void* prims_in, int32_t n_prims, void* prims_out,
+                                        void* nodes_out, int32_t nodes_capacity, int32_t* n_nodes, float* root_box6,
+                                        int32_t device, int32_t* was_loaded) {
+    if (!path || !prims_in || !prims_out || !nodes_out || !n_nodes || n_prims <= 0) return B200PT_EINVAL;
+    float box[6];
+    int32_t np = 0, nn = 0;
+    if (b200pt_bvh_cache_info(path, &np, &nn, box) == B200PT_OK && np == n_prims && nn <= nodes_capacity &&
+        b200pt_bvh_cache_load(path, prims_out, n_prims, nodes_out, nodes_capacity, &np, n_nodes, box) == B200PT_OK) {
+        if (root_box6) std::memcpy(root_box6, box, sizeof(box));
+        if (was_loaded) *was_loaded = 1;
+        return B200PT_OK;
+    }
+    if (was_loaded) *was_loaded = 0;
+    const int rc = device >= 0
+        ? b200pt_bvh_build_gpu(prims_in, n_prims, prims_out, nodes_out, nodes_capacity, n_nodes, box, device, nullptr)
+        : b200pt_bvh_build(prims_in, n_prims, prims_out, nodes_out, nodes_capacity, n_nodes, box);
+    if (rc != B200PT_OK) return rc;
+    if (root_box6) std::memcpy(root_box6, box, sizeof(box));
+    return b200pt_bvh_cache_save(path, prims_out, n_prims, nodes_out, *n_nodes, box);
 }

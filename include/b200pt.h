@@ -41,7 +41,7 @@ extern "C" {
 #define B200PT_EINVAL       -1   /* bad argument / unsupported scene feature */
 #define B200PT_ECUDA        -2   /* CUDA runtime error (message in b200pt_last_error) */
 #define B200PT_ENOMEM       -3
-#define B200PT_EUNSUPPORTED -4   /* integrator / medium type outside the hot path (heterogeneous media, lines under vpt) */
+#define B200PT_EUNSUPPORTED -4   /* integrator / primitive combination outside the hot path (ao/lt/bdpt/..., lines under vpt) */
 
 /* One uchar4 texture (src/texture.h:9, uploaded at src/pathtracer.cu:2646-2661). */
 typedef struct b200pt_texture {
@@ -139,6 +139,25 @@ int b200pt_bvh_build(const void* prims_in, int32_t n_prims, void* prims_out, voi
 int b200pt_bvh_build_gpu(const void* prims_in, int32_t n_prims, void* prims_out, void* nodes_out,
                          int32_t nodes_capacity, int32_t* n_nodes, float* root_box6, int32_t device,
                          double* timing_ms4);
+
+/* The reference's `bvh.cache` file (BVH::LoadOrBuildBVH, src/bvh.cpp:189-217): int total_nodes, int n_prims,
+ * float3 root min, float3 root max, Primitive[n_prims] (176 B each, leaf order), LinearBVHNode[total_nodes] (40 B
+ * each); native endianness, no magic, no checksum.  Files written here load in the reference and vice versa.
+ *   _save: writes exactly that byte stream (temporary file + rename, so a reader never sees a torn file).
+ *   _info: reads the 32-byte header only and checks it against the file's size (the reference does not: a
+ *          truncated or foreign file there is undefined behaviour) -> B200PT_EINVAL on mismatch.
+ *   _load: fills caller arrays (capacities in records); B200PT_ENOMEM if they are too small.
+ *   _load_or_build: the reference's entry point — load `path` if it exists and holds exactly n_prims
+ *          primitives, else build (GPU builder when device >= 0, host builder when device < 0) and write it.
+ *          *was_loaded tells which.  Like the reference, a cache with the right primitive COUNT is trusted. */
+int b200pt_bvh_cache_save(const char* path, const void* prims, int32_t n_prims, const void* nodes, int32_t n_nodes,
+                          const float* root_box6);
+int b200pt_bvh_cache_info(const char* path, int32_t* n_prims, int32_t* n_nodes, float* root_box6);
+int b200pt_bvh_cache_load(const char* path, void* prims_out, int32_t prims_capacity, void* nodes_out,
+                          int32_t nodes_capacity, int32_t* n_prims, int32_t* n_nodes, float* root_box6);
+int b200pt_bvh_load_or_build(const char* path, const void* prims_in, int32_t n_prims, void* prims_out, void* nodes_out,
+                             int32_t nodes_capacity, int32_t* n_nodes, float* root_box6, int32_t device,
+                             int32_t* was_loaded);
 
 /* Camera constructor arithmetic (src/camera.h:31-47 + Lookat :124-129): fills a 104-B reference Camera. */
 int b200pt_camera_init(void* camera104, const float* position3, const float* lookat3, const float* up3,

@@ -237,6 +237,24 @@ extern "C" int refhost_scene_init(const void* prims_in, int n_prims, const void*
     if (infinite72_inout) memcpy(infinite72_inout, (const void*)&s.infinite, sizeof(Infinite));
     return 0;
 }
+// BVH::LoadOrBuildBVH (src/bvh.cpp:189-217) on a caller-chosen scene path: reads <dir>/bvh.cache if it exists, else
+// builds and writes it.  Pins b200pt_bvh_cache_* (file written here loads there and vice versa).
+extern "C" int refhost_bvh_load_or_build(const void* prims_in, int n_prims, const char* scene_file, void* prims_out,
+                                         int prims_capacity, void* nodes_out, int nodes_capacity, int* n_prims_out,
+                                         int* n_nodes, float* box6) {
+    std::vector<Primitive> prims;
+    fill_vec(prims, prims_in, n_prims);
+    BVH bvh;
+    bvh.LoadOrBuildBVH(prims, std::string(scene_file));
+    if ((int)bvh.prims.size() > prims_capacity || bvh.total_nodes > nodes_capacity) return -2;
+    memcpy(prims_out, (const void*)bvh.prims.data(), sizeof(Primitive) * bvh.prims.size());
+    memcpy(nodes_out, (const void*)bvh.linear_root, sizeof(LinearBVHNode) * (size_t)bvh.total_nodes);
+    *n_prims_out = (int)bvh.prims.size();
+    *n_nodes = bvh.total_nodes;
+    box6[0] = bvh.root_box.fmin.x; box6[1] = bvh.root_box.fmin.y; box6[2] = bvh.root_box.fmin.z;
+    box6[3] = bvh.root_box.fmax.x; box6[4] = bvh.root_box.fmax.y; box6[5] = bvh.root_box.fmax.z;
+    return 0;
+}
 extern "C" int refhost_sizeof(int which) {
     switch (which) {
         case 0: return sizeof(Camera); case 1: return sizeof(Primitive); case 2: return sizeof(LinearBVHNode);

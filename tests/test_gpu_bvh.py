@@ -55,3 +55,20 @@ def test_render_through_gpu_built_tree_is_bit_identical():
         ra.render(1, reset=True, spp=4)
         rb.render(1, reset=True, spp=4)
         assert np.array_equal(ra.accum().view(np.uint32), rb.accum().view(np.uint32))
+
+
+def test_load_or_build_with_the_gpu_builder_writes_the_reference_cache(tmp_path):
+    """BVH::LoadOrBuildBVH (src/bvh.cpp:189-217) with the build branch on the GPU: the cache file holds the host
+    builder's (= the reference's) tree, and the second call loads it."""
+    prims = scrambled(pt.scenes.random_triangles(100000, 64, 64, 8, seed=21).prims)
+    path = str(tmp_path / "bvh.cache")
+    gp, gn, gbox, loaded = _lib.bvh_load_or_build(path, prims, device=0)
+    assert not loaded
+    hp, hn, hbox, _ = _lib.bvh_build(prims, gpu=False)
+    same(gn, hn); same(gp, hp)
+    lp, ln, lbox = _lib.bvh_cache_load(path)
+    same(ln, hn); same(lp, hp)
+    assert lbox.tobytes() == hbox.tobytes()
+    p2, n2, _, loaded2 = _lib.bvh_load_or_build(path, prims, device=0)
+    assert loaded2
+    same(n2, hn); same(p2, hp)
