@@ -610,6 +610,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
     if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
+    if (n == "het_ctas_per_sm") { if (value < 1 || value > 16) return fail(B200PT_EINVAL, "het_ctas_per_sm out of range"); c->seq_blocks = c->num_sms * (int)value; return 0; }
     if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr; return 0; }
     if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; } return 0; }
     return fail(B200PT_EINVAL, "unknown option " + n);

@@ -17,6 +17,14 @@
 #include "k_shade.cuh"
 #include "k_trace.cuh"
 
+// The kernel is instruction-fetch bound when everything is inlined (closest hit at 3 call sites, tracking at 5: ncu
+// shows `no_instruction` as the top stall, 7.7 warps per issue slot), so the three big loops are real functions.
+#if defined(PT_SEQ_FORCEINLINE)
+#define PT_SEQ_FN __device__ __forceinline__
+#else
+#define PT_SEQ_FN __device__ __noinline__ inline
+#endif
+
 namespace pt {
 
 struct SeqArgs {
@@ -30,7 +38,7 @@ struct SeqArgs {
 
 // Closest hit in [eps, tmax] (Intersect, src/pathtracer.cu:214-262): near child first, subtrees behind the current
 // hit are dropped on pop; exact-t ties go to the higher primitive index like k_trace (the reference accepts tt == tmax).
-__device__ __forceinline__ bool seq_closest_hit(const SceneDev& sc, f3 o, f3 d, float tmax, Hit& out) {
+PT_SEQ_FN bool seq_closest_hit(const SceneDev& sc, f3 o, f3 d, float tmax, Hit& out) {
     const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
     float tn;
     if (!slab(sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], o, inv, tmax, tn)) return false;
@@ -97,7 +105,7 @@ __device__ __forceinline__ float het_density(const WHetero& H, f3 p) {
     return lerpf(d0, d1, delta.z);
 }
 // Heterogeneous::Tr (src/medium.h:64-135): delta (0) / ratio (1) / residual-ratio (2) tracking over [0, tmax]
-__device__ __forceinline__ f3 het_tr(const WMedium& M, const WHetero& H, f3 o, f3 dir, float tmax, uint32_t& rng) {
+PT_SEQ_FN f3 het_tr(const WMedium& M, const WHetero& H, f3 o, f3 dir, float tmax, uint32_t& rng) {
     float sigma = dot(ld3(M.sigmaT), mk3(0.212671f, 0.715160f, 0.072169f));
     const f3 p0 = ld3(H.p0);
     f3 d = ld3(H.p1) - p0;
@@ -155,7 +163,7 @@ __device__ __forceinline__ f3 seq_medium_tr(const SceneDev& sc, int medium, f3 o
     return het_tr(M, sc.het[medium], o, d, tmax, rng);
 }
 // Homogeneous::Sample (src/medium.h:19-49) / Heterogeneous::Sample (:137-157)
-__device__ __forceinline__ f3 seq_medium_sample(const SceneDev& sc, int medium, f3 o, f3 dir, float tmax, uint32_t& rng, float& t, bool& sampled) {
+PT_SEQ_FN f3 seq_medium_sample(const SceneDev& sc, int medium, f3 o, f3 dir, float tmax, uint32_t& rng, float& t, bool& sampled) {
     const WMedium& M = sc.mediums[medium];
     f3 sigmaT = ld3(M.sigmaT), sigmaS = ld3(M.sigmaS);
     float sigma = dot(sigmaT, mk3(0.212671f, 0.715160f, 0.072169f));
@@ -191,7 +199,7 @@ __device__ __forceinline__ f3 seq_medium_sample(const SceneDev& sc, int medium, 
 
 // Tr() (src/pathtracer.cu:298-322): closest hits until an opaque surface blocks the ray; the transmittance of every
 // segment comes from the medium the segment runs in, medium switch at invisible boundaries.
-__device__ __forceinline__ f3 seq_transmittance(const SceneDev& sc, f3 o, f3 d, float tmax, int medium, uint32_t& rng, uint32_t& nrays) {
+PT_SEQ_FN f3 seq_transmittance(const SceneDev& sc, f3 o, f3 d, float tmax, int medium, uint32_t& rng, uint32_t& nrays) {
     f3 tr = mk3(1, 1, 1);
     float remain = tmax;
     for (;;) {
@@ -213,8 +221,28 @@ __device__ __forceinline__ f3 seq_transmittance(const SceneDev& sc, f3 o, f3 d, 
     return tr;
 }
 
+// Shading pieces used at several places of a bounce, as real functions for the same reason (instruction footprint).
+PT_SEQ_FN void seq_light_sample(const SceneDev& sc, f3 pos, float u, float ua, float ub, LightSample& ls, float& choicePdf) {
+    int idx = lookup_light(sc, u, choicePdf);
+    if (idx < 0) idx = 0;
+    if (idx != sc.n_lights) area_sample(sc.lights[idx], pos, ua, ub, sc.eps, ls);
+    else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+}
 template <uint32_t MATS>
-__global__ void __launch_bounds__(128) k_volpath_seq(const SeqArgs a) {
+PT_SEQ_FN void seq_sample_bsdf(const SceneDev& sc, int matIdx, f2 uv, f3 wo, f3 nor, f3 dpdu, f3 u, f3& out, f3& fr, float& pdf) {
+    const Material mat = sc.mats[matIdx];
+    const f3 albedo = material_albedo(sc, mat, uv);
+    sample_bsdf_m<MATS>(mat, albedo, wo, nor, dpdu, u, out, fr, pdf);
+}
+template <uint32_t MATS>
+PT_SEQ_FN void seq_eval_bsdf(const SceneDev& sc, int matIdx, f2 uv, f3 wo, f3 wi, f3 nor, f3 dpdu, f3& fr, float& pdf) {
+    const Material mat = sc.mats[matIdx];
+    const f3 albedo = material_albedo(sc, mat, uv);
+    eval_bsdf_m<MATS>(mat, albedo, wo, wi, nor, dpdu, fr, pdf);
+}
+
+template <uint32_t MATS>
+__global__ void __launch_bounds__(128) k_volpath_seq(const __grid_constant__ SeqArgs a) {
     const SceneDev& sc = a.sc;
     const uint32_t npix = (uint32_t)a.map.n_local_pixels;
     bool alive = false;
@@ -266,13 +294,10 @@ __global__ void __launch_bounds__(128) k_volpath_seq(const SeqArgs a) {
                 const WMedium& M = sc.mediums[medium];
                 float u = rng_next(rng);
                 float choicePdf;
-                int idx = lookup_light(sc, u, choicePdf);
-                if (idx < 0) idx = 0;
                 f3 samplePos = o + sampledDist * d;
                 float ua = rng_next(rng), ub = rng_next(rng);
                 LightSample ls;
-                if (idx != sc.n_lights) area_sample(sc.lights[idx], samplePos, ua, ub, sc.eps, ls);
-                else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+                seq_light_sample(sc, samplePos, u, ua, ub, ls, choicePdf);
                 f3 tr = seq_transmittance(sc, samplePos, ls.dir, ls.tmax, medium, rng, nrays);  // unconditional, :1088
                 float phase = kInvFourPi;                                                       // Medium::Phase, src/medium.h:222
                 if (M.g != 0) {
@@ -312,29 +337,25 @@ __global__ void __launch_bounds__(128) k_volpath_seq(const SeqArgs a) {
                     o = h.pos;
                     count_bounce = false;                                                       // `bounces--; continue;`
                 } else {
-                    const Material mat = sc.mats[h.matIdx];
-                    const f3 albedo = material_albedo(sc, mat, h.uv);
+                    const int mat_type = sc.mats[h.matIdx].type;
                     const f3 wo = -d;
-                    if (!is_delta(mat.type)) {                                                  // :1128-1211
+                    if (!is_delta(mat_type)) {                                                  // :1128-1211
                         float u = rng_next(rng);
                         float choicePdf;
-                        int idx = lookup_light(sc, u, choicePdf);
-                        if (idx < 0) idx = 0;
                         float ua = rng_next(rng), ub = rng_next(rng);
                         LightSample ls;
-                        if (idx != sc.n_lights) area_sample(sc.lights[idx], h.pos, ua, ub, sc.eps, ls);
-                        else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+                        seq_light_sample(sc, h.pos, u, ua, ub, ls, choicePdf);
                         f3 Ld = mk3(0.f, 0.f, 0.f);
                         if (!is_black(ls.radiance)) {
                             f3 fr; float samplePdf;
-                            eval_bsdf_m<MATS>(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
+                            seq_eval_bsdf<MATS>(sc, h.matIdx, h.uv, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
                             f3 tr = seq_transmittance(sc, h.pos, ls.dir, ls.tmax, medium, rng, nrays);
                             float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
                             Ld += weight * tr * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
                         }
                         float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
                         f3 out, fr; float pdf;
-                        sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
+                        seq_sample_bsdf<MATS>(sc, h.matIdx, h.uv, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
                         if (!(is_black(fr) || pdf == 0)) {
                             const float absdot = fabsf(dot(out, h.nor));
                             Hit h1;
@@ -377,11 +398,11 @@ __global__ void __launch_bounds__(128) k_volpath_seq(const SeqArgs a) {
                     }
                     float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :1213-1219
                     f3 out, fr; float pdf;
-                    sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(c0, c1, c2), out, fr, pdf);
+                    seq_sample_bsdf<MATS>(sc, h.matIdx, h.uv, wo, h.nor, h.dpdu, mk3(c0, c1, c2), out, fr, pdf);
                     if (is_black(fr)) finished = true;
                     else {
                         beta *= fr * fabsf(dot(h.nor, out)) / pdf;
-                        specular = is_delta(mat.type);
+                        specular = is_delta(mat_type);
                         int m = dot(out, h.nor) > 0 ? h.mediumOutside : h.mediumInside;          // :1224-1226
                         m = dot(-d, h.nor) * dot(out, h.nor) > 0 ? medium : m;
                         medium = m;

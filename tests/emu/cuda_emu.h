@@ -15,6 +15,8 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __restrict__
 #define __shared__ static thread_local
