@@ -6,12 +6,16 @@
 // the BSDF-sampled light ray between those and the continuation sample — and each of them needs a traversal first.
 // k_shade draws a bounce's whole fixed sequence before any of its three rays is traced; with these media the order
 // would have to be shade / trace / shade / trace / shade / trace per bounce.  Until that three-phase wavefront
-// exists, such scenes run here: one lane = one path at a time, bounce by bounce in the reference's own order, with
+// exists, such scenes run here: one thread = one path at a time, bounce by bounce in the reference's own order, with
 //   * the same re-laid-out scene (64-B two-child nodes, 48-B intersection records, WShade / WLight),
 //   * ordered stack traversal with the wavefront's slab / Moeller-Trumbore arithmetic and tie rule,
-//   * per-LANE regeneration: a lane whose path ends takes the next (iteration, pixel) from the global counter at
+//   * per-THREAD regeneration: a thread whose path ends takes the next (iteration, pixel) from the global counter at
 //     the top of the bounce loop, so a warp never idles behind its longest path (the reference's megakernel does),
-//   * the same sample planes + ordered k_resolve behind it (NaN handling, accumulation, tonemap unchanged).
+//   * the same sample planes + ordered k_resolve behind it (NaN handling, accumulation, tonemap unchanged),
+//   * the big loops (closest hit, tracking, Tr walk) and the shading calls as real functions: fully inlined the kernel
+//     was instruction-fetch bound (profiles/r01z_het_seq.txt).
+// A context with such a medium runs ONE lane (b200pt_api.cu).  A warp-cooperative variant (lanes post traversal /
+// tracking operations and execute them together after a vote) was measured slower and is not in the tree.
 // No warp collectives: the kernel also runs under the 1-lane CPU emulation of the test suite.
 #pragma once
 #include "k_shade.cuh"
