@@ -518,7 +518,7 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     // Measured (profiles/r01q_lanes.txt): 3 lanes are best when the flat small-scene kernel traces (C2 +5 %), 2 otherwise.
     int n_lanes = c->small_scene ? 3 : 2;
     // heterogeneous media: k_volpath_seq is one persistent launch that fills the GPU by itself — there is no trace / shade
-    // pair to overlap, and several such launches side by side cost up to 9x at 1024^2 (measured; profiles/r01z_het_seq.txt)
+    // pair to overlap (measured: 98.7 ms with three lanes, 98.3 ms with one, 1024^2 x 8 spp), so one lane, two launches per batch
     if (c->het) n_lanes = 1;
     if (const char* env = getenv("B200PT_LANES")) n_lanes = std::max(1, std::min(8, atoi(env)));
     if (width % tw || height % th || c->map.n_local_tiles < n_lanes) n_lanes = 1;

@@ -245,8 +245,10 @@ PT_SEQ_FN void seq_eval_bsdf(const SceneDev& sc, int matIdx, f2 uv, f3 wo, f3 wi
     eval_bsdf_m<MATS>(mat, albedo, wo, wi, nor, dpdu, fr, pdf);
 }
 
+// 8 CTAs per SM (64 registers, ~600 B of spills into L1): the kernel waits on fixed-latency dependencies at 4 of 32
+// active lanes, so more resident warps pay more than the spills cost (+8 % over 4 CTAs per SM at 126 registers).
 template <uint32_t MATS>
-__global__ void __launch_bounds__(128) k_volpath_seq(const __grid_constant__ SeqArgs a) {
+__global__ void __launch_bounds__(128, 8) k_volpath_seq(const __grid_constant__ SeqArgs a) {
     const SceneDev& sc = a.sc;
     const uint32_t npix = (uint32_t)a.map.n_local_pixels;
     bool alive = false;

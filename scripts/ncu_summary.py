@@ -7,6 +7,6 @@ want=['Kernel Name','gpu__time_duration.sum','launch__registers_per_thread','lau
 for w in want:
     if w in H:
         i=H.index(w); print(f"{w:70s}", [r[i][:60] for r in rows[2:]])
-stall=[h for h in H if 'warp_issue_stalled' in h and h.endswith('_per_warp_active.pct')]
-vals=[(float(rows[2][H.index(h)] or 0),h) for h in stall]
-for v,h in sorted(vals,reverse=True)[:8]: print(f"   stall {h.replace('smsp__warp_issue_stalled_','').replace('_per_warp_active.pct',''):32s} {v:.1f}")
+stall=[h for h in H if 'issue_stalled' in h and h.endswith('_per_issue_active.ratio') and 'not_issued' not in h]
+vals=[(float((rows[2][H.index(h)] or '0').replace(',','')),h) for h in stall]
+for v,h in sorted(vals,reverse=True)[:8]: print(f"   stall (warps per issue slot) {h.replace('smsp__average_warps_issue_stalled_','').replace('_per_issue_active.ratio',''):28s} {v:.2f}")
