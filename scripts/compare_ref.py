@@ -66,7 +66,10 @@ def main():
         for kv in a.opt:
             k, v = kv.split("=")
             r.set_option(k, int(v))
-        r.render(1, reset=True, spp=2)
+        # warm-up with the timed call's batch shape: a render that needs larger sample planes than any earlier one
+        # re-allocates them (cudaFree + cudaMalloc: 1-50 ms each on the gpurun boxes, occasionally hundreds), and that
+        # would land inside the timed region; the reference arm allocates everything in BeginRender
+        r.render(1, reset=True, spp=min(a.spp, 128))
         t0 = time.time()
         r.render(1, reset=True, spp=a.spp)
         wall = (time.time() - t0) * 1e3

@@ -13,7 +13,11 @@ ap.add_argument("--spp", type=int, default=32); ap.add_argument("--reps", type=i
 ap.add_argument("--pool", type=int, default=0)
 ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--tag", default="")
+ap.add_argument("--lib", default="", help="alternative libb200pt build to load (A/B experiments)")
 a = ap.parse_args()
+if a.lib:
+    from gpu_pathtracer_b200 import _lib
+    _lib.load(a.lib)
 s = make(a.scene, a.size)
 n = s.width * s.height * a.spp
 with pt.PathTracer(s, pool=a.pool or None) as r:
