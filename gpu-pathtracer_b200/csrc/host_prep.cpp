@@ -250,7 +250,9 @@ extern "C" int b200pt_infinite_init(void* infinite72, const float* root_box6) {
 // Byte stream: int total_nodes | int n_prims | float[3] root min | float[3] root max | Primitive[n_prims] |
 // LinearBVHNode[total_nodes].  The reference reads it without any validation; here the header is checked against
 // the file size before anything is copied.
+int b200pt_internal_fail(int code, const char* msg);   // b200pt_api.cu: sets b200pt_last_error()
 namespace {
+int cache_fail(int code, const std::string& msg) { return b200pt_internal_fail(code, msg.c_str()); }
 struct CacheHeader { int32_t n_nodes; int32_t n_prims; float box[6]; };
 static_assert(sizeof(CacheHeader) == 32, "bvh.cache header is 32 bytes");
 
@@ -261,39 +263,40 @@ struct File {
 };
 
 int cache_read_header(FILE* fp, CacheHeader& h) {
-    if (std::fread(&h, sizeof(h), 1, fp) != 1) return B200PT_EINVAL;
-    if (h.n_nodes <= 0 || h.n_prims <= 0 || (int64_t)h.n_nodes > 2 * (int64_t)h.n_prims + 1) return B200PT_EINVAL;
-    if (std::fseek(fp, 0, SEEK_END) != 0) return B200PT_EINVAL;
+    if (std::fread(&h, sizeof(h), 1, fp) != 1) return cache_fail(B200PT_EINVAL, "bvh.cache: shorter than its 32-byte header");
+    if (h.n_nodes <= 0 || h.n_prims <= 0 || (int64_t)h.n_nodes > 2 * (int64_t)h.n_prims + 1)
+        return cache_fail(B200PT_EINVAL, "bvh.cache: implausible header (" + std::to_string(h.n_nodes) + " nodes, " + std::to_string(h.n_prims) + " primitives)");
+    if (std::fseek(fp, 0, SEEK_END) != 0) return cache_fail(B200PT_EINVAL, "bvh.cache: seek failed");
     const long long size = std::ftell(fp);
     const long long want = (long long)sizeof(h) + (long long)h.n_prims * (long long)sizeof(RefPrimitive) +
                            (long long)h.n_nodes * (long long)sizeof(RefLinearBVHNode);
-    if (size != want) return B200PT_EINVAL;
-    if (std::fseek(fp, (long)sizeof(h), SEEK_SET) != 0) return B200PT_EINVAL;
+    if (size != want) return cache_fail(B200PT_EINVAL, "bvh.cache: file size " + std::to_string(size) + " B does not match its header (" + std::to_string(want) + " B)");
+    if (std::fseek(fp, (long)sizeof(h), SEEK_SET) != 0) return cache_fail(B200PT_EINVAL, "bvh.cache: seek failed");
     return B200PT_OK;
 }
 }  // namespace
 
 extern "C" int b200pt_bvh_cache_save(const char* path, const void* prims, int32_t n_prims, const void* nodes,
                                      int32_t n_nodes, const float* root_box6) {
-    if (!path || !prims || !nodes || !root_box6 || n_prims <= 0 || n_nodes <= 0) return B200PT_EINVAL;
+    if (!path || !prims || !nodes || !root_box6 || n_prims <= 0 || n_nodes <= 0) return cache_fail(B200PT_EINVAL, "bvh_cache_save: null or empty argument");
     const std::string tmp = std::string(path) + ".tmp";
     {
         File f(tmp.c_str(), "wb");
-        if (!f.fp) return B200PT_EINVAL;
+        if (!f.fp) return cache_fail(B200PT_EINVAL, "bvh_cache_save: cannot create " + tmp);
         CacheHeader h; h.n_nodes = n_nodes; h.n_prims = n_prims; std::memcpy(h.box, root_box6, sizeof(h.box));
         bool ok = std::fwrite(&h, sizeof(h), 1, f.fp) == 1;
         ok = ok && std::fwrite(prims, sizeof(RefPrimitive), (size_t)n_prims, f.fp) == (size_t)n_prims;
         ok = ok && std::fwrite(nodes, sizeof(RefLinearBVHNode), (size_t)n_nodes, f.fp) == (size_t)n_nodes;
         ok = ok && std::fflush(f.fp) == 0;
-        if (!ok) { std::remove(tmp.c_str()); return B200PT_EINVAL; }
+        if (!ok) { std::remove(tmp.c_str()); return cache_fail(B200PT_EINVAL, "bvh_cache_save: short write to " + tmp); }
     }
-    if (std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return B200PT_EINVAL; }
+    if (std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return cache_fail(B200PT_EINVAL, std::string("bvh_cache_save: cannot rename onto ") + path); }
     return B200PT_OK;
 }
 
 extern "C" int b200pt_bvh_cache_info(const char* path, int32_t* n_prims, int32_t* n_nodes, float* root_box6) {
     File f(path, "rb");
-    if (!f.fp) return B200PT_EINVAL;
+    if (!f.fp) return cache_fail(B200PT_EINVAL, std::string("bvh.cache: cannot open ") + (path ? path : "(null)"));
     CacheHeader h;
     const int rc = cache_read_header(f.fp, h);
     if (rc != B200PT_OK) return rc;
@@ -305,22 +308,23 @@ extern "C" int b200pt_bvh_cache_info(const char* path, int32_t* n_prims, int32_t
 
 extern "C" int b200pt_bvh_cache_load(const char* path, void* prims_out, int32_t prims_capacity, void* nodes_out,
                                      int32_t nodes_capacity, int32_t* n_prims, int32_t* n_nodes, float* root_box6) {
-    if (!prims_out || !nodes_out || !n_prims || !n_nodes) return B200PT_EINVAL;
+    if (!prims_out || !nodes_out || !n_prims || !n_nodes) return cache_fail(B200PT_EINVAL, "bvh_cache_load: null argument");
     File f(path, "rb");
-    if (!f.fp) return B200PT_EINVAL;
+    if (!f.fp) return cache_fail(B200PT_EINVAL, std::string("bvh.cache: cannot open ") + (path ? path : "(null)"));
     CacheHeader h;
     const int rc = cache_read_header(f.fp, h);
     if (rc != B200PT_OK) return rc;
-    if (h.n_prims > prims_capacity || h.n_nodes > nodes_capacity) return B200PT_ENOMEM;
-    if (std::fread(prims_out, sizeof(RefPrimitive), (size_t)h.n_prims, f.fp) != (size_t)h.n_prims) return B200PT_EINVAL;
-    if (std::fread(nodes_out, sizeof(RefLinearBVHNode), (size_t)h.n_nodes, f.fp) != (size_t)h.n_nodes) return B200PT_EINVAL;
+    if (h.n_prims > prims_capacity || h.n_nodes > nodes_capacity) return cache_fail(B200PT_ENOMEM, "bvh_cache_load: destination arrays are too small");
+    if (std::fread(prims_out, sizeof(RefPrimitive), (size_t)h.n_prims, f.fp) != (size_t)h.n_prims) return cache_fail(B200PT_EINVAL, "bvh.cache: short read (primitives)");
+    if (std::fread(nodes_out, sizeof(RefLinearBVHNode), (size_t)h.n_nodes, f.fp) != (size_t)h.n_nodes) return cache_fail(B200PT_EINVAL, "bvh.cache: short read (nodes)");
     // Structural check of what the traversal will index with (the reference trusts the file blindly).
     const RefLinearBVHNode* nd = (const RefLinearBVHNode*)nodes_out;
     for (int i = 0; i < h.n_nodes; ++i) {
         if (nd[i].is_leaf) {
-            if (nd[i].start < 0 || nd[i].end < nd[i].start || nd[i].end >= h.n_prims) return B200PT_EINVAL;
+            if (nd[i].start < 0 || nd[i].end < nd[i].start || nd[i].end >= h.n_prims)
+                return cache_fail(B200PT_EINVAL, "bvh.cache: leaf " + std::to_string(i) + " ranges outside the primitive array");
         } else if (nd[i].second_child_offset <= i + 1 || nd[i].second_child_offset >= h.n_nodes) {
-            return B200PT_EINVAL;
+            return cache_fail(B200PT_EINVAL, "bvh.cache: node " + std::to_string(i) + " links outside the node array");
         }
     }
     *n_prims = h.n_prims; *n_nodes = h.n_nodes;
@@ -331,7 +335,7 @@ extern "C" int b200pt_bvh_cache_load(const char* path, void* prims_out, int32_t 
 extern "C" int b200pt_bvh_load_or_build(const char* path, const void* prims_in, int32_t n_prims, void* prims_out,
                                         void* nodes_out, int32_t nodes_capacity, int32_t* n_nodes, float* root_box6,
                                         int32_t device, int32_t* was_loaded) {
-    if (!path || !prims_in || !prims_out || !nodes_out || !n_nodes || n_prims <= 0) return B200PT_EINVAL;
+    if (!path || !prims_in || !prims_out || !nodes_out || !n_nodes || n_prims <= 0) return cache_fail(B200PT_EINVAL, "bvh_load_or_build: null or empty argument");
     float box[6];
     int32_t np = 0, nn = 0;
     if (b200pt_bvh_cache_info(path, &np, &nn, box) == B200PT_OK && np == n_prims && nn <= nodes_capacity &&
