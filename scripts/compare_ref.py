@@ -28,6 +28,8 @@ def make(name, size):
         return pt.scenes.cornell_shipped_smoke(size, size, 17)
     if name.startswith("smoke"):                      # smoke / smoke0 / smoke2: heterogeneous medium, Tr estimator 1 / 0 / 2
         return pt.scenes.cornell_smoke(size, size, 8, int(name[5:] or 1))
+    if name == "hair":                                # textures + Line primitives
+        return pt.scenes.cornell_textured_hair(size, size, 6)
     if name.startswith("tris"):
         return pt.scenes.random_triangles(int(name[4:] or 1000000), size, size, 8)
     raise SystemExit(name)
