@@ -257,10 +257,12 @@ PT_SEQ_FN void seq_eval_bsdf(const SceneDev& sc, int matIdx, f2 uv, f3 wo, f3 wi
     eval_bsdf_m<MATS>(mat, albedo, wo, wi, nor, dpdu, fr, pdf);
 }
 
-// 8 CTAs per SM (64 registers, ~600 B of spills into L1): the kernel waits on fixed-latency dependencies at 4 of 32
-// active lanes, so more resident warps pay more than the spills cost (+8 % over 4 CTAs per SM at 126 registers).
+// 12 CTAs per SM (40 registers, ~870 B of spills into L1): the kernel waits on fixed-latency dependencies at 4 of 32
+// active lanes, so resident warps pay more than spills cost.  Measured (smoke 1024^2 / shipped scene 512^2, Msamples/s):
+// 4 CTAs (126 registers) 83 / 51 before the lookup change; then 5: 90 / 58, 6: 92 / 59, 8: 99 / 62, 10: 103 / 63,
+// 12: 105 / 62, 16: 106 / 61.
 template <uint32_t MATS>
-__global__ void __launch_bounds__(128, 8) k_volpath_seq(const __grid_constant__ SeqArgs a) {
+__global__ void __launch_bounds__(128, 12) k_volpath_seq(const __grid_constant__ SeqArgs a) {
     const SceneDev& sc = a.sc;
     const uint32_t npix = (uint32_t)a.map.n_local_pixels;
     bool alive = false;
