@@ -217,8 +217,13 @@ __device__ __forceinline__ void eval_bsdf_m(const Material& m, f3 albedo, f3 in,
     fr = mk3(0, 0, 0); pdf = 0.f;
 }
 
+// Resident CTAs per SM: the kernel is latency bound (long scoreboard), so occupancy beats registers — 8 CTAs (64
+// registers; the lambertian kernel does not even spill) is +3 % on C2 and +6.5 % on C3 over the unconstrained 70 / 96
+// registers; the volumetric instantiations carry one more staged plane and more live state: 6 CTAs (80 registers) is
+// +3.4 % on C5 where 8 is -9 %; the all-materials kernel spills 144 B at 64 registers (-2 % on the textured-hair
+// scene), so it stays at 6 as well (same-box A/B, profiles/r01z_perf_all_configs.txt).
 template <bool VOL, uint32_t MATS>
-__global__ void __launch_bounds__(128) k_shade(const ShadeArgs a) {
+__global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shade(const ShadeArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;      // the pool size is a multiple of the block size
     const SceneDev& sc = a.sc;
     const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
