@@ -41,9 +41,10 @@ ALGO = {
 # ncu-measured DRAM traffic per sample, whole wavefront (see profiles/); filled in from the capture of the round
 DRAM_BYTES_PER_SAMPLE = {"c2": 1684.0}     # profiles/r01s_launches_summary.txt: 21.2 GB over 12.6 Msamples
 # warp instructions per pool slot and wavefront step (ncu smsp__inst_executed.sum of one k_trace_small + one k_shade launch
-# over a 2^20-slot pool, profiles/r01w_ncu_trace.txt + r01w_ncu_shade.txt): the kernels of C2 are instruction-issue bound
-# (the scene lives in shared memory), so the JSON also carries the fraction of the SMs' issue rate they reach
-WARP_INST_PER_SLOT_STEP = {"c2": (134.17e6 + 43.86e6) / float(1 << 20)}
+# over a 2^20-slot pool, profiles/r01z_ncu_wavefront_kernels.txt; r01w: 134.17e6 + 43.86e6): the kernels of C2 are
+# instruction-issue bound (the scene lives in shared memory), so the JSON also carries the fraction of the SMs' issue
+# rate they reach
+WARP_INST_PER_SLOT_STEP = {"c2": (134.10e6 + 43.13e6) / float(1 << 20)}
 
 
 def algo_bytes_per_sample(w):
@@ -293,7 +294,7 @@ def main():
             peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
             roofline["issue"] = {"warp_inst_per_sample": inst / (samples / world), "achieved_warp_inst_per_s": inst / kernel_s,
                                  "peak_warp_inst_per_s": peak_issue, "frac": inst / kernel_s / peak_issue,
-                                 "note": "148 SMs x 4 schedulers x SM clock; instruction counts from ncu (profiles/r01w_*)"}
+                                 "note": "148 SMs x 4 schedulers x SM clock; instruction counts from ncu (profiles/r01z_ncu_wavefront_kernels.txt)"}
         cb = None
         if not a.no_cpu_baseline and world == 1:
             cb, _, _ = cpu_reference(scene, 12.0)          # bounded sample of the SAME workload on the host cores
