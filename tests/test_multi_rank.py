@@ -25,14 +25,20 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, spp, out_path):
+def _scene(pt, name):
+    if name == "smoke":                                  # heterogeneous medium, sequential kernel, one lane
+        return pt.scenes.cornell_smoke(128, 64, 6, 1)
+    return pt.scenes.cornell_pt(128, 64, 6)
+
+
+def _worker(rank, world, port, spp, out_path, scene_name):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import gpu_pathtracer_b200 as pt
     from gpu_pathtracer_b200 import _lib
     _lib.load(EMU)
-    s = pt.scenes.cornell_pt(128, 64, 6)
+    s = _scene(pt, scene_name)
     with pt.PathTracer(s, shard=(rank, world, 32, 32)) as r:
         acc = None
         for batch in range(2):                                   # two spp batches, one reduce each (north_star)
@@ -46,18 +52,19 @@ def _worker(rank, world, port, spp, out_path):
 
 
 @pytest.mark.timeout(300)
-def test_two_ranks_reduce_to_the_single_rank_image(tmp_path):
+@pytest.mark.parametrize("scene_name", ["cornell", "smoke"])
+def test_two_ranks_reduce_to_the_single_rank_image(tmp_path, scene_name):
     sys.path.insert(0, ROOT)
     import gpu_pathtracer_b200 as pt
     from gpu_pathtracer_b200 import _lib
     spp = 2
     out = str(tmp_path / "acc.npy")
-    mp.spawn(_worker, args=(2, _free_port(), spp, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), spp, out, scene_name), nprocs=2, join=True)
     got = np.load(out)
     saved = _lib._lib
     _lib.load(EMU)
     try:
-        s = pt.scenes.cornell_pt(128, 64, 6)
+        s = _scene(pt, scene_name)
         with pt.PathTracer(s) as r:
             r.render(1, reset=True, spp=2 * spp)
             full = r.accum()
