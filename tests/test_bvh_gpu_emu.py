@@ -61,3 +61,21 @@ def test_gpu_builder_edge_cases(emu):
     out = np.zeros(64, L.Primitive); nodes = np.zeros(3, L.LinearBVHNode)
     rc = lib.b200pt_bvh_build_gpu(tri.ctypes.data, 64, out.ctypes.data, nodes.ctypes.data, 3, C.byref(nn), None, 0, None)
     assert rc == -3 and b"capacity" in lib.b200pt_last_error()          # B200PT_ENOMEM
+
+
+def test_load_or_build_through_the_gpu_builder_sources(emu, tmp_path):
+    """BVH::LoadOrBuildBVH (src/bvh.cpp:189-217) with the build branch on the (emulated) GPU builder: the cache file
+    holds the host builder's tree, byte for byte, and the second call takes the load branch."""
+    prims = pt.scenes.random_triangles(3000, 16, 16, 2, seed=31).prims
+    prims = prims[np.random.default_rng(2).permutation(len(prims))]
+    path = str(tmp_path / "bvh.cache")
+    gp, gn, gbox, loaded = _lib.bvh_load_or_build(path, prims, device=0)
+    assert not loaded
+    hp, hn, hbox, _ = _lib.bvh_build(prims, gpu=False)
+    _same(gn, hn); _same(gp, hp)
+    lp, ln, lbox = _lib.bvh_cache_load(path)
+    _same(ln, hn); _same(lp, hp)
+    assert lbox.tobytes() == hbox.tobytes()
+    p2, n2, _, loaded2 = _lib.bvh_load_or_build(path, prims, device=0)
+    assert loaded2
+    _same(n2, hn); _same(p2, hp)
