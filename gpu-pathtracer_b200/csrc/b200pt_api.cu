@@ -609,6 +609,24 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
         }
         return 0;
     }
+    if (n == "reserve_iters") {
+        // Pre-size every lane's sample planes for batches of up to `value` iterations, so that no later b200pt_render has
+        // to re-allocate them inside the call (cudaFree + cudaMalloc there cost 1-50 ms each, occasionally far more).
+        if (value < 1 || value > (1 << 20)) return fail(B200PT_EINVAL, "reserve_iters out of range");
+        CK(cudaSetDevice(c->device));
+        // b200pt_render never puts more iterations into one batch than fit max_batch_bytes (over all lanes)
+        const size_t per_iter = (size_t)std::max(1, c->map.n_local_pixels) * sizeof(float4);
+        const size_t iters = std::min<size_t>((size_t)value, std::max<size_t>(1, c->max_batch_bytes / per_iter));
+        for (Lane& L : c->lanes) {
+            const size_t need = iters * (size_t)L.map.n_local_pixels;
+            if (need <= L.samples_cap) continue;
+            if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
+            cudaError_t e = cudaMalloc((void**)&L.samples, need * sizeof(float4));
+            if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc of the sample planes: ") + cudaGetErrorString(e));
+            L.samples_cap = need;
+        }
+        return 0;
+    }
     if (n == "steps_per_poll") { if (value < 1 || value > 1024) return fail(B200PT_EINVAL, "steps_per_poll out of range"); c->steps_per_poll = (int)value; return 0; }
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
     if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }

@@ -113,7 +113,8 @@ int b200pt_stats(b200pt_ctx* ctx, double* out5);
  * "groups" (primitive groups of the small-scene kernel, 0 if the tree kernel is used), "small_kernel", "lambert_only". */
 int b200pt_get_info(b200pt_ctx* ctx, const char* name, int64_t* out_value);
 
-/* Tunables (pool = number of path slots in flight; 0 keeps default). */
+/* Tunables (pool = number of path slots in flight; 0 keeps default).  "reserve_iters" = n pre-sizes the sample planes
+ * for batches of up to n iterations, so that no later b200pt_render allocates inside the call. */
 int b200pt_set_option(b200pt_ctx* ctx, const char* name, int64_t value);
 
 /* Replaces EndRender (src/pathtracer.cu:2697); frees ALL device memory of the context. */

@@ -203,3 +203,19 @@ def test_heterogeneous_medium_is_ignored_by_pt(emu, oracle):
     with pt.PathTracer(base) as r:
         r.render(1, reset=True, spp=2)
         assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+
+
+def test_reserve_iters_presizes_the_sample_planes(emu, oracle):
+    """`reserve_iters` allocates the sample planes ahead of the first large batch (so b200pt_render does not have to
+    inside the call); the image is the same with or without it, and nonsense values are rejected."""
+    s = pt.scenes.cornell_pt(64, 64, 4)
+    ref_acc, _ = oracle.render(s, 1, 6)
+    with pt.PathTracer(s) as r:
+        r.set_option("reserve_iters", 6)
+        r.render(1, reset=True, spp=6)
+        acc = r.accum()
+        with pytest.raises(RuntimeError):
+            r.set_option("reserve_iters", 0)
+        r.set_option("max_batch_bytes", 1 << 20)                 # 16 iterations of 64 x 64 per batch
+        r.set_option("reserve_iters", 1 << 20)                   # clamped to that budget, not an error
+    assert np.array_equal(_bits(acc), _bits(ref_acc))
