@@ -4,6 +4,7 @@
 #   oracle/_ref/libref_host.so       the same kernel bodies compiled by g++ (no FMA contraction; pins oracle/pt_oracle.cpp)
 #   oracle/_ref/libref_host_fast.so  same, -O3 -march=x86-64-v3, for the CPU-baseline timing only
 #   oracle/_ref/libadapter.so        the product's reference-signature adapter compiled against the reference headers
+#   oracle/_ref/libadapter_emu.so    the same adapter linked against the CPU emulation build (tests/emu), for the GPU-less suite
 # Only binaries are written into the repo tree (oracle/_ref/ is git-ignored, but travels with gpurun).
 # The reference's own build system (CMake + Windows libs) is NOT used; see DESIGN.md.
 set -euo pipefail
@@ -67,5 +68,12 @@ if [ -f "$CSRC/libb200pt.so" ]; then
   g++ -O2 -w -fPIC -std=c++17 -I"$WORK/src" $INC -I/usr/local/cuda/include -c "$HOSTDIR/adapter_harness.cpp" -o "$WORK/adapter_h.o"
   g++ -shared "$WORK/adapter.o" "$WORK/adapter_h.o" "$WORK/bvh.o" -o "$OUT/libadapter.so" -L"$CSRC" -lb200pt \
       -Wl,-rpath,'$ORIGIN/../../gpu-pathtracer_b200/csrc' -L/usr/local/cuda/lib64 -lcudart
+  # the same adapter against the CPU emulation build of the product (drop-in boundary on GPU-less machines)
+  EMU="$HERE/../tests/emu"
+  if [ -f "$EMU/libb200pt_emu.so" ]; then
+    g++ -O2 -w -fPIC -std=c++17 -I/usr/local/cuda/include -c "$HERE/refbuild/cudart_host_shim.cpp" -o "$WORK/cudart_shim.o"
+    g++ -shared "$WORK/adapter.o" "$WORK/adapter_h.o" "$WORK/bvh.o" "$WORK/cudart_shim.o" -o "$OUT/libadapter_emu.so" -L"$EMU" -lb200pt_emu \
+        -Wl,-rpath,'$ORIGIN/../../tests/emu'
+  fi
 fi
 ls -la "$OUT"

@@ -247,8 +247,9 @@ class Adapter:
     """The product behind the reference-signature C++ entry points (gpu-pathtracer_b200/host/pathtracer_adapter.cpp
     compiled against the reference's headers into oracle/_ref/libadapter.so) — what main.cpp would call."""
 
-    def __init__(self):
-        self.lib = C.CDLL(os.path.join(REF_DIR, "libadapter.so"))
+    def __init__(self, name="libadapter.so"):
+        # libadapter_emu.so: the same adapter objects linked against tests/emu/libb200pt_emu.so (CPU)
+        self.lib = C.CDLL(os.path.join(REF_DIR, name))
 
     def begin(self, scene, width=None, height=None):
         from gpu_pathtracer_b200 import _lib
