@@ -68,12 +68,13 @@ if [ -f "$CSRC/libb200pt.so" ]; then
   g++ -O2 -w -fPIC -std=c++17 -I"$WORK/src" $INC -I/usr/local/cuda/include -c "$HOSTDIR/adapter_harness.cpp" -o "$WORK/adapter_h.o"
   g++ -shared "$WORK/adapter.o" "$WORK/adapter_h.o" "$WORK/bvh.o" -o "$OUT/libadapter.so" -L"$CSRC" -lb200pt \
       -Wl,-rpath,'$ORIGIN/../../gpu-pathtracer_b200/csrc' -L/usr/local/cuda/lib64 -lcudart
-  # the same adapter against the CPU emulation build of the product (drop-in boundary on GPU-less machines)
+  # the same adapter against the CPU emulation build of the product (drop-in boundary on GPU-less machines);
+  # -Bsymbolic: the harness's cudaMalloc & co. bind to the host shim in this .so even when a real libcudart is loaded
   EMU="$HERE/../tests/emu"
   if [ -f "$EMU/libb200pt_emu.so" ]; then
     g++ -O2 -w -fPIC -std=c++17 -I/usr/local/cuda/include -c "$HERE/refbuild/cudart_host_shim.cpp" -o "$WORK/cudart_shim.o"
     g++ -shared "$WORK/adapter.o" "$WORK/adapter_h.o" "$WORK/bvh.o" "$WORK/cudart_shim.o" -o "$OUT/libadapter_emu.so" -L"$EMU" -lb200pt_emu \
-        -Wl,-rpath,'$ORIGIN/../../tests/emu'
+        -Wl,-Bsymbolic -Wl,-rpath,'$ORIGIN/../../tests/emu'
   fi
 fi
 ls -la "$OUT"
