@@ -219,3 +219,17 @@ def test_reserve_iters_presizes_the_sample_planes(emu, oracle):
         r.set_option("max_batch_bytes", 1 << 20)                 # 16 iterations of 64 x 64 per batch
         r.set_option("reserve_iters", 1 << 20)                   # clamped to that budget, not an error
     assert np.array_equal(_bits(acc), _bits(ref_acc))
+
+
+def test_default_lane_counts(emu, monkeypatch):
+    """Three lanes when the small-scene kernel traces, two otherwise, ONE for heterogeneous media (k_volpath_seq is a
+    single persistent launch that fills the GPU) — and B200PT_LANES overrides all of them."""
+    monkeypatch.delenv("B200PT_LANES", raising=False)
+    for mk, want in ((lambda: pt.scenes.cornell_pt(128, 128, 4), 3),
+                     (lambda: pt.scenes.random_triangles(2000, 128, 128, 4), 2),
+                     (lambda: pt.scenes.cornell_smoke(128, 128, 4, 1), 1)):
+        with pt.PathTracer(mk()) as r:
+            assert r.info("lanes") == want
+    monkeypatch.setenv("B200PT_LANES", "2")
+    with pt.PathTracer(pt.scenes.cornell_smoke(128, 128, 4, 1)) as r:
+        assert r.info("lanes") == 2
