@@ -201,14 +201,25 @@ bool prim_intersect(const RefPrimitive& p, Ray& ray, Isect* isect) {
     return line_intersect(p.u.line, ray, isect);
 }
 
+// Traversal statistics of SURVEY 8(d) — rays, box tests and primitive tests AS EXECUTED BY THE REFERENCE TRAVERSAL (the
+// R, N, P, H of the algorithmic-bytes formula bench.py uses).  Off by default; oracle_count(1) switches them on.
+// [0] closest-hit queries, [1] any-hit queries, [2] box tests, [3] primitive tests.
+static bool g_counting = false;
+static unsigned long long g_counts[4];
+#define ORACLE_COUNT(i, n) do { if (g_counting) { _Pragma("omp atomic") g_counts[i] += (n); } } while (0)
+
 // Intersect (closest hit), src/pathtracer.cu:214-255: fixed left-then-right DFS over LinearBVHNode[]
 bool intersect(Ray& ray, Isect* isect) {
     int stack[64]; int top = 0;
     bool ret = false;
     int node_idx = 0;
+    unsigned nb = 0, np = 0;
+    struct Flush { unsigned& b; unsigned& p; ~Flush() { ORACLE_COUNT(0, 1); ORACLE_COUNT(2, b); ORACLE_COUNT(3, p); } } flush{nb, np};
     for (;;) {
         const RefLinearBVHNode& node = g->nodes[node_idx];
+        ++nb;
         if (bbox_intersect(node.fmin, node.fmax, ray)) {
+            if (node.is_leaf) np += (unsigned)(node.end - node.start + 1);
             if (!node.is_leaf) {
                 stack[top++] = node.second_child_offset;
                 stack[top++] = node_idx + 1;
@@ -226,15 +237,20 @@ bool intersect(Ray& ray, Isect* isect) {
 bool intersect_p(Ray& ray) {
     int stack[64]; int top = 0;
     int node_idx = 0;
+    unsigned nb = 0, np = 0;
+    struct Flush { unsigned& b; unsigned& p; ~Flush() { ORACLE_COUNT(1, 1); ORACLE_COUNT(2, b); ORACLE_COUNT(3, p); } } flush{nb, np};
     for (;;) {
         const RefLinearBVHNode& node = g->nodes[node_idx];
+        ++nb;
         if (bbox_intersect(node.fmin, node.fmax, ray)) {
             if (!node.is_leaf) {
                 stack[top++] = node.second_child_offset;
                 stack[top++] = node_idx + 1;
             } else {
-                for (int i = node.start; i <= node.end; ++i)
+                for (int i = node.start; i <= node.end; ++i) {
+                    ++np;
                     if (prim_intersect(g->prims[i], ray, nullptr)) return true;
+                }
             }
         }
         if (top == 0) break;
@@ -797,6 +813,8 @@ extern "C" int oracle_render(unsigned first_iter, unsigned n, int reset_first, f
 }
 extern "C" int oracle_get_accum(float* host) { if (!g) return -1; std::memcpy(host, g->acc.data(), sizeof(f3) * g->acc.size()); return 0; }
 extern "C" int oracle_get_color(float* host) { if (!g) return -1; std::memcpy(host, g->color.data(), sizeof(f3) * g->color.size()); return 0; }
+extern "C" void oracle_count(int on) { g_counting = on != 0; for (auto& c : g_counts) c = 0; }
+extern "C" void oracle_get_counts(unsigned long long* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_counts[i]; }
 extern "C" int oracle_end() { if (!g) return -1; delete g; g = nullptr; return 0; }
 
 // ---- function-level entry points (same signatures as the refhost_* ones in oracle/refbuild/ref_host_harness.cpp)

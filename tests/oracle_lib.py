@@ -41,6 +41,22 @@ class Oracle:
         self.lib.oracle_get_color(C.c_void_p(a.ctypes.data))
         return a
 
+    def traversal_counts(self, scene, first_iter, spp, threads=0):
+        """per-sample R (rays), N (box tests per ray), P (primitive tests per ray), H (closest-hit queries per
+        sample) of the REFERENCE traversal on this scene — the inputs of bench.py's algorithmic-bytes formula."""
+        self.begin(scene)
+        try:
+            self.lib.oracle_count(C.c_int(1))
+            self.render_iters(first_iter, spp, True, threads)
+            c = (C.c_ulonglong * 4)()
+            self.lib.oracle_get_counts(c)
+            self.lib.oracle_count(C.c_int(0))
+        finally:
+            self.end()
+        n = float(self.w * self.h * spp)
+        rays = float(c[0] + c[1])
+        return {"R": rays / n, "N": c[2] / rays, "P": c[3] / rays, "H": c[0] / n}
+
     def render(self, scene, first_iter, spp, threads=0, width=None, height=None):
         """(accum, tonemapped) of iterations first_iter..first_iter+spp-1 starting from a reset."""
         self.begin(scene, width, height)
