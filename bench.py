@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the hot path (BASELINE.json: Msamples/s of the unidirectional path tracer).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5|smoke|shipped]
 
 A "step" = one batch of `--spp-per-step` iterations (Render calls) of the workload image through the hot path.
 Default workload: C2 = Cornell box 1024x1024, depth 8 (the configuration the metric is quoted on; K steps of
@@ -35,6 +35,8 @@ ALGO = {
     "c3": dict(R=13.37, N=13.62, P=7.25),
     "c4": dict(R=10.26, N=233.7, P=66.9),
     "c5": dict(R=12.92, N=10.68, P=4.01),
+    "smoke": dict(R=13.09, N=17.82, P=11.28),      # SURVEY 8(f).3 scenes (heterogeneous media)
+    "shipped": dict(R=15.80, N=11.75, P=7.70),
 }
 
 
@@ -64,6 +66,10 @@ def make_scene(pt, name):
         return pt.scenes.random_triangles(1_000_000, 2048, 2048, 8), "1M random triangles + analytic HDRI 2048x2048 depth=8 (configs[3])"
     if name == "c5":
         return pt.scenes.cornell_vol_caustic(512, 512, 17), "cornell_box vol_caustic homogeneous medium vpt 512x512 depth=17 (configs[4])"
+    if name == "smoke":
+        return pt.scenes.cornell_smoke(1024, 1024, 8, 1), "cornell_box + heterogeneous smoke (ratio tracking) vpt 1024x1024 depth=8 (SURVEY 8(f).3)"
+    if name == "shipped":
+        return pt.scenes.cornell_shipped_smoke(1024, 1024, 17), "the reference's shipped cornell_box/scene.json (heterogeneous medium) vpt 1024x1024 depth=17"
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -15,6 +15,8 @@ SCENES = {   # reduced image sizes: the per-sample averages do not depend on the
     "c2": (lambda: pt.scenes.cornell_pt(128, 128, 8), 8),
     "c3": (lambda: pt.scenes.veach_standin(192, 144, 17), 4),
     "c5": (lambda: pt.scenes.cornell_vol_caustic(128, 128, 17), 8),
+    "smoke": (lambda: pt.scenes.cornell_smoke(128, 128, 8, 1), 8),
+    "shipped": (lambda: pt.scenes.cornell_shipped_smoke(128, 128, 17), 8),
 }
 
 
