@@ -166,7 +166,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
             std::memcpy(s.uv1, t.v1.uv, 8); std::memcpy(s.uv2, t.v2.uv, 8); std::memcpy(s.uv3, t.v3.uv, 8);
             s.matIdx = t.matIdx; s.lightIdx = t.lightIdx; s.mediumInside = t.mediumInside; s.mediumOutside = t.mediumOutside;
             s.type = 0;
-            if (t.matIdx >= v->n_materials || (t.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
+            if (t.matIdx >= v->n_materials || t.matIdx < -1 || (t.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
                 return fail(B200PT_EINVAL, "triangle " + std::to_string(i) + " has material index " + std::to_string(t.matIdx) +
                                                " (a material-less medium boundary needs the vpt integrator)");
             if (t.lightIdx >= v->n_lights) return fail(B200PT_EINVAL, "triangle light index out of range");
@@ -178,7 +178,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
             std::memcpy(s.n1, sp.origin, 12); s.n2[0] = sp.radius;
             s.matIdx = sp.matIdx; s.lightIdx = -1; s.mediumInside = sp.mediumInside; s.mediumOutside = sp.mediumOutside;
             s.type = 1;
-            if (sp.matIdx >= v->n_materials || (sp.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
+            if (sp.matIdx >= v->n_materials || sp.matIdx < -1 || (sp.matIdx < 0 && v->integrator_type == B200PT_IT_PT))
                 return fail(B200PT_EINVAL, "sphere material index out of range");
         } else if (p.type == REF_GT_LINES) {
             // Line::Intersect leaves the hit's medium fields untouched (src/line.h:74-83), which Volpath would then read
@@ -194,7 +194,9 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         } else {
             return fail(B200PT_EINVAL, "unknown primitive type");
         }
-        if (s.mediumInside >= v->n_mediums || s.mediumOutside >= v->n_mediums) return fail(B200PT_EINVAL, "medium index out of range");
+        if (s.mediumInside >= v->n_mediums || s.mediumOutside >= v->n_mediums || s.mediumInside < -1 || s.mediumOutside < -1)
+            return fail(B200PT_EINVAL, "medium index out of range");
+        if (s.lightIdx < -1) return fail(B200PT_EINVAL, "light index out of range");
     }
     // -- nodes: reference DFS layout (left child = i+1, right = second_child_offset) -> two-child records
     // inner nodes are renumbered breadth-first, so that the first K records are the top of the tree (the part
@@ -422,7 +424,9 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     if (v->n_light_distribution != expect)
         return fail(B200PT_EINVAL, "light distribution has " + std::to_string(v->n_light_distribution) + " entries, expected " + std::to_string(expect));
     sc.integrator = v->integrator_type; sc.max_depth = v->max_depth;
-    if (v->max_depth < 0 || v->max_depth > 127) return fail(B200PT_EINVAL, "maxDepth must be in [0, 127]");
+    // (maxDepth 0: the reference's `for (bounces = 0; bounces < maxDepth; ...)` never runs and the image is black; a
+    // wavefront slot always traces its primary ray, so that degenerate setting is rejected instead of approximated)
+    if (v->max_depth < 1 || v->max_depth > 127) return fail(B200PT_EINVAL, "maxDepth must be in [1, 127]");
     c->vol = v->integrator_type == B200PT_IT_VPT;
 
     // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
@@ -467,6 +471,21 @@ static int lane_pool_size(const b200pt_ctx* c, const Lane& L) {
     if (L.map.n_local_pixels > pool && (double)L.map.n_local_pixels <= 1.1 * pool) pool = L.map.n_local_pixels;
     if ((size_t)pool > (size_t)L.map.n_local_pixels * 4) pool = std::max(1024, L.map.n_local_pixels * 4);
     return pool;
+}
+
+// The ONE place sample planes are (re)allocated.  A captured frame graph has the old pointer baked into its kernel
+// arguments, so it is destroyed (after a device sync) whenever the planes move.
+static int ensure_samples(b200pt_ctx* c, Lane& L, size_t need) {
+    if (need <= L.samples_cap && L.samples) return 0;
+    need = std::max<size_t>(need, 1);
+#ifndef B200PT_EMULATE
+    if (c->graph_exec) { CK(cudaDeviceSynchronize()); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+#endif
+    if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
+    cudaError_t e = cudaMalloc((void**)&L.samples, need * sizeof(float4));
+    if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc of the sample planes: ") + cudaGetErrorString(e));
+    L.samples_cap = need;
+    return 0;
 }
 
 static void fill_map(ShardMap& m, uint32_t width, uint32_t height, int shard, int n_shards, int tile_w, int tile_h) {
@@ -574,6 +593,13 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&seq_per_sm, k_volpath_seq<kMatsAll>, 128, 0);
         c->seq_blocks = c->num_sms * std::max(seq_per_sm, 1);
     }
+#ifdef B200PT_PROBE
+    if (const char* env = getenv("B200PT_PROBE")) {           // "pixel,iter" (diagnostic build only)
+        int pr[2] = {-1, -1};
+        sscanf(env, "%d,%d", &pr[0], &pr[1]);
+        cudaMemcpyToSymbol(g_probe, pr, sizeof(pr));
+    }
+#endif
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError())));
     *out_ctx = c;
     return B200PT_OK;
@@ -619,11 +645,8 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
         const size_t iters = std::min<size_t>((size_t)value, std::max<size_t>(1, c->max_batch_bytes / per_iter));
         for (Lane& L : c->lanes) {
             const size_t need = iters * (size_t)L.map.n_local_pixels;
-            if (need <= L.samples_cap) continue;
-            if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
-            cudaError_t e = cudaMalloc((void**)&L.samples, need * sizeof(float4));
-            if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc of the sample planes: ") + cudaGetErrorString(e));
-            L.samples_cap = need;
+            int rc = ensure_samples(c, L, need);
+            if (rc) return rc;
         }
         return 0;
     }
@@ -687,10 +710,8 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         const size_t need = (size_t)n_iters * L.map.n_local_pixels;
         if (need > L.samples_cap) {
             if (capture) return fail(B200PT_ECUDA, "internal: sample planes must be allocated before capture");
-            if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
-            cudaError_t e = cudaMalloc((void**)&L.samples, need * sizeof(float4));
-            if (e != cudaSuccess) return fail(B200PT_ENOMEM, std::string("cudaMalloc of the sample planes: ") + cudaGetErrorString(e));
-            L.samples_cap = need;
+            int rc = ensure_samples(c, L, need);
+            if (rc) return rc;
         }
         BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
         if (c->het) {
@@ -793,7 +814,7 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     if (first_iter == 0) return fail(B200PT_EINVAL, "iter is 1-based (src/main.cpp:178 increments before the first Render)");
     CK(cudaSetDevice(c->device));
     Camera cam; std::memcpy(&cam, camera, sizeof(Camera));      // re-read every call, like src/pathtracer.cu:2706
-    if (c->vol && cam.medium >= c->sc.n_mediums) return fail(B200PT_EINVAL, "camera medium index out of range");
+    if (c->vol && (cam.medium >= c->sc.n_mediums || cam.medium < -1)) return fail(B200PT_EINVAL, "camera medium index out of range");
     c->last_filmic = cam.filmic;
     float* out_dev = (output && output_is_device) ? output : c->out;
     const size_t npix = (size_t)c->width * c->height;
@@ -815,13 +836,8 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     for (Lane& L : c->lanes) if (L.map.n_local_pixels > L.pool.n) graph_frame = false;
     if (graph_frame) {
         for (Lane& L : c->lanes) {
-            const size_t need = (size_t)L.map.n_local_pixels;
-            if (need > L.samples_cap) {
-                if (c->graph_exec) { CK(cudaDeviceSynchronize()); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-                if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
-                if (cudaMalloc((void**)&L.samples, std::max<size_t>(need, 1) * sizeof(float4)) != cudaSuccess) return fail(B200PT_ENOMEM, "cudaMalloc of the sample planes");
-                L.samples_cap = need;
-            }
+            int rc2 = ensure_samples(c, L, (size_t)L.map.n_local_pixels);
+            if (rc2) return rc2;
         }
         if (!c->graph_exec) {
             cudaGraph_t graph = nullptr;
@@ -915,11 +931,7 @@ extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t 
     std::vector<float4> hits(npix);
     const uint32_t P = (uint32_t)L.pool.n;
     int rc = 0;
-    if (L.samples_cap < npix) {
-        if (L.samples) { CK(cudaStreamSynchronize(L.stream)); cudaFree(L.samples); L.samples = nullptr; L.samples_cap = 0; }
-        if (cudaMalloc((void**)&L.samples, (size_t)npix * sizeof(float4)) != cudaSuccess) { L.map = saved_map; return fail(B200PT_ENOMEM, "cudaMalloc of the sample plane"); }
-        L.samples_cap = npix;
-    }
+    if ((rc = ensure_samples(c, L, npix))) { L.map = saved_map; return rc; }
     std::vector<float4> tmp(P), bs(P), fl(P);
     for (uint32_t base = 0; base < npix && !rc; base += P) {
         // hand out exactly the samples [base, base + P) of this iteration

@@ -37,6 +37,7 @@
 #endif
 
 int b200pt_internal_fail(int code, const char* msg);   // b200pt_api.cu: sets b200pt_last_error()
+extern "C" int b200pt_internal_prims_finite(const void* prims, int n, int* bad);   // host_prep.cpp
 
 namespace bvhb {
 
@@ -400,6 +401,9 @@ extern "C" int b200pt_bvh_build_gpu(const void* prims_in, int32_t n_prims, void*
                                     double* timing_ms4) {
     if (!prims_in || !prims_out || !nodes_out || !n_nodes || n_prims <= 0 || nodes_capacity <= 0)
         return b200pt_internal_fail(B200PT_EINVAL, "b200pt_bvh_build_gpu: null argument or empty input");
+    int bad = -1;
+    if (!b200pt_internal_prims_finite(prims_in, n_prims, &bad))
+        return b200pt_internal_fail(B200PT_EINVAL, ("b200pt_bvh_build_gpu: primitive " + std::to_string(bad) + " has a non-finite bounding box").c_str());
     std::vector<void*> allocs;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return b200pt_internal_fail(B200PT_ECUDA, "b200pt_bvh_build_gpu: no CUDA device");

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+int b200pt_internal_fail(int code, const char* msg);   // b200pt_api.cu: sets b200pt_last_error()
+extern "C" int b200pt_internal_prims_finite(const void* prims, int n, int* bad);
 namespace {
 
 // Host-side min/max as the reference's host build defines them (src/cutil_math.h:36-44): on ties (and NaN)
@@ -57,6 +59,18 @@ Box prim_box(const RefPrimitive& p) {
     return b;
 }
 
+// Bucket indices (src/bvh.cpp:74-76) are computed from primitive boxes without range checks — in the reference a NaN /
+// Inf vertex indexes outside its 12-entry arrays.  Behind a public C ABI the input is checked instead: every box, its
+// centre (lo + hi) and its extent (hi - lo) must be finite, which keeps every bucket index in [0, 12].
+bool prims_finite(const RefPrimitive* prims, int n, int* bad) {
+    for (int i = 0; i < n; ++i) {
+        const Box b = prim_box(prims[i]);
+        for (int a = 0; a < 3; ++a)
+            if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a]) || !std::isfinite(b.lo[a] + b.hi[a]) || !std::isfinite(b.hi[a] - b.lo[a])) { *bad = i; return false; }
+    }
+    return true;
+}
+
 struct Builder {
     const RefPrimitive* prims;
     std::vector<Box> boxes;          // per input primitive
@@ -93,6 +107,7 @@ struct Builder {
                     const int id = ids[j];
                     int no = (int)((centre[3 * id + axis] - v0) / (v1 - v0) * kBuckets);
                     no = (no == 12) ? no - 1 : no;
+                    no = no < 0 ? 0 : (no > kBuckets - 1 ? kBuckets - 1 : no);     // unreachable for finite boxes (checked on entry)
                     cnt[no]++; bb[no].grow(boxes[id]);
                 }
                 for (int j = 1; j < kBuckets; ++j) {
@@ -144,9 +159,15 @@ inline void v3normalize(float* v) { float inv = 1.0f / sqrtf(v3dot(v, v)); v[0] 
 
 }  // namespace
 
+extern "C" int b200pt_internal_prims_finite(const void* prims, int n, int* bad) { return prims_finite((const RefPrimitive*)prims, n, bad) ? 1 : 0; }
+
 extern "C" int b200pt_bvh_build(const void* prims_in, int32_t n_prims, void* prims_out, void* nodes_out,
                                 int32_t nodes_capacity, int32_t* n_nodes, float* root_box6) {
-    if (!prims_in || !prims_out || !nodes_out || !n_nodes || n_prims <= 0) return B200PT_EINVAL;
+    if (!prims_in || !prims_out || !nodes_out || !n_nodes || n_prims <= 0)
+        return b200pt_internal_fail(B200PT_EINVAL, "b200pt_bvh_build: null argument or empty input");
+    int bad = -1;
+    if (!prims_finite((const RefPrimitive*)prims_in, n_prims, &bad))
+        return b200pt_internal_fail(B200PT_EINVAL, ("b200pt_bvh_build: primitive " + std::to_string(bad) + " has a non-finite bounding box").c_str());
     Builder b;
     b.prims = (const RefPrimitive*)prims_in;
     b.nodes = (RefLinearBVHNode*)nodes_out;
@@ -162,7 +183,7 @@ extern "C" int b200pt_bvh_build(const void* prims_in, int32_t n_prims, void* pri
     }
     b.leaf_order.reserve(n_prims);
     b.build(ids, root);
-    if (b.overflow) return B200PT_ENOMEM;
+    if (b.overflow) return b200pt_internal_fail(B200PT_ENOMEM, "b200pt_bvh_build: nodes_capacity too small");
     RefPrimitive* out = (RefPrimitive*)prims_out;
     for (int i = 0; i < n_prims; ++i) std::memcpy(&out[i], &b.prims[b.leaf_order[i]], sizeof(RefPrimitive));
     *n_nodes = b.n_nodes;
@@ -250,7 +271,6 @@ extern "C" int b200pt_infinite_init(void* infinite72, const float* root_box6) {
 // Byte stream: int total_nodes | int n_prims | float[3] root min | float[3] root max | Primitive[n_prims] |
 // LinearBVHNode[total_nodes].  The reference reads it without any validation; here the header is checked against
 // the file size before anything is copied.
-int b200pt_internal_fail(int code, const char* msg);   // b200pt_api.cu: sets b200pt_last_error()
 namespace {
 int cache_fail(int code, const std::string& msg) { return b200pt_internal_fail(code, msg.c_str()); }
 struct CacheHeader { int32_t n_nodes; int32_t n_prims; float box[6]; };

@@ -11,6 +11,9 @@
 //      (iteration, pixel) pair from the global counter (ray generation, :881-903)
 #pragma once
 #include "wavefront.cuh"
+#ifdef B200PT_PROBE
+#include <cstdio>
+#endif
 
 namespace pt {
 
@@ -194,6 +197,17 @@ __device__ __forceinline__ void st_pool(float4* p, float4 v) {
 static inline void st_pool(float4* p, float4 v) { *p = v; }
 #endif
 
+// ---- parity probes (diagnostic build only, -DB200PT_PROBE -> libb200pt_probe.so; scripts/parity_diag.py) ---------------
+// printf of the per-bounce state of ONE (pixel, iteration) sample, in the format of the probe build of the reference
+// (oracle/build_ref_debug.sh), so the first diverging intermediate of a flipped sample can be read off a diff.
+#ifdef B200PT_PROBE
+__device__ int g_probe[2] = {-1, -1};            // global pixel index, iteration
+#define PT_P3(v) (double)(v).x, (double)(v).y, (double)(v).z
+#define PT_PROBE(...) do { if (probe_on) printf(__VA_ARGS__); } while (0)
+#else
+#define PT_PROBE(...) do { } while (0)
+#endif
+
 // Material specialisation: a scene whose materials are all lambertian gets a kernel without the GGX / dielectric
 // code (a quarter of the instructions and registers of the general one); MATS is the set of MaterialTypes present.
 constexpr uint32_t kMatsLambertOnly = 1u << MT_LAMBERTIAN;
@@ -276,6 +290,15 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     f3 Li = alive ? mk3(lt4.x, lt4.y, lt4.z) : mk3(0, 0, 0);
     uint32_t sample = alive ? __float_as_uint(bs.w) : 0u;
     uint32_t kdone = __float_as_uint(lt4.w);                        // static samples this slot has consumed
+#ifdef B200PT_PROBE
+    bool probe_on = false;
+    if (alive) {
+        const uint32_t npix_ = (uint32_t)a.map.n_local_pixels;
+        const uint32_t itl_ = sample / npix_; uint32_t px_, py_;
+        local_to_xy(a.map, sample - itl_ * npix_, px_, py_);
+        probe_on = (int)(px_ + py_ * (uint32_t)a.map.width) == g_probe[0] && (int)(a.batch.first_iter + itl_) == g_probe[1];
+    }
+#endif
     // a dead slot regenerates while samples are left for it (its static share, then the global counter — a snapshot
     // of it is exact enough, see below)
     bool finished = !alive && (kdone < a.batch.k_static || next_snapshot < a.batch.total);
@@ -358,6 +381,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
 #else
             Lacc += beta_old * Ld;                                                                // :994
 #endif
+            if (!carried) PT_PROBE("D Li %a %a %a Ld %a %a %a\n", PT_P3(Lacc), PT_P3(Ld));
         }
         if (carried) {
             st_pool(a.samples + __float_as_uint(po.w), make_float4(Lacc.x, Lacc.y, Lacc.z, 1.f));
@@ -380,6 +404,8 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
         } else {
             SurfaceHit h;
             reconstruct_hit(sc, o, d, h0.x, __float_as_int(h0.y), h0.z, h0.w, h);
+            PT_PROBE("H %d o %a %a %a d %a %a %a t %a pos %a %a %a nor %a %a %a uv %a %a dpdu %a %a %a beta %a %a %a Li %a %a %a prim %d %d\n", bounces,
+                     PT_P3(o), PT_P3(d), (double)h0.x, PT_P3(h.pos), PT_P3(h.nor), (double)h.uv.x, (double)h.uv.y, PT_P3(h.dpdu), PT_P3(beta), PT_P3(Li), h.matIdx, h.lightIdx);
             bool shade_surface = true;
             if (VOL) {
                 float sampledDist = 0.f; bool sampledMedium = false;
@@ -394,6 +420,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                     sampledDist = dist;
                     beta *= sampledMedium ? (Tr * sigmaS / pdf) : sigmaT * Tr / pdf;
                 }
+                PT_PROBE("V beta %a %a %a dist %a med %d\n", PT_P3(beta), (double)sampledDist, (int)sampledMedium);
                 if (is_black(beta)) { finished = true; shade_surface = false; }                 // :1070
                 else if (sampledMedium) {                                                       // :1071-1101
                     shade_surface = false;
@@ -407,6 +434,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                     LightSample ls;
                     if (idx != sc.n_lights) area_sample(sc.lights[idx], samplePos, ua, ub, sc.eps, ls);
                     else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+                    PT_PROBE("L lpdf %a cpdf %a sd %a %a %a tmax %a rad %a %a %a idx %d\n", (double)ls.pdf, (double)choicePdf, PT_P3(ls.dir), (double)ls.tmax, PT_P3(ls.radiance), idx);
                     float phase = kInvFourPi;                                                   // Medium::Phase, src/medium.h:222
                     if (M.g != 0) {
                         float costheta = dot(-d, ls.dir);
@@ -481,6 +509,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                         LightSample ls;
                         if (idx != sc.n_lights) area_sample(sc.lights[idx], h.pos, ua, ub, sc.eps, ls);
                         else inf_sample(sc.inf, ua, ub, sc.eps, ls);
+                        PT_PROBE("L lpdf %a cpdf %a sd %a %a %a tmax %a rad %a %a %a idx %d\n", (double)ls.pdf, (double)choicePdf, PT_P3(ls.dir), (double)ls.tmax, PT_P3(ls.radiance), idx);
                         nf |= F_PENDING;
                         pend_origin = h.pos;
                         st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
@@ -501,6 +530,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                         float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
                         f3 out, fr; float pdf;
                         sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
+                        PT_PROBE("M out %a %a %a fr %a %a %a pdf %a\n", PT_P3(out), PT_P3(fr), (double)pdf);
                         float denom = ls.pdf * choicePdf;
                         if (!(is_black(fr) || pdf == 0)) {
                             nf |= F_MIS;
@@ -516,6 +546,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                     float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :997-1003
                     f3 out, fr; float pdf;
                     sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(c0, c1, c2), out, fr, pdf);
+                    PT_PROBE("C out %a %a %a fr %a %a %a pdf %a\n", PT_P3(out), PT_P3(fr), (double)pdf);
                     if (is_black(fr)) {
                         nf |= F_TERMINATE;
                     } else {
@@ -557,6 +588,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     const bool carry_now = emitted_pending && (nf & F_TERMINATE) != 0u && have_more;
     const bool want_new = finished || carry_now;
     if (finished && alive) {
+        PT_PROBE("E Li %a %a %a\n", PT_P3(Li));
         st_pool(a.samples + sample, make_float4(Li.x, Li.y, Li.z, 1.f));
     }
     const bool take_static = want_new && kdone < a.batch.k_static;

@@ -339,26 +339,27 @@ def load_scene_json(path, prep=None, overrides=None):
 
 
 # ------------------------------------------------------------------------------------------------ configs
-def golden_dir():
-    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+def data_dir():
+    """Input scene files shipped with the package (the reference's Cornell-box JSON / OBJ / density grid)."""
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 def cornell_pt(width=256, height=256, max_depth=4, prep=None):
     """C1/C2: shipped Cornell materials/camera/light as `pt`, with short+tall boxes."""
-    return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "cornell_pt.json"), prep=prep,
+    return load_scene_json(os.path.join(data_dir(), "scenes", "cornell_box", "cornell_pt.json"), prep=prep,
                            overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
 
 
 def cornell_shipped_smoke(width=512, height=512, max_depth=17, prep=None):
     """scenes/cornell_box/scene.json as shipped — `vpt`, the 100 x 100 x 40 smoke grid `hhh` (ratio
     tracking) inside the invisible boundary mesh density_render.obj; what result/heterogeneous.png shows."""
-    return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "scene_smoke_vpt.json"), prep=prep,
+    return load_scene_json(os.path.join(data_dir(), "scenes", "cornell_box", "scene_smoke_vpt.json"), prep=prep,
                            overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
 
 
 def cornell_vol_caustic(width=512, height=512, max_depth=17, prep=None):
     """C5: vol_caustic.json as `vpt` with the regular Cornell emitter."""
-    return load_scene_json(os.path.join(golden_dir(), "scenes", "cornell_box", "vol_caustic_vpt.json"), prep=prep,
+    return load_scene_json(os.path.join(data_dir(), "scenes", "cornell_box", "vol_caustic_vpt.json"), prep=prep,
                            overrides={"screen_width": width, "screen_height": height, "maxDepth": max_depth})
 
 
@@ -549,3 +550,66 @@ def cornell_smoke(width=256, height=256, max_depth=8, eval_transmittance_type=1,
     cam = {"position": [0, 1.0, 6.8], "lookat": [0, 1.0, 0], "up": [0, 1, 0], "fov": 19.5, "medium": -1}
     return assemble("cornell_smoke", width, height, base.epsilon, "vpt", max_depth, cam, base.materials, med,
                     L.cat([base.prims, boundary], L.Primitive), base.lights, prep=prep, densities=[grid])
+
+
+def cornell_material_zoo(width=256, height=256, max_depth=8, integrator="pt", prep=None):
+    """Parity-coverage scene: the Cornell room with every BSDF branch of SampleBSDF / Fr
+    (src/pathtracer.cu:491-826) in view — mirror tall box (:506), isotropic rough-dielectric short box (:642, Fr :787),
+    substrate floor (:580), ANISOTROPIC rough-conductor back wall (SampleGGX's alphaU != alphaV branch, :117), a smooth
+    dielectric sphere — behind a THIN-LENS camera (apertureRadius > 1e-5, src/camera.h:62-76) with the gamma
+    tone map (`filmicTonemap: false`, src/pathtracer.cu:187).  `integrator="vpt"`: the room is filled with a thin
+    forward-scattering fog (Henyey-Greenstein g = 0.6, src/medium.h:197-246), the rough-dielectric box holds a medium
+    with |g| < 1e-3 (SamplePhase's near-isotropic branch, :203) and the sphere a back-scattering one (g = -0.4)."""
+    vpt = integrator == "vpt"
+    base = cornell_pt(width, height, max_depth, prep=prep)
+    mats = np.concatenate([base.materials,
+                           make_material("mirror", specular=(0.95, 0.95, 0.95)),
+                           make_material("roughdielectric", specular=(1, 1, 1), alphaU=0.15, alphaV=0.15, insideIOR=1.5, outsideIOR=1.0),
+                           make_material("substrate", diffuse=(0.5, 0.3, 0.2), specular=(0.05, 0.05, 0.05), alphaU=0.1, alphaV=0.1),
+                           make_material("roughconduct", specular=(1, 1, 1), alphaU=0.05, alphaV=0.3,
+                                         eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421)),
+                           make_material("dielectric", specular=(1, 1, 1), insideIOR=1.5, outsideIOR=1.0)])
+    n0 = len(base.materials)
+    MIRROR, RDIEL, SUBSTR, RCOND, GLASS = n0, n0 + 1, n0 + 2, n0 + 3, n0 + 4
+    prims = base.prims.copy()
+    t = prims["triangle"]
+    v = np.stack([t["v1"]["v"], t["v2"]["v"], t["v3"]["v"]], 1)
+    is_tri = prims["type"] == L.GT_TRIANGLE
+    floor = is_tri & (np.abs(v[..., 1]).max(1) < 1e-6)
+    back = is_tri & (np.abs(v[..., 2] + 1.0).max(1) < 1e-6)
+    not_light = t["lightIdx"] == -1
+    ymax = v[..., 1].max(1)
+    xz_inside = (np.abs(v[..., 0]).max(1) < 0.99) & (np.abs(v[..., 2]).max(1) < 0.99)
+    tall = is_tri & not_light & xz_inside & (ymax > 0.9) & (ymax < 1.5) & ~back
+    short = is_tri & not_light & xz_inside & (ymax <= 0.9) & ~floor
+    assert tall.sum() == 10 and short.sum() == 10, (int(tall.sum()), int(short.sum()))
+    t["matIdx"] = np.where(floor, SUBSTR, np.where(back, RCOND, np.where(tall, MIRROR, np.where(short, RDIEL, t["matIdx"]))))
+    FOG, TINT, BACKSC = 0, 1, 2
+    if vpt:
+        # every surface sits in the fog; transmission through the rough-dielectric box / the sphere switches medium
+        t["mediumOutside"] = FOG
+        t["mediumInside"] = np.where(short, TINT, FOG)
+    prims["triangle"] = t
+    sphere = sphere_prim((-0.45, 1.45, 0.35), 0.28, GLASS, BACKSC if vpt else -1, FOG if vpt else -1)
+    lights = base.lights.copy()
+    if vpt:
+        # Area.triangle is a copy of the emitter triangle (src/parsescene.cpp:531-541)
+        lt = lights["triangle"]; lt["mediumOutside"] = FOG; lt["mediumInside"] = FOG; lights["triangle"] = lt
+        mediums = L.cat([make_homogeneous_medium((0.005, 0.005, 0.005), (0.08, 0.08, 0.08), g=0.6),
+                         make_homogeneous_medium((0.3, 0.1, 0.05), (0.6, 0.6, 0.6), g=0.0005),
+                         make_homogeneous_medium((0.05, 0.2, 0.4), (0.8, 0.8, 0.8), g=-0.4)], L.Medium)
+    else:
+        mediums = base.mediums
+    cam = {"position": [0.15, 1.05, 6.8], "lookat": [0, 1.0, 0], "up": [0, 1, 0], "fov": 19.5,
+           "apertureRadius": 0.06, "focalDistance": 6.6, "filmicTonemap": False, "medium": FOG if vpt else -1}
+    return assemble("cornell_material_zoo_" + integrator, width, height, base.epsilon, integrator, max_depth, cam, mats, mediums,
+                    L.cat([prims, sphere], L.Primitive), lights, prep=prep)
+
+
+def cornell_environment_camera(width=256, height=128, max_depth=6, prep=None):
+    """Parity-coverage scene: the C1 Cornell box through the lat-long `environment` camera (src/camera.h:50-58), placed
+    inside the room."""
+    base = cornell_pt(width, height, max_depth, prep=prep)
+    cam = {"position": [0.1, 1.0, 0.2], "lookat": [0, 1.0, -1.0], "up": [0, 1, 0], "fov": 19.5, "environment": True}
+    return assemble("cornell_environment", width, height, base.epsilon, "pt", max_depth, cam, base.materials, base.mediums,
+                    base.prims, base.lights, prep=prep)

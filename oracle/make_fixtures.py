@@ -9,7 +9,7 @@
     run through oracle/_ref/libref_host.so, for every config scene (cornell, vol_caustic, veach stand-in,
     20k random triangles).
  3. golden function-level vectors and small golden images rendered by the reference's own kernel bodies
-    (host build).  GPU goldens (reference CUDA build on a B200) are added by oracle/make_gpu_goldens.py.
+    (host build).  On the GPU the reference's CUDA build itself (oracle/_ref/libref_cuda.so) is run live by the tests.
 """
 import json
 import os
@@ -26,7 +26,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def stage_scene_files():
     src = os.path.join(REF, "scenes", "cornell_box")
-    dst = os.path.join(GOLD, "scenes", "cornell_box")
+    dst = os.path.join(ROOT, "gpu-pathtracer_b200", "data", "scenes", "cornell_box")     # package data: input scene files
     os.makedirs(os.path.join(dst, "geometry"), exist_ok=True)
     for f in ["floor", "ceil", "back", "left", "right", "short", "tall", "light",
               "mesh_0", "mesh_1", "mesh_2", "mesh_3", "mesh_4", "mesh_5", "mesh_6"]:
@@ -82,6 +82,11 @@ def main():
         "cornell_smoke_delta_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 0, prep=prep),
         "cornell_smoke_residual_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 2, prep=prep),
         "shipped_smoke_64": lambda: pt.scenes.cornell_shipped_smoke(64, 64, 17, prep=prep),      # the reference's own scene.json
+        # parity coverage of the remaining branches: mirror / rough dielectric / substrate / anisotropic GGX, thin lens, gamma
+        # tone map, Henyey-Greenstein media (g = 0.6, |g| < 1e-3, g = -0.4), lat-long camera
+        "material_zoo_pt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 8, "pt", prep=prep),
+        "material_zoo_vpt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 12, "vpt", prep=prep),
+        "environment_camera_128x64": lambda: pt.scenes.cornell_environment_camera(128, 64, 6, prep=prep),
     }
     only = [a for a in sys.argv[1:] if not a.startswith("-")]          # optional: regenerate just these fixtures
     for name, mk in scenes.items():

@@ -61,3 +61,9 @@ extern "C" int refcuda_end() {
     delete g_scene; g_scene = nullptr;
     return 0;
 }
+
+#ifdef REFDBG
+// probe build only (oracle/build_ref_debug.sh): choose the pixel whose per-bounce state the kernels print
+extern "C" void refdbg_set(int pixel);
+extern "C" int refcuda_debug_pixel(int pixel) { refdbg_set(pixel); fflush(stdout); return 0; }
+#endif

@@ -25,6 +25,12 @@ SCENES = {
     "smoke_delta": (lambda: pt.scenes.cornell_smoke(256, 256, 8, 0), 32),
     "smoke_residual": (lambda: pt.scenes.cornell_smoke(256, 256, 8, 2), 32),
     "smoke_shipped": (lambda: pt.scenes.cornell_shipped_smoke(256, 256, 17), 16),    # the reference's own scene.json + grid
+    # branch coverage: mirror, rough dielectric (SampleBSDF + Fr), substrate, anisotropic GGX, smooth
+    # dielectric sphere, THIN-LENS camera, GAMMA tone map; under vpt additionally Henyey-Greenstein media with
+    # g = 0.6 / 5e-4 / -0.4 (Phase + SamplePhase, all three branches); and the lat-long environment camera
+    "material_zoo_pt": (lambda: pt.scenes.cornell_material_zoo(256, 256, 8, "pt"), 32),
+    "material_zoo_vpt": (lambda: pt.scenes.cornell_material_zoo(256, 256, 12, "vpt"), 32),
+    "environment_camera": (lambda: pt.scenes.cornell_environment_camera(256, 128, 6), 32),
 }
 
 
@@ -89,11 +95,15 @@ def test_matches_reference_cuda_integrator(name):
     acc, tone = _render(s, 1, spp)
     assert ref_acc.mean() / spp > 1e-3
     _check_parity(name, acc, ref_acc, spp)
-    assert np.median(np.abs(tone - ref_tone)) <= 1e-6                   # tonemapped output of the last iteration
+    # tonemapped output of the last iteration: the bulk of the pixels to the last bits, 99 % within 1e-4 (a pixel holding
+    # one of the rare flipped samples is off by that sample's radiance / spp)
+    dt = np.abs(tone.astype(np.float64) - ref_tone.astype(np.float64))
+    assert np.median(dt) <= 1e-6 and np.percentile(dt, 99.0) <= 1e-4, (np.median(dt), np.percentile(dt, 99.0))
 
 
 @pytest.mark.parametrize("name", ["cornell_c1", "veach_c3", "vol_caustic_c5", "random_tris_c4", "textured_hair", "smoke_ratio",
-                                  "smoke_delta", "smoke_residual", "smoke_shipped"])
+                                  "smoke_delta", "smoke_residual", "smoke_shipped", "material_zoo_pt", "material_zoo_vpt",
+                                  "environment_camera"])
 def test_matches_cpu_oracle(name, oracle):
     mk, _ = SCENES[name]
     s = mk()
@@ -257,3 +267,46 @@ def test_captured_frame_graph_equals_plain_launches():
     for x, y in zip(res[0][:4], res[1][:4]):
         assert np.array_equal(_bits(x), _bits(y))
     assert res[0][4] == res[1][4] > 0
+
+
+def test_sample_plane_reallocation_invalidates_the_captured_frame():
+    """the captured frame bakes the sample-plane pointer into its kernel arguments.  render(spp=1),
+    render(spp=8) (re-allocates larger planes), render(spp=1) must not replay the stale graph; trace_primary between
+    two 1-spp frames re-allocates as well.  Bits must equal the graph-less path."""
+    s = pt.scenes.cornell_pt(256, 256, 6)
+    res = []
+    for use_graph in (1, 0):
+        with pt.PathTracer(s) as r:
+            r.set_option("graph", use_graph)
+            out = [r.render(1, reset=True, spp=1), r.render(2, reset=False, spp=8), r.render(10, reset=False, spp=1)]
+            out.append(r.accum())
+            hits = r.trace_primary(iter=3)
+            out.append(r.render(11, reset=False, spp=1))
+            out.append(r.accum())
+            out.append(hits)
+            res.append(out)
+    for x, y in zip(*res):
+        assert np.array_equal(_bits(x), _bits(y))
+    ref_acc = None
+    with pt.PathTracer(s) as r:
+        r.set_option("graph", 0)
+        r.render(1, reset=True, spp=11)
+        ref_acc = r.accum()
+    assert np.array_equal(_bits(res[0][5]), _bits(ref_acc))
+
+
+@pytest.mark.skipif(not refhost.have("libref_cuda.so"), reason="oracle/_ref/libref_cuda.so not present")
+def test_full_config_c4_one_million_triangles_matches_reference_cuda():
+    """BASELINE configs[3] at its stated geometry and image size: 1 M random triangles + HDRI, 2048 x 2048, depth 8,
+    64 iterations (a quarter of the stated 256 spp: the reference's integrator needs ~50 s for them on a B200)."""
+    s = pt.scenes.random_triangles(1_000_000, 2048, 2048, 8)
+    spp = 64
+    ref = refhost.RefCuda()
+    ref.begin(s)
+    try:
+        ref.render(1, spp, want_output=False)
+        ref_acc = ref.accum()
+    finally:
+        ref.end()
+    acc, _ = _render(s, 1, spp)
+    _check_parity("C4 1M triangles 2048x2048x64spp", acc, ref_acc, spp)

@@ -21,6 +21,10 @@ SCENES = {
     "cornell_smoke_delta_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 0),
     "cornell_smoke_residual_64": lambda: pt.scenes.cornell_smoke(64, 64, 8, 2),
     "shipped_smoke_64": lambda: pt.scenes.cornell_shipped_smoke(64, 64, 17),           # the reference's own scene.json + density grid
+    # mirror / rough dielectric / substrate / anisotropic GGX + thin lens + gamma; HG media under vpt; lat-long camera
+    "material_zoo_pt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 8, "pt"),
+    "material_zoo_vpt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 12, "vpt"),
+    "environment_camera_128x64": lambda: pt.scenes.cornell_environment_camera(128, 64, 6),
 }
 
 
@@ -84,7 +88,8 @@ def test_kat_rng_camera_intersect_bsdf_lights_tonemap(oracle, golden_dir):
 @pytest.mark.parametrize("name,spp,first", [("cornell_pt_64", 3, 5), ("vol_caustic_64", 2, 9), ("veach_standin_64x48", 2, 1000),
                                              ("cornell_textured_hair_64", 2, 77), ("cornell_smoke_ratio_64", 3, 31),
                                              ("cornell_smoke_delta_64", 2, 8), ("cornell_smoke_residual_64", 2, 400),
-                                             ("shipped_smoke_64", 2, 6)])
+                                             ("shipped_smoke_64", 2, 6), ("material_zoo_pt_64", 3, 12), ("material_zoo_vpt_64", 3, 200),
+                                             ("environment_camera_128x64", 2, 3)])
 def test_oracle_bit_exact_vs_live_reference(name, spp, first, oracle):
     s = SCENES[name]()
     ref_acc, ref_tone = refhost.RefHost().render(s, first, spp)

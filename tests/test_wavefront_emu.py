@@ -32,6 +32,9 @@ SCENES = {
     "textured_hair": lambda: pt.scenes.cornell_textured_hair(64, 64, 6),            # textures + lines
     "smoke_ratio": lambda: pt.scenes.cornell_smoke(64, 64, 8, 1),                   # heterogeneous media
     "shipped_smoke": lambda: pt.scenes.cornell_shipped_smoke(64, 64, 17),           # the reference's own scene.json
+    "material_zoo_pt": lambda: pt.scenes.cornell_material_zoo(64, 64, 8, "pt"),     # all six BSDFs, thin lens, gamma tone map
+    "material_zoo_vpt": lambda: pt.scenes.cornell_material_zoo(64, 64, 12, "vpt"),  # + Henyey-Greenstein media, g = 0.6 / 5e-4 / -0.4
+    "environment_camera": lambda: pt.scenes.cornell_environment_camera(128, 64, 6),  # lat-long camera
 }
 
 
