@@ -488,13 +488,31 @@ static int ensure_samples(b200pt_ctx* c, Lane& L, size_t need) {
     return 0;
 }
 
-static void fill_map(ShardMap& m, uint32_t width, uint32_t height, int shard, int n_shards, int tile_w, int tile_h) {
+// `owner_of(k)` decides which tiles this map holds: rank-level shards use shard_owner(k, n); the lanes of a context
+// split the rank's tiles once more among themselves (j-th tile of the rank -> lane j % n_lanes).
+static int fill_map(b200pt_ctx* c, ShardMap& m, uint32_t width, uint32_t height, int shard, int n_shards, int tile_w, int tile_h,
+                    int lane = 0, int n_lanes = 1) {
     m.width = (int)width; m.height = (int)height;
-    m.shard = shard; m.n_shards = n_shards; m.tile_w = tile_w; m.tile_h = tile_h;
+    m.shard = shard * n_lanes + lane; m.n_shards = n_shards * n_lanes; m.tile_w = tile_w; m.tile_h = tile_h;
     m.tiles_x = (int)width / tile_w; m.tiles_y = (int)height / tile_h;
+    m.tiles = nullptr;
     const int n_tiles = m.tiles_x * m.tiles_y;
-    m.n_local_tiles = n_shards == 1 ? n_tiles : (shard < n_tiles ? (n_tiles - shard + n_shards - 1) / n_shards : 0);
-    m.n_local_pixels = n_shards == 1 ? (int)(width * height) : m.n_local_tiles * tile_w * tile_h;
+    if (m.n_shards == 1) { m.n_local_tiles = n_tiles; m.n_local_pixels = (int)(width * height); return 0; }
+    if (m.tiles_x > 0xffff || m.tiles_y > 0xffff) return fail(B200PT_EINVAL, "too many tiles");
+    std::vector<uint32_t> mine;
+    int j = 0;
+    for (int k = 0; k < n_tiles; ++k) {
+        if (shard_owner(k, n_shards) != shard) continue;
+        if (j++ % n_lanes == lane) mine.push_back((uint32_t)(k % m.tiles_x) | ((uint32_t)(k / m.tiles_x) << 16));
+    }
+    m.n_local_tiles = (int)mine.size();
+    m.n_local_pixels = m.n_local_tiles * tile_w * tile_h;
+    uint32_t* d = nullptr;
+    int rc = dev_upload(c, &d, mine.data(), mine.size());
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    m.tiles = d;
+    return 0;
 }
 
 extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uint32_t height, float epsilon,
@@ -519,7 +537,6 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
             return bail(fail(B200PT_EINVAL, "bad shard description (tiles must divide the image)"));
         sh = shard->shard; nsh = shard->n_shards; tw = shard->tile_w; th = shard->tile_h;
     }
-    fill_map(c->map, width, height, sh, nsh, tw, th);
 
     // lane 0's stream carries the scene upload
     c->lanes.resize(1);
@@ -532,6 +549,7 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     c->sc.eps = epsilon;
     int rc = build_scene(c, scene);
     if (rc) return bail(rc);
+    if ((rc = fill_map(c, c->map, width, height, sh, nsh, tw, th))) return bail(rc);
 
     // lanes: local tile j of this context goes to lane j % n_lanes, i.e. lane k is shard (sh + nsh * k) of nsh * n_lanes.
     // Measured (profiles/r01q_lanes.txt): 3 lanes are best when the flat small-scene kernel traces (C2 +5 %), 2 otherwise.
@@ -548,7 +566,7 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
         cudaEventCreateWithFlags(&L.ev_poll[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&L.ev_poll[1], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming);
         if (n_lanes == 1) L.map = c->map;
-        else fill_map(L.map, width, height, sh + nsh * k, nsh * n_lanes, tw, th);
+        else if ((rc = fill_map(c, L.map, width, height, sh, nsh, tw, th, k, n_lanes))) return bail(rc);
     }
 
     size_t npix = (size_t)width * height;
@@ -690,7 +708,7 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
-    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0;
+    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0; sa.cta_retired = nullptr; sa.cta_busy = nullptr;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
     ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
 }

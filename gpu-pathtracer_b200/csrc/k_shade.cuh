@@ -29,7 +29,14 @@ struct ShadeArgs {
     BatchParams batch;
     const FrameParams* frame;  // non-null inside a captured frame: camera and first_iter come from here
     int32_t drain_hint;        // the host saw the sample counter exhausted: dead tiles may leave early
+    // CTA-local wavefront (k_wave.cuh): the pool planes and the ray queue above point into SHARED memory and these two
+    // per-CTA words replace the global retired-sample counter / tell the CTA that some slot still has work
+    uint32_t* cta_retired;
+    uint32_t* cta_busy;
 };
+
+// One slot's record as the shade stage reads it (13 planes, 14 for vpt).
+struct SlotRec { float4 df, orng, bs, lt4, h0, bo, pv, pl, pmd, pmf, h1, po, cy, pax; };
 
 struct SurfaceHit { f3 pos, nor, dpdu; f2 uv; int matIdx, lightIdx, mediumInside, mediumOutside; };
 
@@ -71,8 +78,8 @@ __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, 
     h.pos = o + t * d;
 #endif
     if (s.type == 0) {
-                h.nor = normalize(lin3(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
-        h.uv = mk2(s.uv1[0], s.uv1[1]) * (1.f - b1 - b2) + mk2(s.uv2[0], s.uv2[1]) * b1 + mk2(s.uv3[0], s.uv3[1]) * b2;
+        h.nor = normalize(lin3_seq(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
+        h.uv = lin3_seq2(1.f - b1 - b2, mk2(s.uv1[0], s.uv1[1]), b1, mk2(s.uv2[0], s.uv2[1]), b2, mk2(s.uv3[0], s.uv3[1]));
         h.dpdu = normalize(cross(h.nor, ld3(s.ndpdv)));
     } else if (s.type == 2) {                                            // hair segment, src/line.h:74-83
         h.nor = -d;
@@ -95,7 +102,7 @@ __device__ __forceinline__ void reconstruct_hit(const SceneDev& sc, f3 o, f3 d, 
 // shading normal only (MIS hit, :962)
 __device__ __forceinline__ f3 hit_normal(const SceneDev& sc, f3 pos, int prim, float b1, float b2) {
     const WShade& s = sc.shade[prim];
-    if (s.type == 0) return normalize(lin3(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
+    if (s.type == 0) return normalize(lin3_seq(1.f - b1 - b2, ld3(s.n1), b1, ld3(s.n2), b2, ld3(s.n3)));
     return normalize(pos - ld3(s.n1));     // sphere (hair segments never carry a light, so their normal is not needed here)
 }
 
@@ -208,6 +215,11 @@ __device__ int g_probe[2] = {-1, -1};            // global pixel index, iteratio
 #define PT_PROBE(...) do { } while (0)
 #endif
 
+// FUSED (k_wave.cuh): the record lives in shared memory, reached through a generic pointer.
+template <bool FUSED> __device__ __forceinline__ void st_rec(float4* p, float4 v) {
+    if (FUSED) *p = v; else st_pool(p, v);
+}
+
 // Material specialisation: a scene whose materials are all lambertian gets a kernel without the GGX / dielectric
 // code (a quarter of the instructions and registers of the general one); MATS is the set of MaterialTypes present.
 constexpr uint32_t kMatsLambertOnly = 1u << MT_LAMBERTIAN;
@@ -231,55 +243,25 @@ __device__ __forceinline__ void eval_bsdf_m(const Material& m, f3 albedo, f3 in,
     fr = mk3(0, 0, 0); pdf = 0.f;
 }
 
-// Resident CTAs per SM: the kernel is latency bound (long scoreboard), so occupancy beats registers — 8 CTAs (64
-// registers; the lambertian kernel does not even spill) is +3 % on C2 and +6.5 % on C3 over the unconstrained 70 / 96
-// registers; the volumetric instantiations carry one more staged plane and more live state: 6 CTAs (80 registers) is
-// +3.4 % on C5 where 8 is -9 %; the all-materials kernel spills 144 B at 64 registers (-2 % on the textured-hair
-// scene), so it stays at 6 as well (same-box A/B, profiles/r01z_perf_all_configs.txt).
-template <bool VOL, uint32_t MATS>
-__global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shade(const ShadeArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;      // the pool size is a multiple of the block size
+// plain loads of one slot's record (emulation build; CTA-local wavefront, where the planes are in shared memory)
+template <bool VOL> __device__ __forceinline__ void load_slot(const Pool& p, uint32_t slot, SlotRec& r) {
+    r.df = p.d_flags[slot]; r.orng = p.o_rng[slot]; r.bs = p.beta_s[slot]; r.lt4 = p.li_t[slot];
+    r.h0 = p.hit0[slot]; r.bo = p.beta_old[slot]; r.pv = p.vis[slot]; r.pl = p.ldl[slot];
+    r.pmd = p.misd[slot]; r.pmf = p.misf[slot]; r.h1 = p.hit1[slot];
+    r.po = p.pend_o[slot]; r.cy = p.carry[slot];
+    r.pax = VOL ? p.aux[slot] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// The shade stage of ONE slot (sections A-C above).  `slot` indexes the pool planes / queue entries, `gslot` is the
+// slot's number among all `pool_n` slots of the wavefront (static sample hand-out); FUSED: called from the CTA-local
+// wavefront kernel (k_wave.cuh) with the planes in shared memory.
+template <bool VOL, uint32_t MATS, bool FUSED>
+__device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t slot, const uint32_t gslot, const uint32_t pool_n,
+                                           const SlotRec& r, const unsigned long long next_snapshot) {
     const SceneDev& sc = a.sc;
     const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
-
-    // ---------------------------------------------------------------- loads: the CTA's 128 pool records, all arrays,
-    // staged into shared memory by TMA bulk copies (one elected thread issues them, everyone waits on the mbarrier)
-    constexpr int kArrays = VOL ? 14 : 13;
-#ifndef B200PT_EMULATE
-    // drain phase (no sample left to hand out): a tile whose slots are all dead has nothing to do — find that out
-    // with one 16-byte load per thread instead of staging 13 planes
-    // (drain_hint comes from the host's last poll of the sample counter, so steps before the drain phase pay nothing)
-    if (a.drain_hint) {
-        const uint32_t f = __float_as_uint(a.pool.d_flags[slot].w);
-        const uint32_t k = __float_as_uint(a.pool.li_t[slot].w);
-        if (!__syncthreads_or((f & F_ALIVE) != 0u || k < a.batch.k_static)) return;
-    }
-    __shared__ __align__(128) float4 s_rec[kArrays][128];
-    __shared__ uint64_t bar;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const float4* src[14] = {a.pool.d_flags, a.pool.o_rng, a.pool.beta_s, a.pool.li_t, a.pool.hit0, a.pool.beta_old,
-                                 a.pool.vis, a.pool.ldl, a.pool.misd, a.pool.misf, a.pool.hit1, a.pool.pend_o, a.pool.carry, a.pool.aux};
-        mbar_expect_tx(&bar, (uint32_t)(kArrays * 128 * sizeof(float4)));
-#pragma unroll
-        for (int k = 0; k < kArrays; ++k) tma_bulk_g2s(&s_rec[k][0], src[k] + (size_t)blockIdx.x * 128, 128 * sizeof(float4), &bar);
-    }
-    __syncthreads();                       // the barrier object is initialised before anyone polls it
-    mbar_wait(&bar, 0);
-    const float4 df = s_rec[0][threadIdx.x], orng = s_rec[1][threadIdx.x], bs = s_rec[2][threadIdx.x], lt4 = s_rec[3][threadIdx.x];
-    const float4 h0 = s_rec[4][threadIdx.x], bo = s_rec[5][threadIdx.x], pv = s_rec[6][threadIdx.x], pl = s_rec[7][threadIdx.x];
-    const float4 pmd = s_rec[8][threadIdx.x], pmf = s_rec[9][threadIdx.x], h1 = s_rec[10][threadIdx.x];
-    const float4 po = s_rec[11][threadIdx.x], cy = s_rec[12][threadIdx.x];
-    const float4 pax = VOL ? s_rec[kArrays - 1][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-    const float4 df = a.pool.d_flags[slot], orng = a.pool.o_rng[slot], bs = a.pool.beta_s[slot], lt4 = a.pool.li_t[slot];
-    const float4 h0 = a.pool.hit0[slot], bo = a.pool.beta_old[slot], pv = a.pool.vis[slot], pl = a.pool.ldl[slot];
-    const float4 pmd = a.pool.misd[slot], pmf = a.pool.misf[slot], h1 = a.pool.hit1[slot];
-    const float4 po = a.pool.pend_o[slot], cy = a.pool.carry[slot];
-    const float4 pax = VOL ? a.pool.aux[slot] : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
-    const unsigned long long next_snapshot = a.counters->next_sample;
+    const float4 df = r.df, orng = r.orng, bs = r.bs, lt4 = r.lt4, h0 = r.h0, bo = r.bo, pv = r.pv, pl = r.pl;
+    const float4 pmd = r.pmd, pmf = r.pmf, h1 = r.h1, po = r.po, cy = r.cy, pax = r.pax;
 
     uint32_t flags = __float_as_uint(df.w);
     uint32_t rng = __float_as_uint(orng.w);
@@ -384,7 +366,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
             if (!carried) PT_PROBE("D Li %a %a %a Ld %a %a %a\n", PT_P3(Lacc), PT_P3(Ld));
         }
         if (carried) {
-            st_pool(a.samples + __float_as_uint(po.w), make_float4(Lacc.x, Lacc.y, Lacc.z, 1.f));
+            st_rec<FUSED>(a.samples + __float_as_uint(po.w), make_float4(Lacc.x, Lacc.y, Lacc.z, 1.f));
             retire_carry = true;
         } else {
             Li = Lacc;
@@ -443,12 +425,12 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                     }
                     nf |= F_PENDING | F_MEDSCATTER;
                     pend_origin = samplePos;
-                    st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, 0.f));
+                    st_rec<FUSED>(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, 0.f));
                     if (!is_black(ls.radiance)) {                                               // Tr() is side-effect free otherwise
                         nf |= F_SHADOW;
-                        st_pool(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
-                        st_pool(a.pool.ldl + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f));
-                        st_pool(a.pool.misf + slot, make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f));
+                        st_rec<FUSED>(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
+                        st_rec<FUSED>(a.pool.ldl + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f));
+                        st_rec<FUSED>(a.pool.misf + slot, make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f));
                     }
                     float pa = rng_next(rng), pb = rng_next(rng);                               // Medium::SamplePhase, src/medium.h:197
                     f3 dir;
@@ -512,7 +494,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                         PT_PROBE("L lpdf %a cpdf %a sd %a %a %a tmax %a rad %a %a %a idx %d\n", (double)ls.pdf, (double)choicePdf, PT_P3(ls.dir), (double)ls.tmax, PT_P3(ls.radiance), idx);
                         nf |= F_PENDING;
                         pend_origin = h.pos;
-                        st_pool(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
+                        st_rec<FUSED>(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
                         float mis_absdot = 0.f;
                         f3 ldl = mk3(0, 0, 0);
                         if (!is_black(ls.radiance)) {
@@ -520,11 +502,11 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                             eval_bsdf_m<MATS>(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
                             float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
                             nf |= F_SHADOW;
-                            st_pool(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
+                            st_rec<FUSED>(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
                             if (!VOL) ldl = weight * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
                             else {
                                 ldl = fr;
-                                st_pool(a.pool.aux + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight));
+                                st_rec<FUSED>(a.pool.aux + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight));
                             }
                         }
                         float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
@@ -535,12 +517,12 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
                         if (!(is_black(fr) || pdf == 0)) {
                             nf |= F_MIS;
                             mis_absdot = fabsf(dot(out, h.nor));
-                            st_pool(a.pool.misd + slot, make_float4(out.x, out.y, out.z, pdf));
-                            st_pool(a.pool.misf + slot, make_float4(fr.x, fr.y, fr.z, denom));
+                            st_rec<FUSED>(a.pool.misd + slot, make_float4(out.x, out.y, out.z, pdf));
+                            st_rec<FUSED>(a.pool.misf + slot, make_float4(fr.x, fr.y, fr.z, denom));
                         } else if (VOL) {
-                            st_pool(a.pool.misf + slot, make_float4(0.f, 0.f, 0.f, denom));
+                            st_rec<FUSED>(a.pool.misf + slot, make_float4(0.f, 0.f, 0.f, denom));
                         }
-                        st_pool(a.pool.ldl + slot, make_float4(ldl.x, ldl.y, ldl.z, mis_absdot));
+                        st_rec<FUSED>(a.pool.ldl + slot, make_float4(ldl.x, ldl.y, ldl.z, mis_absdot));
                         nf |= ((uint32_t)(medium + 1) << kMedium2Shift);
                     }
                     float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :997-1003
@@ -589,7 +571,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     const bool want_new = finished || carry_now;
     if (finished && alive) {
         PT_PROBE("E Li %a %a %a\n", PT_P3(Li));
-        st_pool(a.samples + sample, make_float4(Li.x, Li.y, Li.z, 1.f));
+        st_rec<FUSED>(a.samples + sample, make_float4(Li.x, Li.y, Li.z, 1.f));
     }
     const bool take_static = want_new && kdone < a.batch.k_static;
     const uint32_t m_fin = __ballot_sync(kFullMask, want_new && !take_static);      // lanes that need the global counter
@@ -606,7 +588,10 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     if (lane == 0u) {
         if (m_fin) sbase = atomicAdd(&a.counters->next_sample, (unsigned long long)__popc(m_fin));
         if (nc + ns + nm) qbase = atomicAdd(&a.q.ctl->tail[a.parity & 1u], nc + ns + nm);
-        if (m_ret | m_ret2) atomicAdd(&a.counters->done_samples, (unsigned long long)(__popc(m_ret) + __popc(m_ret2)));
+        if (m_ret | m_ret2) {
+            if (FUSED) atomicAdd(a.cta_retired, (uint32_t)(__popc(m_ret) + __popc(m_ret2)));
+            else atomicAdd(&a.counters->done_samples, (unsigned long long)(__popc(m_ret) + __popc(m_ret2)));
+        }
     }
     sbase = __shfl_sync(kFullMask, sbase, 0);
     qbase = __shfl_sync(kFullMask, qbase, 0);
@@ -614,25 +599,26 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     if (rays & F_SHADOW) a.q.entries[qbase + nc + (uint32_t)__popc(ms & lt)] = slot | (1u << kKindShift);
     if (rays & F_MIS) a.q.entries[qbase + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
     if (idle_dead) return;
+    if (FUSED) *a.cta_busy = 1u;                 // (benign race: every writer stores the same value)
 
     uint32_t carried_sample = 0u;
     if (want_new) {
         unsigned long long s;
-        if (take_static) { s = (unsigned long long)slot + (unsigned long long)kdone * (unsigned long long)a.pool.n; ++kdone; }
+        if (take_static) { s = (unsigned long long)gslot + (unsigned long long)kdone * (unsigned long long)pool_n; ++kdone; }
         else s = sbase + (unsigned long long)__popc(m_fin & lt);
         if (s >= a.batch.total) {
             // the batch ran out between the snapshot and the atomic (at most one step per batch); the reserved queue
             // entry stays and traces one harmless ray
             if (finished) {                                   // the slot dies
-                st_pool(a.pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
-                st_pool(a.pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
+                st_rec<FUSED>(a.pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
+                st_rec<FUSED>(a.pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
                 return;
             }
             // carry_now: fall back to the idle step — the state computed by section B (TERMINATE | PENDING) is kept
         } else {
             uint32_t pending_bits = 0u;
             if (carry_now) {
-                st_pool(a.pool.carry + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
+                st_rec<FUSED>(a.pool.carry + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
                 carried_sample = sample;
                 pending_bits = F_CARRY | (nf & (F_PENDING | F_SHADOW | F_MIS | F_MEDSCATTER)) | (nf & (0xffu << kMedium2Shift));
             }
@@ -657,13 +643,60 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
         }
     }
     if (emitted_pending)
-        st_pool(a.pool.pend_o + slot, make_float4(pend_origin.x, pend_origin.y, pend_origin.z, __uint_as_float(carried_sample)));
+        st_rec<FUSED>(a.pool.pend_o + slot, make_float4(pend_origin.x, pend_origin.y, pend_origin.z, __uint_as_float(carried_sample)));
     if (specular) nf |= F_SPECULAR;
     nf |= ((uint32_t)bounces & 0x7fu) << kBounceShift;
-    st_pool(a.pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
-    st_pool(a.pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
-    st_pool(a.pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));
-    st_pool(a.pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, __uint_as_float(kdone)));
+    st_rec<FUSED>(a.pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
+    st_rec<FUSED>(a.pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
+    st_rec<FUSED>(a.pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));
+    st_rec<FUSED>(a.pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, __uint_as_float(kdone)));
+}
+
+// Resident CTAs per SM: the kernel is latency bound (long scoreboard), so occupancy beats registers — 8 CTAs (64
+// registers; the lambertian kernel does not even spill) is +3 % on C2 and +6.5 % on C3 over the unconstrained 70 / 96
+// registers; the volumetric instantiations carry one more staged plane and more live state: 6 CTAs (80 registers) is
+// +3.4 % on C5 where 8 is -9 %; the all-materials kernel spills 144 B at 64 registers (-2 % on the textured-hair
+// scene), so it stays at 6 as well (same-box A/B, profiles/r01z_perf_all_configs.txt).
+template <bool VOL, uint32_t MATS>
+__global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shade(const ShadeArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;      // the pool size is a multiple of the block size
+
+    // ---------------------------------------------------------------- loads: the CTA's 128 pool records, all arrays,
+    // staged into shared memory by TMA bulk copies (one elected thread issues them, everyone waits on the mbarrier)
+    constexpr int kArrays = VOL ? 14 : 13;
+#ifndef B200PT_EMULATE
+    // drain phase (no sample left to hand out): a tile whose slots are all dead has nothing to do — find that out
+    // with one 16-byte load per thread instead of staging 13 planes
+    // (drain_hint comes from the host's last poll of the sample counter, so steps before the drain phase pay nothing)
+    if (a.drain_hint) {
+        const uint32_t f = __float_as_uint(a.pool.d_flags[slot].w);
+        const uint32_t k = __float_as_uint(a.pool.li_t[slot].w);
+        if (!__syncthreads_or((f & F_ALIVE) != 0u || k < a.batch.k_static)) return;
+    }
+    __shared__ __align__(128) float4 s_rec[kArrays][128];
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const float4* src[14] = {a.pool.d_flags, a.pool.o_rng, a.pool.beta_s, a.pool.li_t, a.pool.hit0, a.pool.beta_old,
+                                 a.pool.vis, a.pool.ldl, a.pool.misd, a.pool.misf, a.pool.hit1, a.pool.pend_o, a.pool.carry, a.pool.aux};
+        mbar_expect_tx(&bar, (uint32_t)(kArrays * 128 * sizeof(float4)));
+#pragma unroll
+        for (int k = 0; k < kArrays; ++k) tma_bulk_g2s(&s_rec[k][0], src[k] + (size_t)blockIdx.x * 128, 128 * sizeof(float4), &bar);
+    }
+    __syncthreads();                       // the barrier object is initialised before anyone polls it
+    mbar_wait(&bar, 0);
+    SlotRec r;
+    r.df = s_rec[0][threadIdx.x]; r.orng = s_rec[1][threadIdx.x]; r.bs = s_rec[2][threadIdx.x]; r.lt4 = s_rec[3][threadIdx.x];
+    r.h0 = s_rec[4][threadIdx.x]; r.bo = s_rec[5][threadIdx.x]; r.pv = s_rec[6][threadIdx.x]; r.pl = s_rec[7][threadIdx.x];
+    r.pmd = s_rec[8][threadIdx.x]; r.pmf = s_rec[9][threadIdx.x]; r.h1 = s_rec[10][threadIdx.x];
+    r.po = s_rec[11][threadIdx.x]; r.cy = s_rec[12][threadIdx.x];
+    r.pax = VOL ? s_rec[kArrays - 1][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+    SlotRec r;
+    load_slot<VOL>(a.pool, slot, r);
+#endif
+    shade_slot<VOL, MATS, false>(a, slot, slot, (uint32_t)a.pool.n, r, a.counters->next_sample);
 }
 
 // ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------

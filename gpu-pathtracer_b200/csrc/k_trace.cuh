@@ -91,8 +91,9 @@ __device__ __forceinline__ int prim_test(const float4 q0, const float4 q1, const
         float radius = q0.w;
         float B = dot_pinned(op, d);
 #if defined(__CUDA_ARCH__)
-        // B*B - (dot(op,op) - r*r) as the reference build contracts it: fma(B, B, r*r - dot(op,op))
-        float delta = __fmaf_rn(B, B, __fsub_rn(__fmul_rn(radius, radius), dot_pinned(op, op)));
+        // B*B - (dot(op,op) - r*r) as the reference build contracts it at all seven Sphere::Intersect sites of Path and
+        // Volpath (SASS: FFMA c, r, r, -dot ; FFMA delta, B, B, c): fma(B, B, fma(r, r, -dot(op,op))) — BOTH products fused
+        float delta = __fmaf_rn(B, B, __fmaf_rn(radius, radius, -dot_pinned(op, op)));
 #else
         float C = dot(op, op) - radius * radius;
         float delta = B * B - C;
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                             if (invisible) {
                                 const WShade& s = a.sc.shade[hprim];
                                 f3 nor;
-                                if (s.type == 0) nor = normalize(lin3(1.f - hb1 - hb2, ld3(s.n1), hb1, ld3(s.n2), hb2, ld3(s.n3)));
+                                if (s.type == 0) nor = normalize(lin3_seq(1.f - hb1 - hb2, ld3(s.n1), hb1, ld3(s.n2), hb2, ld3(s.n3)));
                                 else nor = normalize((o + seg * d) - ld3(s.n1));
                                 medium = dot(d, nor) > 0 ? s.mediumOutside : s.mediumInside;
                                 remain -= seg;
@@ -383,6 +384,111 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
 
 #undef STK_PUSH
 #undef STK_POP
+
+// One ray of the flat small-scene traversal (see k_trace_small below): fetch the ray of queue entry `entry` from the
+// pool planes, test all group boxes, run the flat primitive loop, write the hit / visibility back.  `prims` / `leaves`
+// point at the staged (shared-memory) copies; the pool planes are global (k_trace_small) or shared (k_wave.cuh).
+template <bool VOL>
+__device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const WPrim* __restrict__ prims, const float4* __restrict__ leaves,
+                                                const uint32_t entry, uint32_t& nrays) {
+    const float eps = a.sc.eps;
+    const int n_leaves = a.n_leaves;
+    const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
+    const float4 orng = kind == 0u ? a.pool.o_rng[slot] : a.pool.pend_o[slot];             // shadow / MIS rays keep their own origin
+    f3 o = mk3(orng.x, orng.y, orng.z);
+    float4 dv;
+    if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
+    else if (kind == 1u) dv = a.pool.shd[slot];
+    else { dv = a.pool.misd[slot]; dv.w = INFINITY; }
+    const f3 d = mk3(dv.x, dv.y, dv.z);
+    float tmax = dv.w;
+    const bool anyhit = !VOL && kind == 1u;
+    f3 tr = mk3(1, 1, 1);
+    float remain = tmax;
+    int medium = -1;
+    if (VOL && kind == 1u) medium = (int)((__float_as_uint(a.pool.d_flags[slot].w) >> kMedium2Shift) & 0xffu) - 1;
+    const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    int hprim; float hb1 = 0.f, hb2 = 0.f;
+    for (;;) {                                   // one pass per ray; vpt shadow rays repeat it per segment (Tr())
+        ++nrays;
+        hprim = -1;
+        // ---- all group boxes, warp-uniform; remember the group the ray enters first
+        unsigned long long mask = 0ull;
+        float tn, best_t = INFINITY;
+        int best = -1;
+        if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
+            for (int l = 0; l < n_leaves; ++l) {
+                const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
+                if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
+                    mask |= 1ull << l;
+                    if (tn < best_t) { best_t = tn; best = l; }
+                }
+            }
+        }
+        // ---- flat primitive loop over the hit groups: nearest group first, then the others in index order; once
+        // a closest hit is known, a group is re-tested against the shrunken interval before its primitives are
+        // (the `tmin > ray.tmax` rejection of BBox::Intersect, src/bbox.h:93)
+        uint32_t w0 = 0u, w1 = 0u;        // remaining primitive indices of the current group, 16 bits each
+        int left = 0;
+        for (;;) {
+            if (left == 0) {
+                int l;
+                if (best >= 0) { l = best; mask &= ~(1ull << best); best = -1; }
+                else {
+                    if (mask == 0ull) break;
+                    l = __ffsll((long long)mask) - 1;
+                    mask &= mask - 1ull;
+                    if (hprim >= 0) {
+                        const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
+                        if (!slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) continue;
+                    }
+                }
+                const float4 q1 = leaves[2 * l + 1];
+                w0 = __float_as_uint(q1.z); w1 = __float_as_uint(q1.w);
+                left = (w0 >> 16) == 0xffffu ? 1 : ((w1 & 0xffffu) == 0xffffu ? 2 : ((w1 >> 16) == 0xffffu ? 3 : 4));
+            }
+            const int pi = (int)(w0 & 0xffffu);
+            w0 = (w0 >> 16) | (w1 << 16); w1 >>= 16;
+            --left;
+            const float4* pp = reinterpret_cast<const float4*>(prims + pi);
+            const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+            float t, b1, b2;
+            const int acc = prim_test(p0, p1, p2, o, d, eps, tmax, t, b1, b2);
+            if (acc) {
+                if (anyhit) { hprim = pi; break; }
+                if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
+                tmax = t;
+            }
+        }
+        if (!(VOL && kind == 1u)) break;
+        // Tr() (src/pathtracer.cu:298-322), same walk as in k_trace
+        const bool invisible = hprim >= 0;
+        const float seg = invisible ? tmax : remain;
+        if (invisible && a.sc.shade[hprim].matIdx != -1) { tr = mk3(0, 0, 0); break; }
+        if (medium >= 0) {
+            const f3 c = ld3(a.sc.mediums[medium].sigmaT) * (-seg);
+            tr *= mk3(expf(c.x), expf(c.y), expf(c.z));
+        }
+        if (!invisible) break;
+        const WShade& sh = a.sc.shade[hprim];
+        f3 nor;
+        if (sh.type == 0) nor = normalize(lin3_seq(1.f - hb1 - hb2, ld3(sh.n1), hb1, ld3(sh.n2), hb2, ld3(sh.n3)));
+        else nor = normalize((o + seg * d) - ld3(sh.n1));
+        medium = dot(d, nor) > 0 ? sh.mediumOutside : sh.mediumInside;
+        remain -= seg;
+        o = o + seg * d;
+        tmax = remain;
+    }
+    if (kind != 1u) {
+        const float4 h = make_float4(hprim >= 0 ? tmax : -1.f, __int_as_float(hprim), hb1, hb2);
+        if (kind == 0u) a.pool.hit0[slot] = h; else a.pool.hit1[slot] = h;
+    } else if (!VOL) {
+        const float v = hprim >= 0 ? 0.f : 1.f;
+        a.pool.vis[slot] = make_float4(v, v, v, 0.f);
+    } else {
+        a.pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
+    }
+}
 
 // ---- small scenes (<= 256 primitives): flat list of tight primitive groups instead of a tree walk ----------
 // A Cornell-box-sized scene has a few dozen primitives.  Walking its tree costs more in divergence (every lane is
@@ -423,107 +529,10 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
     const uint32_t par = a.parity & 1u;
     const uint32_t tail = a.q.ctl->tail[par];
     if (blockIdx.x == 0 && threadIdx.x == 0) { a.q.ctl->tail[par ^ 1u] = 0u; a.q.ctl->head[par ^ 1u] = 0u; }
-    const float eps = a.sc.eps;
-    const int n_leaves = a.n_leaves;
     uint32_t nrays = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tail; idx += stride) {
-        const uint32_t entry = a.q.entries[idx];
-        const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
-        const float4 orng = kind == 0u ? a.pool.o_rng[slot] : a.pool.pend_o[slot];             // shadow / MIS rays keep their own origin
-        f3 o = mk3(orng.x, orng.y, orng.z);
-        float4 dv;
-        if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
-        else if (kind == 1u) dv = a.pool.shd[slot];
-        else { dv = a.pool.misd[slot]; dv.w = INFINITY; }
-        const f3 d = mk3(dv.x, dv.y, dv.z);
-        float tmax = dv.w;
-        const bool anyhit = !VOL && kind == 1u;
-        f3 tr = mk3(1, 1, 1);
-        float remain = tmax;
-        int medium = -1;
-        if (VOL && kind == 1u) medium = (int)((__float_as_uint(a.pool.d_flags[slot].w) >> kMedium2Shift) & 0xffu) - 1;
-        const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-        int hprim; float hb1 = 0.f, hb2 = 0.f;
-        for (;;) {                                   // one pass per ray; vpt shadow rays repeat it per segment (Tr())
-            ++nrays;
-            hprim = -1;
-            // ---- all group boxes, warp-uniform; remember the group the ray enters first
-            unsigned long long mask = 0ull;
-            float tn, best_t = INFINITY;
-            int best = -1;
-            if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
-                for (int l = 0; l < n_leaves; ++l) {
-                    const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
-                    if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
-                        mask |= 1ull << l;
-                        if (tn < best_t) { best_t = tn; best = l; }
-                    }
-                }
-            }
-            // ---- flat primitive loop over the hit groups: nearest group first, then the others in index order; once
-            // a closest hit is known, a group is re-tested against the shrunken interval before its primitives are
-            // (the `tmin > ray.tmax` rejection of BBox::Intersect, src/bbox.h:93)
-            uint32_t w0 = 0u, w1 = 0u;        // remaining primitive indices of the current group, 16 bits each
-            int left = 0;
-            for (;;) {
-                if (left == 0) {
-                    int l;
-                    if (best >= 0) { l = best; mask &= ~(1ull << best); best = -1; }
-                    else {
-                        if (mask == 0ull) break;
-                        l = __ffsll((long long)mask) - 1;
-                        mask &= mask - 1ull;
-                        if (hprim >= 0) {
-                            const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
-                            if (!slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) continue;
-                        }
-                    }
-                    const float4 q1 = leaves[2 * l + 1];
-                    w0 = __float_as_uint(q1.z); w1 = __float_as_uint(q1.w);
-                    left = (w0 >> 16) == 0xffffu ? 1 : ((w1 & 0xffffu) == 0xffffu ? 2 : ((w1 >> 16) == 0xffffu ? 3 : 4));
-                }
-                const int pi = (int)(w0 & 0xffffu);
-                w0 = (w0 >> 16) | (w1 << 16); w1 >>= 16;
-                --left;
-                const float4* pp = reinterpret_cast<const float4*>(prims + pi);
-                const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
-                float t, b1, b2;
-                const int acc = prim_test(p0, p1, p2, o, d, eps, tmax, t, b1, b2);
-                if (acc) {
-                    if (anyhit) { hprim = pi; break; }
-                    if (acc == 2 || t < tmax || pi > hprim) { hprim = pi; hb1 = b1; hb2 = b2; }
-                    tmax = t;
-                }
-            }
-            if (!(VOL && kind == 1u)) break;
-            // Tr() (src/pathtracer.cu:298-322), same walk as in k_trace
-            const bool invisible = hprim >= 0;
-            const float seg = invisible ? tmax : remain;
-            if (invisible && a.sc.shade[hprim].matIdx != -1) { tr = mk3(0, 0, 0); break; }
-            if (medium >= 0) {
-                const f3 c = ld3(a.sc.mediums[medium].sigmaT) * (-seg);
-                tr *= mk3(expf(c.x), expf(c.y), expf(c.z));
-            }
-            if (!invisible) break;
-            const WShade& sh = a.sc.shade[hprim];
-            f3 nor;
-            if (sh.type == 0) nor = normalize(lin3(1.f - hb1 - hb2, ld3(sh.n1), hb1, ld3(sh.n2), hb2, ld3(sh.n3)));
-            else nor = normalize((o + seg * d) - ld3(sh.n1));
-            medium = dot(d, nor) > 0 ? sh.mediumOutside : sh.mediumInside;
-            remain -= seg;
-            o = o + seg * d;
-            tmax = remain;
-        }
-        if (kind != 1u) {
-            const float4 h = make_float4(hprim >= 0 ? tmax : -1.f, __int_as_float(hprim), hb1, hb2);
-            if (kind == 0u) a.pool.hit0[slot] = h; else a.pool.hit1[slot] = h;
-        } else if (!VOL) {
-            const float v = hprim >= 0 ? 0.f : 1.f;
-            a.pool.vis[slot] = make_float4(v, v, v, 0.f);
-        } else {
-            a.pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
-        }
+        trace_small_ray<VOL>(a, prims, leaves, a.q.entries[idx], nrays);
     }
 #ifndef B200PT_EMULATE
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);

@@ -228,7 +228,7 @@ PT_SEQ_FN f3 seq_transmittance(const SceneDev& sc, f3 o, f3 d, float tmax, int m
         if (!invisible) break;
         const WShade& s = sc.shade[h.prim];
         f3 nor;
-        if (s.type == 0) nor = normalize(lin3(1.f - h.b1 - h.b2, ld3(s.n1), h.b1, ld3(s.n2), h.b2, ld3(s.n3)));
+        if (s.type == 0) nor = normalize(lin3_seq(1.f - h.b1 - h.b2, ld3(s.n1), h.b1, ld3(s.n2), h.b2, ld3(s.n3)));
         else nor = normalize((o + seg * d) - ld3(s.n1));
         medium = dot(d, nor) > 0 ? s.mediumOutside : s.mediumInside;
         remain -= seg;

@@ -84,6 +84,26 @@ PT_HD f3 lin3(float a, f3 U, float b, f3 V, float c, f3 W) {
     return a * U + b * V + c * W;
 #endif
 }
+// a*U + b*V + c*W contracted in SOURCE order — mul(a,U), then b*V fused on, then c*W fused on.  This is what the
+// reference's sm_100a build does for the barycentric interpolation of the shading normal and uv in
+// Triangle::Intersect's epilogue (src/mesh.h:87-88) at every site (Path closest-hit and MIS hit, Volpath closest-hit;
+// read off the SASS with scripts/sass_expr.py: `fma(n3, b2, fma(n2, b1, mul(n1, 1-b1-b2)))`), unlike
+// Triangle::SampleShape (src/mesh.h:102-103), where the SECOND product is the plain one (lin3 above).
+PT_HD f3 lin3_seq(float a, f3 U, float b, f3 V, float c, f3 W) {
+#if defined(__CUDA_ARCH__)
+    return mk3(__fmaf_rn(c, W.x, __fmaf_rn(b, V.x, __fmul_rn(a, U.x))), __fmaf_rn(c, W.y, __fmaf_rn(b, V.y, __fmul_rn(a, U.y))),
+               __fmaf_rn(c, W.z, __fmaf_rn(b, V.z, __fmul_rn(a, U.z))));
+#else
+    return a * U + b * V + c * W;
+#endif
+}
+PT_HD f2 lin3_seq2(float a, f2 U, float b, f2 V, float c, f2 W) {
+#if defined(__CUDA_ARCH__)
+    return mk2(__fmaf_rn(c, W.x, __fmaf_rn(b, V.x, __fmul_rn(a, U.x))), __fmaf_rn(c, W.y, __fmaf_rn(b, V.y, __fmul_rn(a, U.y))));
+#else
+    return U * a + V * b + W * c;
+#endif
+}
 // Hit/miss decisions must not depend on how the compiler happens to contract a*b+c in a given inlining context
 // (nvcc's choice of WHICH product of a dot/cross gets fused changes with the surrounding code).  These two spell
 // out the contraction the reference's own sm_100a build uses at every Triangle::Intersect site
@@ -258,12 +278,13 @@ PT_HD bool is_delta(int type) { return type == MT_MIRROR || type == MT_DIELECTRI
 
 PT_HD float dielectric_fresnel(float cosi, float cost, float etai, float etat) {                            // pathtracer.cu:51
 #if defined(__CUDA_ARCH__)
-    // feeds the reflect/refract decision `u > fresnel`: contraction pinned to the reference build's
-    // (products shared by numerator and denominator stay plain; Rparl^2 is fused onto mul(Rperp^2))
-    const float a = __fmul_rn(etat, cosi), b = __fmul_rn(etai, cost);
-    const float Rparl = __fdiv_rn(__fsub_rn(a, b), __fadd_rn(a, b));
-    const float c = __fmul_rn(etai, cosi), d = __fmul_rn(etat, cost);
-    const float Rperp = __fdiv_rn(__fsub_rn(c, d), __fadd_rn(c, d));
+    // feeds the reflect/refract decision `u > fresnel`: contraction pinned to the reference build's SASS (the same at
+    // every inlined copy in Path and Volpath, read with scripts/sass_expr.py): in numerator and denominator the FIRST
+    // product is fused onto the plainly rounded second one — ptxas does that on top of the PTX, which still shows
+    // separate mul / sub — and Rparl^2 is fused onto mul(Rperp^2)
+    const float b = __fmul_rn(etai, cost), d = __fmul_rn(etat, cost);
+    const float Rparl = __fdiv_rn(__fmaf_rn(etat, cosi, -b), __fmaf_rn(etat, cosi, b));
+    const float Rperp = __fdiv_rn(__fmaf_rn(etai, cosi, -d), __fmaf_rn(etai, cosi, d));
     return __fmul_rn(__fmaf_rn(Rparl, Rparl, __fmul_rn(Rperp, Rperp)), 0.5f);
 #else
     float Rparl = (etat * cosi - etai * cost) / (etat * cosi + etai * cost);
@@ -381,6 +402,37 @@ PT_HD void sample_bsdf(const Material& m, f3 albedo, f3 in, f3 nor, f3 dpdu, f3 
         f3 wi = -in;
         f3 normal = nor;
         float ei = m.outsideIOR, et = m.insideIOR;
+#if defined(__CUDA_ARCH__)
+        // Contraction of this branch as the reference's sm_100a build has it in the copy of SampleBSDF that feeds the path
+        // continuation (the only one a delta material reaches; identical in Path and Volpath — SASS read with
+        // scripts/sass_expr.py): dot(in, nor) = (in.x*n.x (+) in.y*n.y) + in.z*n.z with the z product rounded separately;
+        // Reflect = fma(n, 2*dot, -in); Refract = fma(fma(n, dot, -in), eta, n * (+-cost)) with 1 - sint2 contracted as
+        // fma(-(sini2*eta), eta, 1), normalised with x*x as the plain product; |dot(out, n)| of fr = fma(z, fma(y, mul(x))).
+        const float E = __fadd_rn(__fmaf_rn(in.x, nor.x, __fmul_rn(in.y, nor.y)), __fmul_rn(in.z, nor.z));
+        const float cosi = -E;
+        bool enter = cosi < 0;
+        if (!enter) { float t = ei; ei = et; et = t; }
+        float eta = __fdiv_rn(ei, et), cost;
+        float sint2 = __fmul_rn(__fmul_rn(eta, eta), __fmaf_rn(-cosi, cosi, 1.f));
+        cost = sqrtf(1.f - sint2 < 0.f ? 0.f : 1.f - sint2);
+        const float E2 = __fadd_rn(E, E);
+        f3 rdir = mk3(__fmaf_rn(nor.x, E2, wi.x), __fmaf_rn(nor.y, E2, wi.y), __fmaf_rn(nor.z, E2, wi.z));
+        f3 tdir;
+        {
+            const bool enter_r = E > 0;
+            const float etai = enter_r ? m.outsideIOR : m.insideIOR, etat = enter_r ? m.insideIOR : m.outsideIOR;
+            const float eta_r = __fdiv_rn(etai, etat);
+            const float sini2 = __fmaf_rn(-E, E, 1.f);
+            const float cost_r = sqrtf(__fmaf_rn(__fmul_rn(sini2, eta_r), -eta_r, 1.f));
+            const float sc = enter_r ? -cost_r : cost_r;
+            const f3 tv = mk3(__fmaf_rn(__fmaf_rn(nor.x, E, wi.x), eta_r, __fmul_rn(nor.x, sc)),
+                              __fmaf_rn(__fmaf_rn(nor.y, E, wi.y), eta_r, __fmul_rn(nor.y, sc)),
+                              __fmaf_rn(__fmaf_rn(nor.z, E, wi.z), eta_r, __fmul_rn(nor.z, sc)));
+            const float inv = rsqrtf(__fmaf_rn(tv.z, tv.z, __fmaf_rn(tv.y, tv.y, __fmul_rn(tv.x, tv.x))));
+            tdir = mk3(__fmul_rn(tv.x, inv), __fmul_rn(tv.y, inv), __fmul_rn(tv.z, inv));
+        }
+#define PT_DOT_XYZ(a, b) __fmaf_rn((a).z, (b).z, __fmaf_rn((a).y, (b).y, __fmul_rn((a).x, (b).x)))
+#else
         float cosi = dot(wi, normal);
         bool enter = cosi < 0;
         if (!enter) { float t = ei; ei = et; et = t; }
@@ -389,23 +441,26 @@ PT_HD void sample_bsdf(const Material& m, f3 albedo, f3 in, f3 nor, f3 dpdu, f3 
         cost = sqrtf(1.f - sint2 < 0.f ? 0.f : 1.f - sint2);
         f3 rdir = reflect(-wi, normal);
         f3 tdir = refract(in, nor, m.outsideIOR, m.insideIOR);
+#define PT_DOT_XYZ(a, b) dot(a, b)
+#endif
         if (sint2 > 1.f) {  // total reflection
             out = rdir;
-            fr = specular / fabsf(dot(out, normal));
+            fr = specular / fabsf(PT_DOT_XYZ(out, normal));
             pdf = 1.f;
             return;
         }
         float fresnel = dielectric_fresnel(fabsf(cost), fabsf(cosi), et, ei);
         if (u.x > fresnel) {  // refract
             out = tdir;
-            fr = specular / fabsf(dot(out, normal)) * (1.f - fresnel);
+            fr = specular / fabsf(PT_DOT_XYZ(out, normal)) * (1.f - fresnel);
             fr *= eta * eta;
             pdf = 1.f - fresnel;
         } else {              // reflect
             out = rdir;
-            fr = specular / fabsf(dot(out, normal)) * fresnel;
+            fr = specular / fabsf(PT_DOT_XYZ(out, normal)) * fresnel;
             pdf = fresnel;
         }
+#undef PT_DOT_XYZ
         break;
     }
     case MT_ROUGHCONDUCTOR: {

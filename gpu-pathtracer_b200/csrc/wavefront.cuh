@@ -173,21 +173,28 @@ struct Counters {
 };
 
 // Which pixels this context renders: interleaved screen tiles (multi-GPU sharding).
+// Which tiles a shard owns is decided once on the host (shard_owner) and handed to the kernels as a table of tile
+// origins, one 32-bit entry (tile x | tile y << 16) per local tile.
 struct ShardMap {
     int32_t width, height;
     int32_t tile_w, tile_h, tiles_x, tiles_y;
     int32_t shard, n_shards;
     int32_t n_local_tiles, n_local_pixels;
+    const uint32_t* tiles;          // [n_local_tiles] (device memory); unused when n_shards == 1
 };
+// Owner of tile k (row-major tile index).  Every group of n consecutive tiles holds one tile of each shard, and the
+// assignment inside a group rotates by 3 from group to group: a shard's tiles are spread over columns AND rows.
+// (Plain k % n gave each of 8 ranks four fixed COLUMNS of a 32-tile-wide image — shard 3 of the Cornell box needed
+// 9 % longer than shard 0, which was most of the 1 -> 8 GPU scaling loss of round 1, profiles/r02b_shard_tax.txt.)
+PT_HD int shard_owner(int k, int n) { return (k % n + (k / n) * 3) % n; }
 // local pixel index -> global pixel (x, y). Local order: tile-major, row-major inside the tile.
 __device__ __forceinline__ void local_to_xy(const ShardMap& m, uint32_t local, uint32_t& x, uint32_t& y) {
     if (m.n_shards == 1) { x = local % (uint32_t)m.width; y = local / (uint32_t)m.width; return; }
     uint32_t per_tile = (uint32_t)(m.tile_w * m.tile_h);
     uint32_t lt = local / per_tile, in = local - lt * per_tile;
-    uint32_t tile = lt * (uint32_t)m.n_shards + (uint32_t)m.shard;
-    uint32_t ty = tile / (uint32_t)m.tiles_x, tx = tile - ty * (uint32_t)m.tiles_x;
+    const uint32_t e = m.tiles[lt];
     uint32_t iy = in / (uint32_t)m.tile_w, ix = in - iy * (uint32_t)m.tile_w;
-    x = tx * (uint32_t)m.tile_w + ix; y = ty * (uint32_t)m.tile_h + iy;
+    x = (e & 0xffffu) * (uint32_t)m.tile_w + ix; y = (e >> 16) * (uint32_t)m.tile_h + iy;
 }
 
 // Per-call inputs of a captured (CUDA graph) frame: read through a pointer so that the graph's kernel arguments stay

@@ -554,12 +554,16 @@ def cornell_smoke(width=256, height=256, max_depth=8, eval_transmittance_type=1,
 
 def cornell_material_zoo(width=256, height=256, max_depth=8, integrator="pt", prep=None):
     """Parity-coverage scene: the Cornell room with every BSDF branch of SampleBSDF / Fr
-    (src/pathtracer.cu:491-826) in view — mirror tall box (:506), isotropic rough-dielectric short box (:642, Fr :787),
-    substrate floor (:580), ANISOTROPIC rough-conductor back wall (SampleGGX's alphaU != alphaV branch, :117), a smooth
-    dielectric sphere — behind a THIN-LENS camera (apertureRadius > 1e-5, src/camera.h:62-76) with the gamma
-    tone map (`filmicTonemap: false`, src/pathtracer.cu:187).  `integrator="vpt"`: the room is filled with a thin
-    forward-scattering fog (Henyey-Greenstein g = 0.6, src/medium.h:197-246), the rough-dielectric box holds a medium
-    with |g| < 1e-3 (SamplePhase's near-isotropic branch, :203) and the sphere a back-scattering one (g = -0.4)."""
+    (src/pathtracer.cu:491-826) in view — mirror tall box (:506), substrate short box (:580), ANISOTROPIC
+    rough-conductor back wall (SampleGGX's alphaU != alphaV branch, :117), a floating isotropic rough-dielectric box
+    (:642, Fr :787), a smooth dielectric sphere — behind a THIN-LENS camera (apertureRadius > 1e-5,
+    src/camera.h:62-76) with the gamma tone map (`filmicTonemap: false`, src/pathtracer.cu:187).
+    `integrator="vpt"`: the room is filled with a thin forward-scattering fog (Henyey-Greenstein g = 0.6,
+    src/medium.h:197-246), the rough-dielectric box holds a medium with |g| < 1e-3 (SamplePhase's near-isotropic branch,
+    :203) and the sphere a back-scattering one (g = -0.4).
+    (The transmissive box floats: the Cornell boxes' bottom faces are coplanar with the floor, and a ray travelling
+    INSIDE one of them would hit two surfaces at the same distance up to rounding — a tie that any two builds break
+    differently.)"""
     vpt = integrator == "vpt"
     base = cornell_pt(width, height, max_depth, prep=prep)
     mats = np.concatenate([base.materials,
@@ -583,13 +587,14 @@ def cornell_material_zoo(width=256, height=256, max_depth=8, integrator="pt", pr
     tall = is_tri & not_light & xz_inside & (ymax > 0.9) & (ymax < 1.5) & ~back
     short = is_tri & not_light & xz_inside & (ymax <= 0.9) & ~floor
     assert tall.sum() == 10 and short.sum() == 10, (int(tall.sum()), int(short.sum()))
-    t["matIdx"] = np.where(floor, SUBSTR, np.where(back, RCOND, np.where(tall, MIRROR, np.where(short, RDIEL, t["matIdx"]))))
+    t["matIdx"] = np.where(back, RCOND, np.where(tall, MIRROR, np.where(short, SUBSTR, t["matIdx"])))
     FOG, TINT, BACKSC = 0, 1, 2
     if vpt:
         # every surface sits in the fog; transmission through the rough-dielectric box / the sphere switches medium
         t["mediumOutside"] = FOG
-        t["mediumInside"] = np.where(short, TINT, FOG)
+        t["mediumInside"] = FOG
     prims["triangle"] = t
+    rbox = triangles_to_prims(*_box_tris((-0.92, 0.12, 0.28), (-0.48, 0.58, 0.78)), RDIEL, TINT if vpt else -1, FOG if vpt else -1)
     sphere = sphere_prim((-0.45, 1.45, 0.35), 0.28, GLASS, BACKSC if vpt else -1, FOG if vpt else -1)
     lights = base.lights.copy()
     if vpt:
@@ -603,7 +608,7 @@ def cornell_material_zoo(width=256, height=256, max_depth=8, integrator="pt", pr
     cam = {"position": [0.15, 1.05, 6.8], "lookat": [0, 1.0, 0], "up": [0, 1, 0], "fov": 19.5,
            "apertureRadius": 0.06, "focalDistance": 6.6, "filmicTonemap": False, "medium": FOG if vpt else -1}
     return assemble("cornell_material_zoo_" + integrator, width, height, base.epsilon, integrator, max_depth, cam, mats, mediums,
-                    L.cat([prims, sphere], L.Primitive), lights, prep=prep)
+                    L.cat([prims, rbox, sphere], L.Primitive), lights, prep=prep)
 
 
 def cornell_environment_camera(width=256, height=128, max_depth=6, prep=None):

@@ -65,8 +65,10 @@ typedef struct b200pt_scene_view {
     int32_t max_depth;               /* scene.integrator.maxDepth                                            */
 } b200pt_scene_view;
 
-/* Pixel-tile shard of the image this context renders (multi-GPU: rank r of n takes tiles k with k % n == r).
- * tile_w x tile_h screen tiles in row-major tile order; n_shards == 1 renders everything. */
+/* Pixel-tile shard of the image this context renders (multi-GPU: the tile_w x tile_h screen tiles are dealt out to the
+ * n_shards ranks so that every rank's tiles are spread over the whole image — every group of n consecutive tiles in
+ * row-major order holds one tile per rank, rotating from group to group; the shards of ranks 0..n-1 are disjoint and
+ * cover the image).  n_shards == 1 renders everything. */
 typedef struct b200pt_shard {
     int32_t shard, n_shards;
     int32_t tile_w, tile_h;
