@@ -5,7 +5,7 @@
 #include "ref_layouts.h"
 #include "k_shade.cuh"
 #include "k_trace.cuh"
-#include "k_volpath_seq.cuh"
+#include "k_wave.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -64,6 +64,8 @@ struct b200pt_ctx {
     uint32_t mats_used = 0;                // MaterialTypes referenced by primitives (picks the k_shade instantiation)
     float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
     bool small_scene = false;              // use k_trace_small
+    bool fused = false;                    // CTA-local wavefront (k_wave_small): one persistent launch per batch and lane
+    int wave_blocks = 0;
     uint32_t small_prim_bytes = 0;
     size_t max_batch_bytes = (size_t)2 << 30;
     int steps_per_poll = 8;
@@ -71,8 +73,7 @@ struct b200pt_ctx {
     double stats[5] = {0, 0, 0, 0, 0};
     double total_ms = 0;
     bool vol = false;
-    bool het = false;                      // `vpt` with a heterogeneous medium: k_volpath_seq renders (k_volpath_seq.cuh)
-    int seq_blocks = 0;
+    bool het = false;                      // `vpt` with a heterogeneous medium: the coroutine shade stage (k_het.cuh)
     int last_filmic = 1;
     // captured frame (CUDA graph) for the one-Render-per-frame usage: `pt`, spp == 1, every lane single-pass
     FrameParams* d_frame = nullptr;        // device copy read by the captured kernels
@@ -443,6 +444,25 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     return 0;
 }
 
+// k_wave_small instantiation for this context (volumetric or not, referenced material set, heterogeneous media)
+template <class F> static void with_wave_kernel(const b200pt_ctx* c, F&& f) {
+    const bool ldc = (c->mats_used & ~kMatsLDC) == 0u;
+    if (c->het) {
+        if (c->lambert_only) f(k_wave_small<true, kMatsLambertOnly, true>, true);
+        else f(k_wave_small<true, kMatsAll, true>, true);
+    } else if (c->vol) {
+        if (c->lambert_only) f(k_wave_small<true, kMatsLambertOnly, false>, true);
+        else if (ldc) f(k_wave_small<true, kMatsLDC, false>, true);
+        else f(k_wave_small<true, kMatsAll, false>, true);
+    } else {
+        if (c->lambert_only) f(k_wave_small<false, kMatsLambertOnly, false>, false);
+        else if (ldc) f(k_wave_small<false, kMatsLDC, false>, false);
+        else f(k_wave_small<false, kMatsAll, false>, false);
+    }
+}
+static size_t wave_smem(const b200pt_ctx* c) {
+    return c->vol ? wave_smem_bytes<true>(c->small_prim_bytes, c->n_leaves) : wave_smem_bytes<false>(c->small_prim_bytes, c->n_leaves);
+}
 static void free_pool(Lane& L) {
     for (void* p : L.pool_allocs) cudaFree(p);
     L.pool_allocs.clear();
@@ -553,10 +573,11 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
 
     // lanes: local tile j of this context goes to lane j % n_lanes, i.e. lane k is shard (sh + nsh * k) of nsh * n_lanes.
     // Measured (profiles/r01q_lanes.txt): 3 lanes are best when the flat small-scene kernel traces (C2 +5 %), 2 otherwise.
-    int n_lanes = c->small_scene ? 3 : 2;
-    // heterogeneous media: k_volpath_seq is one persistent launch that fills the GPU by itself — there is no trace / shade
-    // pair to overlap (measured: 98.7 ms with three lanes, 98.3 ms with one, 1024^2 x 8 spp), so one lane, two launches per batch
-    if (c->het) n_lanes = 1;
+    // scenes whose primitives fit in shared memory run the CTA-local wavefront (k_wave.cuh); B200PT_FUSED=0 keeps the
+    // global wavefront (k_shade + k_trace_small over the HBM pool) for A/B runs
+    c->fused = c->small_scene;
+    if (const char* env = getenv("B200PT_FUSED")) c->fused = c->fused && atoi(env) != 0;
+    int n_lanes = c->fused ? 1 : (c->small_scene ? 3 : 2);
     if (const char* env = getenv("B200PT_LANES")) n_lanes = std::max(1, std::min(8, atoi(env)));
     if (width % tw || height % th || c->map.n_local_tiles < n_lanes) n_lanes = 1;
     c->lanes.resize(n_lanes);
@@ -605,11 +626,21 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
 #endif
     if (per_sm <= 0) per_sm = 1;
     c->trace_blocks = c->num_sms * per_sm;
-    if (c->het) {
-        int seq_per_sm = 0;
-        if (c->lambert_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&seq_per_sm, k_volpath_seq<kMatsLambertOnly>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&seq_per_sm, k_volpath_seq<kMatsAll>, 128, 0);
-        c->seq_blocks = c->num_sms * std::max(seq_per_sm, 1);
+    if (c->fused) {
+        const size_t wsmem = wave_smem(c);
+        int wave_per_sm = 0;
+        cudaError_t we = cudaSuccess;
+        with_wave_kernel(c, [&](auto kernel, bool) {
+#ifndef B200PT_EMULATE
+            we = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+#endif
+            if (we == cudaSuccess) we = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wave_per_sm, kernel, kWaveThreads, wsmem);
+        });
+        if (we != cudaSuccess || wave_per_sm <= 0) { c->fused = false; cudaGetLastError(); }      // does not fit: global wavefront
+        else {
+            if (const char* env = getenv("B200PT_WAVE_CTAS")) wave_per_sm = std::max(1, std::min(wave_per_sm, atoi(env)));
+            c->wave_blocks = c->num_sms * wave_per_sm;
+        }
     }
 #ifdef B200PT_PROBE
     if (const char* env = getenv("B200PT_PROBE")) {           // "pixel,iter" (diagnostic build only)
@@ -631,6 +662,8 @@ extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_val
     else if (n == "groups") *out_value = c->small_scene ? c->n_leaves : 0;
     else if (n == "small_kernel") *out_value = c->small_scene ? 1 : 0;
     else if (n == "lambert_only") *out_value = c->lambert_only ? 1 : 0;
+    else if (n == "fused") *out_value = c->fused ? 1 : 0;
+    else if (n == "wave_blocks") *out_value = c->wave_blocks;
     else return fail(B200PT_EINVAL, "unknown info " + n);
     return 0;
 }
@@ -672,15 +705,21 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "max_batch_bytes") { if (value < (1 << 20)) return fail(B200PT_EINVAL, "max_batch_bytes too small"); c->max_batch_bytes = (size_t)value; return 0; }
     if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
-    if (n == "het_ctas_per_sm") { if (value < 1 || value > 16) return fail(B200PT_EINVAL, "het_ctas_per_sm out of range"); c->seq_blocks = c->num_sms * (int)value; return 0; }
-    if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr; return 0; }
-    if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; } return 0; }
+    if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr; if (!c->small_scene) c->fused = false; return 0; }
+    if (n == "fused") { c->fused = value != 0 && c->small_scene && c->wave_blocks > 0; return 0; }
+    if (n == "wave_ctas_per_sm") { if (value < 1 || value > 8) return fail(B200PT_EINVAL, "wave_ctas_per_sm out of range"); c->wave_blocks = c->num_sms * (int)value; return 0; }
+    if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; c->fused = false; } return 0; }
     return fail(B200PT_EINVAL, "unknown option " + n);
 }
 
 static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
     const int blocks = L.pool.n / 128;
     const bool ldc = (c->mats_used & ~kMatsLDC) == 0u;
+    if (c->het) {            // heterogeneous media: the coroutine stage (k_het.cuh)
+        if (c->lambert_only) PT_LAUNCH((k_het_shade<kMatsLambertOnly>), blocks, 128, 0, L.stream, sa);
+        else PT_LAUNCH((k_het_shade<kMatsAll>), blocks, 128, 0, L.stream, sa);
+        return;
+    }
     if (c->vol) {
         if (c->lambert_only) PT_LAUNCH((k_shade<true, kMatsLambertOnly>), blocks, 128, 0, L.stream, sa);
         else if (ldc) PT_LAUNCH((k_shade<true, kMatsLDC>), blocks, 128, 0, L.stream, sa);
@@ -691,9 +730,9 @@ static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
         else PT_LAUNCH((k_shade<false, kMatsAll>), blocks, 128, 0, L.stream, sa);
     }
 }
-static void launch_seq(b200pt_ctx* c, const Lane& L, const SeqArgs& qa) {
-    if (c->lambert_only) PT_LAUNCH((k_volpath_seq<kMatsLambertOnly>), c->seq_blocks, 128, 0, L.stream, qa);
-    else PT_LAUNCH((k_volpath_seq<kMatsAll>), c->seq_blocks, 128, 0, L.stream, qa);
+static void launch_wave(b200pt_ctx* c, const Lane& L, const WaveArgs& wa) {
+    const size_t smem = wave_smem(c);
+    with_wave_kernel(c, [&](auto kernel, bool) { PT_LAUNCH_CTA(kernel, c->wave_blocks, kWaveThreads, smem, L.stream, wa); });
 }
 static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
     if (c->small_scene) {
@@ -708,9 +747,9 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
-    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0; sa.cta_retired = nullptr; sa.cta_busy = nullptr;
+    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
-    ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves;
+    ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves; ta.sec_tmax = c->het ? 1 : 0;
 }
 
 // One batch = n_iters iterations of every local pixel through the wavefronts of all lanes, then the ordered resolve.
@@ -732,15 +771,19 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
             if (rc) return rc;
         }
         BatchParams bp; bp.first_iter = first_iter; bp.n_iters = n_iters; bp.total = need;
-        if (c->het) {
-            // heterogeneous media: every sample of the batch runs start to finish in one launch of the sequential kernel
-            bp.k_static = 0;
-            L.h_init[0] = 0ull; L.h_init[1] = 0ull;
+        if (c->fused) {
+            // CTA-local wavefront: the whole batch of this lane is ONE persistent launch (slots, queue and scene in shared
+            // memory); ~3/4 of the samples are handed out statically per slot, the rest from the global counter
+            const unsigned long long P = (unsigned long long)c->wave_blocks * kWaveThreads;
+            bp.k_static = (uint32_t)((need - need / 4) / P);
+            L.h_init[0] = (unsigned long long)bp.k_static * P; L.h_init[1] = 0ull;
             CK(cudaMemcpyAsync(L.counters, L.h_init, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, L.stream));
-            SeqArgs qa; qa.sc = c->sc; qa.samples = L.samples; qa.counters = L.counters; qa.cam = cam; qa.map = L.map; qa.batch = bp;
-            launch_seq(c, L, qa);
-            L.sa.batch = bp;
+            fill_args(c, L, cam, bp);
+            L.sa.frame = capture ? c->d_frame : nullptr;
+            WaveArgs wa; wa.sa = L.sa; wa.ta = L.ta;
+            launch_wave(c, L, wa);
             *launches += 1; *steps += 1;
+            if (capture) CK(cudaMemcpyAsync(&L.h_counters[0], L.counters, sizeof(Counters), cudaMemcpyDeviceToHost, L.stream));
             L.done = true;
             continue;
         }
@@ -851,7 +894,7 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     // one Render per frame (`pt`, 1 spp, every lane single-pass): the whole frame — uploads, shade / trace steps of all
     // lanes, resolves — is ONE captured CUDA graph, replayed with the per-call inputs refreshed through c->d_frame
     bool graph_frame = c->use_graph && !c->vol && spp == 1;
-    for (Lane& L : c->lanes) if (L.map.n_local_pixels > L.pool.n) graph_frame = false;
+    if (!c->fused) for (Lane& L : c->lanes) if (L.map.n_local_pixels > L.pool.n) graph_frame = false;
     if (graph_frame) {
         for (Lane& L : c->lanes) {
             int rc2 = ensure_samples(c, L, (size_t)L.map.n_local_pixels);

@@ -7,4 +7,6 @@
 #else
 #include <cuda_runtime.h>
 #define PT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// kernels whose body plays a whole CTA per call under emulation (phases separated by block barriers: k_wave.cuh)
+#define PT_LAUNCH_CTA(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif

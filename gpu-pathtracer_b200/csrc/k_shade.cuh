@@ -29,10 +29,6 @@ struct ShadeArgs {
     BatchParams batch;
     const FrameParams* frame;  // non-null inside a captured frame: camera and first_iter come from here
     int32_t drain_hint;        // the host saw the sample counter exhausted: dead tiles may leave early
-    // CTA-local wavefront (k_wave.cuh): the pool planes and the ray queue above point into SHARED memory and these two
-    // per-CTA words replace the global retired-sample counter / tell the CTA that some slot still has work
-    uint32_t* cta_retired;
-    uint32_t* cta_busy;
 };
 
 // One slot's record as the shade stage reads it (13 planes, 14 for vpt).
@@ -256,8 +252,9 @@ template <bool VOL> __device__ __forceinline__ void load_slot(const Pool& p, uin
 // slot's number among all `pool_n` slots of the wavefront (static sample hand-out); FUSED: called from the CTA-local
 // wavefront kernel (k_wave.cuh) with the planes in shared memory.
 template <bool VOL, uint32_t MATS, bool FUSED>
-__device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t slot, const uint32_t gslot, const uint32_t pool_n,
-                                           const SlotRec& r, const unsigned long long next_snapshot) {
+__device__ __forceinline__ void shade_slot(const ShadeArgs& a, const Pool& pool, const RayQueue& q, const uint32_t parity,
+                                           uint32_t* cta_retired, uint32_t* cta_busy, const uint32_t slot, const uint32_t gslot,
+                                           const uint32_t pool_n, const SlotRec& r, const unsigned long long next_snapshot) {
     const SceneDev& sc = a.sc;
     const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
     const float4 df = r.df, orng = r.orng, bs = r.bs, lt4 = r.lt4, h0 = r.h0, bo = r.bo, pv = r.pv, pl = r.pl;
@@ -425,12 +422,12 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
                     }
                     nf |= F_PENDING | F_MEDSCATTER;
                     pend_origin = samplePos;
-                    st_rec<FUSED>(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, 0.f));
+                    st_rec<FUSED>(pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, 0.f));
                     if (!is_black(ls.radiance)) {                                               // Tr() is side-effect free otherwise
                         nf |= F_SHADOW;
-                        st_rec<FUSED>(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
-                        st_rec<FUSED>(a.pool.ldl + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f));
-                        st_rec<FUSED>(a.pool.misf + slot, make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f));
+                        st_rec<FUSED>(pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
+                        st_rec<FUSED>(pool.ldl + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, 0.f));
+                        st_rec<FUSED>(pool.misf + slot, make_float4(phase, ls.pdf * choicePdf, 0.f, 0.f));
                     }
                     float pa = rng_next(rng), pb = rng_next(rng);                               // Medium::SamplePhase, src/medium.h:197
                     f3 dir;
@@ -494,7 +491,7 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
                         PT_PROBE("L lpdf %a cpdf %a sd %a %a %a tmax %a rad %a %a %a idx %d\n", (double)ls.pdf, (double)choicePdf, PT_P3(ls.dir), (double)ls.tmax, PT_P3(ls.radiance), idx);
                         nf |= F_PENDING;
                         pend_origin = h.pos;
-                        st_rec<FUSED>(a.pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
+                        st_rec<FUSED>(pool.beta_old + slot, make_float4(beta.x, beta.y, beta.z, fabsf(dot(h.nor, ls.dir))));
                         float mis_absdot = 0.f;
                         f3 ldl = mk3(0, 0, 0);
                         if (!is_black(ls.radiance)) {
@@ -502,11 +499,11 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
                             eval_bsdf_m<MATS>(mat, albedo, wo, ls.dir, h.nor, h.dpdu, fr, samplePdf);
                             float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
                             nf |= F_SHADOW;
-                            st_rec<FUSED>(a.pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
+                            st_rec<FUSED>(pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
                             if (!VOL) ldl = weight * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
                             else {
                                 ldl = fr;
-                                st_rec<FUSED>(a.pool.aux + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight));
+                                st_rec<FUSED>(pool.aux + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight));
                             }
                         }
                         float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
@@ -517,12 +514,12 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
                         if (!(is_black(fr) || pdf == 0)) {
                             nf |= F_MIS;
                             mis_absdot = fabsf(dot(out, h.nor));
-                            st_rec<FUSED>(a.pool.misd + slot, make_float4(out.x, out.y, out.z, pdf));
-                            st_rec<FUSED>(a.pool.misf + slot, make_float4(fr.x, fr.y, fr.z, denom));
+                            st_rec<FUSED>(pool.misd + slot, make_float4(out.x, out.y, out.z, pdf));
+                            st_rec<FUSED>(pool.misf + slot, make_float4(fr.x, fr.y, fr.z, denom));
                         } else if (VOL) {
-                            st_rec<FUSED>(a.pool.misf + slot, make_float4(0.f, 0.f, 0.f, denom));
+                            st_rec<FUSED>(pool.misf + slot, make_float4(0.f, 0.f, 0.f, denom));
                         }
-                        st_rec<FUSED>(a.pool.ldl + slot, make_float4(ldl.x, ldl.y, ldl.z, mis_absdot));
+                        st_rec<FUSED>(pool.ldl + slot, make_float4(ldl.x, ldl.y, ldl.z, mis_absdot));
                         nf |= ((uint32_t)(medium + 1) << kMedium2Shift);
                     }
                     float c0 = rng_next(rng), c1 = rng_next(rng), c2 = rng_next(rng);            // :997-1003
@@ -587,19 +584,19 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
     uint32_t qbase = 0u;
     if (lane == 0u) {
         if (m_fin) sbase = atomicAdd(&a.counters->next_sample, (unsigned long long)__popc(m_fin));
-        if (nc + ns + nm) qbase = atomicAdd(&a.q.ctl->tail[a.parity & 1u], nc + ns + nm);
+        if (nc + ns + nm) qbase = atomicAdd(&q.ctl->tail[parity & 1u], nc + ns + nm);
         if (m_ret | m_ret2) {
-            if (FUSED) atomicAdd(a.cta_retired, (uint32_t)(__popc(m_ret) + __popc(m_ret2)));
+            if (FUSED) atomicAdd(cta_retired, (uint32_t)(__popc(m_ret) + __popc(m_ret2)));
             else atomicAdd(&a.counters->done_samples, (unsigned long long)(__popc(m_ret) + __popc(m_ret2)));
         }
     }
     sbase = __shfl_sync(kFullMask, sbase, 0);
     qbase = __shfl_sync(kFullMask, qbase, 0);
-    if (rays & F_CONT) a.q.entries[qbase + (uint32_t)__popc(mc & lt)] = slot;
-    if (rays & F_SHADOW) a.q.entries[qbase + nc + (uint32_t)__popc(ms & lt)] = slot | (1u << kKindShift);
-    if (rays & F_MIS) a.q.entries[qbase + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
+    if (rays & F_CONT) q.entries[qbase + (uint32_t)__popc(mc & lt)] = slot;
+    if (rays & F_SHADOW) q.entries[qbase + nc + (uint32_t)__popc(ms & lt)] = slot | (1u << kKindShift);
+    if (rays & F_MIS) q.entries[qbase + nc + ns + (uint32_t)__popc(mm & lt)] = slot | (2u << kKindShift);
     if (idle_dead) return;
-    if (FUSED) *a.cta_busy = 1u;                 // (benign race: every writer stores the same value)
+    if (FUSED) *cta_busy = 1u;                 // (benign race: every writer stores the same value)
 
     uint32_t carried_sample = 0u;
     if (want_new) {
@@ -610,15 +607,15 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
             // the batch ran out between the snapshot and the atomic (at most one step per batch); the reserved queue
             // entry stays and traces one harmless ray
             if (finished) {                                   // the slot dies
-                st_rec<FUSED>(a.pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
-                st_rec<FUSED>(a.pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
+                st_rec<FUSED>(pool.o_rng + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(rng)));
+                st_rec<FUSED>(pool.d_flags + slot, make_float4(0.f, 0.f, 1.f, __uint_as_float(0u)));
                 return;
             }
             // carry_now: fall back to the idle step — the state computed by section B (TERMINATE | PENDING) is kept
         } else {
             uint32_t pending_bits = 0u;
             if (carry_now) {
-                st_rec<FUSED>(a.pool.carry + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
+                st_rec<FUSED>(pool.carry + slot, make_float4(Li.x, Li.y, Li.z, 0.f));
                 carried_sample = sample;
                 pending_bits = F_CARRY | (nf & (F_PENDING | F_SHADOW | F_MIS | F_MEDSCATTER)) | (nf & (0xffu << kMedium2Shift));
             }
@@ -643,13 +640,13 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const uint32_t sl
         }
     }
     if (emitted_pending)
-        st_rec<FUSED>(a.pool.pend_o + slot, make_float4(pend_origin.x, pend_origin.y, pend_origin.z, __uint_as_float(carried_sample)));
+        st_rec<FUSED>(pool.pend_o + slot, make_float4(pend_origin.x, pend_origin.y, pend_origin.z, __uint_as_float(carried_sample)));
     if (specular) nf |= F_SPECULAR;
     nf |= ((uint32_t)bounces & 0x7fu) << kBounceShift;
-    st_rec<FUSED>(a.pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
-    st_rec<FUSED>(a.pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
-    st_rec<FUSED>(a.pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));
-    st_rec<FUSED>(a.pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, __uint_as_float(kdone)));
+    st_rec<FUSED>(pool.o_rng + slot, make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng)));
+    st_rec<FUSED>(pool.d_flags + slot, make_float4(new_d.x, new_d.y, new_d.z, __uint_as_float(nf)));
+    st_rec<FUSED>(pool.beta_s + slot, make_float4(beta.x, beta.y, beta.z, __uint_as_float(sample)));
+    st_rec<FUSED>(pool.li_t + slot, make_float4(Li.x, Li.y, Li.z, __uint_as_float(kdone)));
 }
 
 // Resident CTAs per SM: the kernel is latency bound (long scoreboard), so occupancy beats registers — 8 CTAs (64
@@ -696,7 +693,7 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     SlotRec r;
     load_slot<VOL>(a.pool, slot, r);
 #endif
-    shade_slot<VOL, MATS, false>(a, slot, slot, (uint32_t)a.pool.n, r, a.counters->next_sample);
+    shade_slot<VOL, MATS, false>(a, a.pool, a.q, a.parity, nullptr, nullptr, slot, slot, (uint32_t)a.pool.n, r, a.counters->next_sample);
 }
 
 // ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------

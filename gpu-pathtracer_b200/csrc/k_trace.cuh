@@ -130,6 +130,7 @@ struct TraceArgs {
     uint32_t small_prim_bytes;                       // k_trace_small: bytes of ALL primitive records (always staged)
     const float4* leaves;                            // small scenes: primitive-group records (box + <= 4 primitives)
     int32_t n_leaves;
+    int32_t sec_tmax;                                // kind-2 rays carry their own tmax in misd.w (heterogeneous-media wavefront: Tr() segments)
 };
 
 constexpr int kDone = (int)0x80000000;               // traversal cursor: nothing left to visit (also "no postponed leaf")
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                 float4 dv;
                 if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
                 else if (kind == 1u) dv = a.pool.shd[slot];
-                else { dv = a.pool.misd[slot]; dv.w = INFINITY; }
+                else { dv = a.pool.misd[slot]; if (!a.sec_tmax) dv.w = INFINITY; }
                 d = mk3(dv.x, dv.y, dv.z);
                 tmax = dv.w;
                 anyhit = !VOL && kind == 1u;
@@ -389,24 +390,24 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
 // pool planes, test all group boxes, run the flat primitive loop, write the hit / visibility back.  `prims` / `leaves`
 // point at the staged (shared-memory) copies; the pool planes are global (k_trace_small) or shared (k_wave.cuh).
 template <bool VOL>
-__device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const WPrim* __restrict__ prims, const float4* __restrict__ leaves,
-                                                const uint32_t entry, uint32_t& nrays) {
+__device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const Pool& pool, const WPrim* __restrict__ prims,
+                                                const float4* __restrict__ leaves, const uint32_t entry, uint32_t& nrays) {
     const float eps = a.sc.eps;
     const int n_leaves = a.n_leaves;
     const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
-    const float4 orng = kind == 0u ? a.pool.o_rng[slot] : a.pool.pend_o[slot];             // shadow / MIS rays keep their own origin
+    const float4 orng = kind == 0u ? pool.o_rng[slot] : pool.pend_o[slot];             // shadow / MIS rays keep their own origin
     f3 o = mk3(orng.x, orng.y, orng.z);
     float4 dv;
-    if (kind == 0u) { dv = a.pool.d_flags[slot]; dv.w = INFINITY; }
-    else if (kind == 1u) dv = a.pool.shd[slot];
-    else { dv = a.pool.misd[slot]; dv.w = INFINITY; }
+    if (kind == 0u) { dv = pool.d_flags[slot]; dv.w = INFINITY; }
+    else if (kind == 1u) dv = pool.shd[slot];
+    else { dv = pool.misd[slot]; if (!a.sec_tmax) dv.w = INFINITY; }
     const f3 d = mk3(dv.x, dv.y, dv.z);
     float tmax = dv.w;
     const bool anyhit = !VOL && kind == 1u;
     f3 tr = mk3(1, 1, 1);
     float remain = tmax;
     int medium = -1;
-    if (VOL && kind == 1u) medium = (int)((__float_as_uint(a.pool.d_flags[slot].w) >> kMedium2Shift) & 0xffu) - 1;
+    if (VOL && kind == 1u) medium = (int)((__float_as_uint(pool.d_flags[slot].w) >> kMedium2Shift) & 0xffu) - 1;
     const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
     int hprim; float hb1 = 0.f, hb2 = 0.f;
     for (;;) {                                   // one pass per ray; vpt shadow rays repeat it per segment (Tr())
@@ -481,12 +482,12 @@ __device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const WPrim*
     }
     if (kind != 1u) {
         const float4 h = make_float4(hprim >= 0 ? tmax : -1.f, __int_as_float(hprim), hb1, hb2);
-        if (kind == 0u) a.pool.hit0[slot] = h; else a.pool.hit1[slot] = h;
+        if (kind == 0u) pool.hit0[slot] = h; else pool.hit1[slot] = h;
     } else if (!VOL) {
         const float v = hprim >= 0 ? 0.f : 1.f;
-        a.pool.vis[slot] = make_float4(v, v, v, 0.f);
+        pool.vis[slot] = make_float4(v, v, v, 0.f);
     } else {
-        a.pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
+        pool.vis[slot] = make_float4(tr.x, tr.y, tr.z, 0.f);
     }
 }
 
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_small(const TraceArgs a
     uint32_t nrays = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tail; idx += stride) {
-        trace_small_ray<VOL>(a, prims, leaves, a.q.entries[idx], nrays);
+        trace_small_ray<VOL>(a, a.pool, prims, leaves, a.q.entries[idx], nrays);
     }
 #ifndef B200PT_EMULATE
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);

@@ -1,0 +1,159 @@
+// k_wave.cuh — CTA-LOCAL wavefront for scenes whose acceleration structure fits in shared memory (<= 256 primitives:
+// the Cornell-box family, BASELINE configs C1 / C2 / C5).
+//
+// The global wavefront (k_shade + k_trace over a path pool in HBM) streams ~1.8 KB of path state per sample through
+// HBM for a scene of 3 KB, and pays two kernel launches per bounce.  Here a persistent CTA owns kWaveThreads path
+// SLOTS whose whole state (the same 14 / 15 float4 planes) lives in SHARED memory next to the TMA-staged scene, and
+// runs the SAME two stages as phases of one kernel:
+//
+//   shade phase   thread t runs shade_slot() on slot t (finish the previous bounce's direct light, shade the hit,
+//                 retire + regenerate from the batch's sample counter) and appends the slot's <= 3 rays to the
+//                 CTA's ray queue in shared memory (one warp-aggregated shared-memory atomic per warp);
+//   trace phase   the CTA's threads take the queued rays in order — a COMPACT list, so every lane of every warp but
+//                 the last carries a ray whatever mix of live / dead / shadow-less slots produced it — and run
+//                 trace_small_ray() (flat box list + Moeller-Trumbore, k_trace.cuh) with ray and hit records in
+//                 shared memory.
+//
+// Nothing but the finished samples (16 B each) and three counters ever goes to global memory; one launch renders a
+// whole spp batch.  Paths still move wavefront-fashion (all slots shade, then all rays trace), which keeps the SIMT
+// width the megakernel of the reference loses to path-length divergence.
+#pragma once
+#include "k_shade.cuh"
+#include "k_trace.cuh"
+#include "k_het.cuh"
+#ifdef B200PT_EMULATE
+#include <vector>
+#endif
+
+namespace pt {
+
+constexpr int kWaveThreads = 256;
+
+// The shade / trace bodies read scene, camera, shard map and batch from the same argument structs as the global
+// wavefront (kernel parameters: constant bank); their pool / queue members are unused here — the CTA's own planes and
+// queue in shared memory are handed to the bodies explicitly.
+struct WaveArgs {
+    ShadeArgs sa;
+    TraceArgs ta;
+};
+
+// Shared-memory footprint of one CTA: scene (primitive records + group boxes) + path planes + ray queue.
+template <bool VOL> struct WavePlanes { static constexpr int value = VOL ? 15 : 14; };
+template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_leaves) {
+    return (size_t)((prim_bytes + (uint32_t)n_leaves * 32u + 127u) & ~127u) + (size_t)WavePlanes<VOL>::value * kWaveThreads * sizeof(float4) +
+           (size_t)3 * kWaveThreads * sizeof(uint32_t);
+}
+
+#ifndef B200PT_EMULATE
+#define PT_WAVE_FOR_THREADS(t) for (uint32_t t = threadIdx.x, once_ = 1u; once_; once_ = 0u)
+#define PT_WAVE_SYNC() __syncthreads()
+#else
+// CPU emulation of the test suite: one host thread plays a whole CTA, phase by phase
+#define PT_WAVE_FOR_THREADS(t) for (uint32_t t = 0; t < (uint32_t)kWaveThreads; ++t)
+#define PT_WAVE_SYNC() do { } while (0)
+#endif
+
+// HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
+template <bool VOL, uint32_t MATS, bool HET>
+__global__ void __launch_bounds__(kWaveThreads, (VOL || MATS != kMatsLambertOnly) ? 2 : 3) k_wave_small(const WaveArgs a) {
+    const ShadeArgs& sa = a.sa;
+    const TraceArgs& ta = a.ta;
+#ifndef B200PT_EMULATE
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+#else
+    static thread_local std::vector<unsigned char> smem_vec;
+    smem_vec.assign(wave_smem_bytes<VOL>(ta.small_prim_bytes, ta.n_leaves) + 128, 0);
+    unsigned char* smem_raw = smem_vec.data();
+#endif
+    __shared__ uint32_t s_busy[2], s_retired, s_rays;
+    __shared__ QueueCtl s_ctl;
+    __shared__ unsigned long long s_next;
+
+    const uint32_t scene_bytes = (ta.small_prim_bytes + (uint32_t)ta.n_leaves * 32u + 127u) & ~127u;
+    float4* const planes = reinterpret_cast<float4*>(smem_raw + scene_bytes);
+    uint32_t* const s_queue = reinterpret_cast<uint32_t*>(planes + (size_t)WavePlanes<VOL>::value * kWaveThreads);
+    const WPrim* prims = ta.sc.prims;
+    const float4* leaves = ta.leaves;
+
+    // ---- stage the scene with TMA, clear the slots
+#ifndef B200PT_EMULATE
+    {
+        const uint32_t lb = (uint32_t)ta.n_leaves * 32u;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            s_ctl.tail[0] = s_ctl.tail[1] = 0u; s_ctl.head[0] = s_ctl.head[1] = 0u;
+            s_busy[0] = s_busy[1] = 0u; s_retired = 0u; s_rays = 0u;
+            s_next = sa.counters->next_sample;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, ta.small_prim_bytes + lb);
+            tma_bulk_g2s(smem_raw, ta.sc.prims, ta.small_prim_bytes, &bar);
+            tma_bulk_g2s(smem_raw + ta.small_prim_bytes, ta.leaves, lb, &bar);
+        }
+        // all slots start dead with no static sample consumed (the flags word and li_t.w are what shade_slot looks at)
+        for (int k = 0; k < WavePlanes<VOL>::value; ++k) planes[(size_t)k * kWaveThreads + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(&bar, 0);
+        prims = reinterpret_cast<const WPrim*>(smem_raw);
+        leaves = reinterpret_cast<const float4*>(smem_raw + ta.small_prim_bytes);
+        __syncthreads();
+    }
+#else
+    s_ctl.tail[0] = s_ctl.tail[1] = 0u; s_ctl.head[0] = s_ctl.head[1] = 0u;
+    s_busy[0] = s_busy[1] = 0u; s_retired = 0u; s_rays = 0u;
+    s_next = sa.counters->next_sample;
+#endif
+
+    Pool P;
+    P.o_rng = planes; P.d_flags = planes + 1 * kWaveThreads; P.beta_s = planes + 2 * kWaveThreads; P.li_t = planes + 3 * kWaveThreads;
+    P.shd = planes + 4 * kWaveThreads; P.misd = planes + 5 * kWaveThreads; P.ldl = planes + 6 * kWaveThreads; P.misf = planes + 7 * kWaveThreads;
+    P.beta_old = planes + 8 * kWaveThreads; P.hit0 = planes + 9 * kWaveThreads; P.hit1 = planes + 10 * kWaveThreads; P.vis = planes + 11 * kWaveThreads;
+    P.pend_o = planes + 12 * kWaveThreads; P.carry = planes + 13 * kWaveThreads; P.aux = planes + (VOL ? 14 : 0) * kWaveThreads;
+    P.n = kWaveThreads;
+    RayQueue Q; Q.entries = s_queue; Q.ctl = &s_ctl;
+    const uint32_t pool_n = gridDim.x * (uint32_t)kWaveThreads;
+
+    for (uint32_t step = 0;; ++step) {
+        const uint32_t par = step & 1u;
+        // ---- shade phase
+        PT_WAVE_FOR_THREADS(t) {
+#ifdef B200PT_EMULATE
+            threadIdx.x = t;
+#endif
+            if (HET) het_slot<MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, s_next);
+            else {
+                SlotRec r;
+                load_slot<VOL>(P, t, r);
+                shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, r, s_next);
+            }
+        }
+        PT_WAVE_SYNC();
+        const uint32_t tail = s_ctl.tail[par];
+        if (tail == 0u && s_busy[par] == 0u) break;          // no ray in flight, no slot alive, no sample left
+        // ---- trace phase (thread 0 also refreshes the sample-counter snapshot and re-arms the other control set)
+        PT_WAVE_FOR_THREADS(t) {
+#ifdef B200PT_EMULATE
+            threadIdx.x = t;
+#endif
+            if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
+            uint32_t nrays = 0;
+            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kWaveThreads) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
+#ifndef B200PT_EMULATE
+            for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
+#endif
+            if (pt_lane() == 0u && nrays) atomicAdd(&s_rays, nrays);
+        }
+        PT_WAVE_SYNC();
+    }
+    // ---- per-CTA statistics: one atomic each
+    PT_WAVE_FOR_THREADS(t) {
+        if (t == 0u) {
+            if (s_retired) atomicAdd(&sa.counters->done_samples, (unsigned long long)s_retired);
+            if (s_rays) atomicAdd(&sa.counters->rays, (unsigned long long)s_rays);
+        }
+    }
+}
+
+}  // namespace pt

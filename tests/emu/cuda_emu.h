@@ -98,3 +98,6 @@ template <class F> static inline void emu_launch(F&& body, unsigned grid, unsign
     }
 }
 #define PT_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch([&]() { kernel(__VA_ARGS__); }, (unsigned)(grid), (unsigned)(block))
+// kernels written CTA-at-a-time (k_wave.cuh: phases separated by block barriers): the body is called ONCE per block and
+// loops over the block's threads itself, phase by phase
+#define PT_LAUNCH_CTA(kernel, grid, block, smem, stream, ...) emu_launch([&]() { kernel(__VA_ARGS__); }, (unsigned)(grid), 1u)

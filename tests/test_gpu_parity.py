@@ -118,7 +118,9 @@ def test_matches_cpu_oracle(name, oracle):
     # The 50k-random-triangle scene has ~1000x more silhouette edges per ray and a bright sun, so there the
     # CPU-vs-GPU check is on the FRACTION of visibly different pixels (the reference's own CUDA build is the
     # oracle of record for that scene: test_matches_reference_cuda_integrator, <= 1e-4).
-    if name.startswith("smoke"):
+    if name.startswith("smoke") or name.startswith("material_zoo"):
+        # (material zoo: mirror / glass caustic paths onto a small emitter are fireflies by construction, and the
+        # microfacet code draws through sinf / cosf / atanf / rsqrtf, which differ from libm in the last ulp)
         # delta / ratio tracking takes a discrete decision (density / max > u) at every step of every free flight, each
         # behind a logf: device-vs-libm last-ulp differences flip ~100x more decisions than in the surface-only scenes.
         # The CPU oracle bounds gross errors here; parity proper is vs the reference CUDA build (above, <= 1e-4).

@@ -225,14 +225,60 @@ def test_reserve_iters_presizes_the_sample_planes(emu, oracle):
 
 
 def test_default_lane_counts(emu, monkeypatch):
-    """Three lanes when the small-scene kernel traces, two otherwise, ONE for heterogeneous media (k_volpath_seq is a
-    single persistent launch that fills the GPU) — and B200PT_LANES overrides all of them."""
+    """ONE lane when the CTA-local wavefront renders (scenes of <= 256 primitives, heterogeneous media included:
+    k_wave_small is a single persistent launch per batch), three when the small-scene kernel traces for the global
+    wavefront (B200PT_FUSED=0), two for the tree kernel — and B200PT_LANES overrides all of them."""
     monkeypatch.delenv("B200PT_LANES", raising=False)
-    for mk, want in ((lambda: pt.scenes.cornell_pt(128, 128, 4), 3),
-                     (lambda: pt.scenes.random_triangles(2000, 128, 128, 4), 2),
-                     (lambda: pt.scenes.cornell_smoke(128, 128, 4, 1), 1)):
+    monkeypatch.delenv("B200PT_FUSED", raising=False)
+    for mk, want, fused in ((lambda: pt.scenes.cornell_pt(128, 128, 4), 1, 1),
+                            (lambda: pt.scenes.random_triangles(2000, 128, 128, 4), 2, 0),
+                            (lambda: pt.scenes.cornell_smoke(128, 128, 4, 1), 1, 1)):
         with pt.PathTracer(mk()) as r:
-            assert r.info("lanes") == want
+            assert r.info("lanes") == want and r.info("fused") == fused
+    monkeypatch.setenv("B200PT_FUSED", "0")
+    with pt.PathTracer(pt.scenes.cornell_pt(128, 128, 4)) as r:
+        assert r.info("lanes") == 3 and r.info("fused") == 0
     monkeypatch.setenv("B200PT_LANES", "2")
     with pt.PathTracer(pt.scenes.cornell_smoke(128, 128, 4, 1)) as r:
         assert r.info("lanes") == 2
+
+
+@pytest.mark.parametrize("name", ["cornell", "vol_caustic", "material_zoo_vpt", "smoke_ratio", "shipped_smoke"])
+def test_cta_local_and_global_wavefront_give_the_same_bits(name, emu, monkeypatch):
+    """k_wave_small (path state in shared memory, one launch per batch) and the global wavefront (k_shade + k_trace_small
+    over the HBM pool) run the same shade / trace bodies: same image, same ray count — also when sharded and with the
+    CTA-local kernel limited to a single CTA per SM."""
+    s = SCENES[name]()
+    out = []
+    for fused, shard in ((1, None), (0, None), (1, (1, 2, 32, 32)), (0, (1, 2, 32, 32))):
+        monkeypatch.setenv("B200PT_FUSED", str(fused))
+        with pt.PathTracer(s, shard=shard) as r:
+            assert r.info("fused") == fused
+            if fused:
+                r.set_option("wave_ctas_per_sm", 1)
+            tone = r.render(2, reset=True, spp=5)
+            out.append((r.accum(), tone, r.stats()["rays"], r.stats()["samples"]))
+    for a, b in ((out[0], out[1]), (out[2], out[3])):
+        assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
+        assert a[3] == b[3] and 0 <= b[2] - a[2] <= 0.2 * a[2]           # (the global wavefront traces spare rays for slots that die on an exhausted batch)
+
+
+@pytest.mark.parametrize("estimator", [0, 1, 2])
+@pytest.mark.parametrize("mode", ["cta_local", "global_small", "global_tree"])
+def test_heterogeneous_media_coroutine_equals_oracle(estimator, mode, emu, oracle, monkeypatch):
+    """The heterogeneous-media wavefront (k_het.cuh: one closest-hit query per step, tracking loops in the glue) against the
+    oracle, bit for bit, for delta / ratio / residual-ratio transmittance estimators — as phases of the CTA-local kernel,
+    as k_het_shade + k_trace_small over the HBM pool, and as k_het_shade + the tree kernel k_trace."""
+    s = pt.scenes.cornell_smoke(64, 64, 8, estimator)
+    ref_acc, ref_tone = oracle.render(s, 4, 3)
+    if mode != "cta_local":
+        monkeypatch.setenv("B200PT_FUSED", "0")
+    with pt.PathTracer(s, pool=2048 if mode == "global_small" else None) as r:
+        if mode == "global_tree":
+            r.set_option("small_kernel", 0)
+        assert r.info("fused") == (1 if mode == "cta_local" else 0)
+        tone = r.render(4, reset=True, spp=3)
+        acc = r.accum()
+        assert r.stats()["samples"] == 3 * 64 * 64
+    assert np.array_equal(_bits(acc), _bits(ref_acc))
+    assert np.array_equal(_bits(tone), _bits(ref_tone))
