@@ -14,6 +14,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#ifndef B200PT_EMULATE
+#include <dlfcn.h>
+#endif
 
 using namespace pt;
 
@@ -84,6 +88,10 @@ struct b200pt_ctx {
 #endif
     double graph_launches = 0, graph_steps = 0;
     unsigned long long rays_seen = 0;      // device ray counters at the end of the previous render call
+    // multi-GPU: NCCL communicator of this rank (opaque ncclComm_t) and, on the reduce root, the full-image sum
+    void* comm = nullptr; int comm_rank = 0, comm_size = 1;
+    float* reduced = nullptr;
+    uint32_t reduced_iter = 0;
 };
 
 template <class T> static int dev_alloc(b200pt_ctx* c, T** p, size_t n, bool zero = false) {
@@ -1027,10 +1035,16 @@ extern "C" int b200pt_stats(b200pt_ctx* c, double* out5) {
     return 0;
 }
 
+#ifndef B200PT_EMULATE
+static void comm_destroy(void* comm);
+#endif
 extern "C" int b200pt_destroy(b200pt_ctx* c) {
     if (!c) return fail(B200PT_EINVAL, "null context");
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+#ifndef B200PT_EMULATE
+    if (c->comm) { comm_destroy(c->comm); c->comm = nullptr; }
+#endif
     for (void* p : c->allocs) cudaFree(p);
     for (Lane& L : c->lanes) {
         free_pool(L);
@@ -1049,6 +1063,226 @@ extern "C" int b200pt_destroy(b200pt_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     delete c;
+    return 0;
+}
+
+// ---- multi-GPU: NCCL reduce of the accumulation framebuffers inside the library -------------------------------
+#ifndef B200PT_EMULATE
+namespace {
+// NCCL is bound at run time: the library has no link-time dependency on it, and a process that already carries an NCCL
+// (torch's bundled one) shares it.
+struct Id128 { char b[128]; };                         // ncclUniqueId (passed BY VALUE to ncclCommInitRank)
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, struct Id128, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+int nccl_load() {
+    if (g_nccl.h) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(B200PT_EUNSUPPORTED, std::string("NCCL not available: ") + dlerror());
+    auto sym = [&](const char* n) { return dlsym(h, n); };
+    g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))sym("ncclCommInitRank");
+    g_nccl.CommInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
+    g_nccl.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))sym("ncclReduce");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommInitAll || !g_nccl.Reduce || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.CommDestroy)
+        return fail(B200PT_EUNSUPPORTED, "libnccl.so.2 lacks a required symbol");
+    g_nccl.h = h;
+    return 0;
+}
+int nccl_fail(int rc, const char* what) {
+    return fail(B200PT_ECUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error") + " (" + std::to_string(rc) + ")");
+}
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;          // ncclDataType_t / ncclRedOp_t values (nccl.h)
+}  // namespace
+static void comm_destroy(void* comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+#endif
+
+static int ensure_reduced(b200pt_ctx* c) {
+    if (c->reduced) return 0;
+    return dev_alloc(c, &c->reduced, 3 * (size_t)c->width * c->height, true);
+}
+// root side of a reduce: tonemap the full-image sum into `output` (what Output does after the last iteration)
+static int finish_reduced(b200pt_ctx* c, uint32_t iter, float* output, int output_is_device) {
+    const size_t npix = (size_t)c->width * c->height;
+    c->reduced_iter = iter;
+    if (!output) { CK(cudaStreamSynchronize(c->stream)); return 0; }
+    float* out_dev = output_is_device ? output : c->out;
+    PT_LAUNCH(k_tonemap, ((uint32_t)npix + 255) / 256, 256, 0, c->stream, c->reduced, out_dev, (uint32_t)npix, iter, c->last_filmic);
+    if (!output_is_device) CK(cudaMemcpyAsync(output, out_dev, 3 * npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200pt_comm_unique_id(void* id128) {
+#ifdef B200PT_EMULATE
+    (void)id128; return fail(B200PT_EUNSUPPORTED, "NCCL communicators need a GPU build");
+#else
+    if (!id128) return fail(B200PT_EINVAL, "null argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    int nr = g_nccl.GetUniqueId(id128);
+    return nr ? nccl_fail(nr, "ncclGetUniqueId") : 0;
+#endif
+}
+extern "C" int b200pt_comm_init(b200pt_ctx* c, int n_ranks, int rank, const void* id128) {
+#ifdef B200PT_EMULATE
+    (void)c; (void)n_ranks; (void)rank; (void)id128; return fail(B200PT_EUNSUPPORTED, "NCCL communicators need a GPU build");
+#else
+    if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(B200PT_EINVAL, "bad argument");
+    if (c->comm) return fail(B200PT_EINVAL, "context already has a communicator");
+    if (c->map.n_shards != n_ranks || c->map.shard != rank) return fail(B200PT_EINVAL, "the context's shard must be {rank, n_ranks}");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    Id128 id; std::memcpy(&id, id128, sizeof(id));
+    int nr = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+    if (nr) { c->comm = nullptr; return nccl_fail(nr, "ncclCommInitRank"); }
+    c->comm_rank = rank; c->comm_size = n_ranks;
+    return 0;
+#endif
+}
+extern "C" int b200pt_render_reduce(b200pt_ctx* c, const void* camera, uint32_t first_iter, uint32_t spp, int reset, int root,
+                                    float* output, int output_is_device) {
+#ifdef B200PT_EMULATE
+    (void)c; (void)camera; (void)first_iter; (void)spp; (void)reset; (void)root; (void)output; (void)output_is_device;
+    return fail(B200PT_EUNSUPPORTED, "NCCL communicators need a GPU build");
+#else
+    if (!c || !c->comm) return fail(B200PT_EINVAL, "b200pt_comm_init first");
+    if (root < 0 || root >= c->comm_size) return fail(B200PT_EINVAL, "bad root");
+    int rc = b200pt_render(c, camera, first_iter, spp, reset, nullptr, 0);
+    if (rc) return rc;
+    const bool is_root = c->comm_rank == root;
+    if (is_root && (rc = ensure_reduced(c))) return rc;
+    // the ONE collective of the data path: float3 framebuffer, sum, onto root, on the context's stream (NVLink / NVSwitch)
+    int nr = g_nccl.Reduce(c->acc, is_root ? c->reduced : nullptr, 3 * (size_t)c->width * c->height, kNcclFloat32, kNcclSum, root, c->comm, c->stream);
+    if (nr) return nccl_fail(nr, "ncclReduce");
+    if (is_root) return finish_reduced(c, first_iter + spp - 1, output, output_is_device);
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+#endif
+}
+extern "C" int b200pt_reduced_accum(b200pt_ctx* c, float* dst, int dst_is_device) {
+    if (!c || !dst) return fail(B200PT_EINVAL, "null argument");
+    if (!c->reduced) return fail(B200PT_EINVAL, "no reduced image on this context (not the root of a reduce)");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, c->reduced, 3 * (size_t)c->width * c->height * sizeof(float),
+                       dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// single process, several GPUs
+struct b200pt_multi {
+    std::vector<b200pt_ctx*> ctx;
+    std::vector<void*> comms;
+    double stats[5] = {0, 0, 0, 0, 0};
+};
+extern "C" int b200pt_multi_destroy(b200pt_multi* m) {
+    if (!m) return fail(B200PT_EINVAL, "null argument");
+#ifndef B200PT_EMULATE
+    for (void* cm : m->comms) if (cm && g_nccl.CommDestroy) g_nccl.CommDestroy(cm);
+#endif
+    for (b200pt_ctx* c : m->ctx) if (c) { c->comm = nullptr; b200pt_destroy(c); }
+    delete m;
+    return 0;
+}
+extern "C" int b200pt_create_multi(const b200pt_scene_view* scene, uint32_t width, uint32_t height, float epsilon,
+                                   int n_gpus, const int* devices, b200pt_multi** out_multi) {
+    if (!scene || !out_multi || n_gpus < 1 || n_gpus > 64) return fail(B200PT_EINVAL, "bad argument");
+    b200pt_multi* m = new b200pt_multi();
+    m->ctx.assign(n_gpus, nullptr);
+    std::vector<int> devs(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) devs[i] = devices ? devices[i] : i;
+#ifdef B200PT_EMULATE
+    for (int i = 0; i < n_gpus; ++i) devs[i] = 0;              // the emulation has one "device"
+#endif
+    for (int i = 0; i < n_gpus; ++i) {
+        b200pt_shard sh{i, n_gpus, 32, 32};
+        int rc = b200pt_create(scene, width, height, epsilon, devs[i], n_gpus > 1 ? &sh : nullptr, &m->ctx[i]);
+        if (rc) { std::string keep = g_err; b200pt_multi_destroy(m); g_err = keep; return rc; }
+    }
+#ifndef B200PT_EMULATE
+    if (n_gpus > 1) {
+        int rc = nccl_load();
+        if (rc) { std::string keep = g_err; b200pt_multi_destroy(m); g_err = keep; return rc; }
+        m->comms.assign(n_gpus, nullptr);
+        int nr = g_nccl.CommInitAll(m->comms.data(), n_gpus, devs.data());
+        if (nr) { m->comms.clear(); nccl_fail(nr, "ncclCommInitAll"); std::string keep = g_err; b200pt_multi_destroy(m); g_err = keep; return B200PT_ECUDA; }
+        for (int i = 0; i < n_gpus; ++i) { m->ctx[i]->comm = m->comms[i]; m->ctx[i]->comm_rank = i; m->ctx[i]->comm_size = n_gpus; }
+    }
+#endif
+    *out_multi = m;
+    return 0;
+}
+extern "C" int b200pt_multi_render(b200pt_multi* m, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
+                                   float* output, int output_is_device) {
+    if (!m || !camera) return fail(B200PT_EINVAL, "null argument");
+    const int n = (int)m->ctx.size();
+    if (n == 1) {
+        int rc = b200pt_render(m->ctx[0], camera, first_iter, spp, reset, output, output_is_device);
+        if (!rc) b200pt_stats(m->ctx[0], m->stats);
+        return rc;
+    }
+    // all shards render concurrently: one host thread per GPU drives that context's (blocking) render call
+    std::vector<int> rcs(n, 0);
+    std::vector<std::string> errs(n);
+    {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n; ++i)
+            th.emplace_back([&, i]() { rcs[i] = b200pt_render(m->ctx[i], camera, first_iter, spp, reset, nullptr, 0); if (rcs[i]) errs[i] = b200pt_last_error(); });
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < n; ++i) if (rcs[i]) return fail(rcs[i], "GPU " + std::to_string(i) + ": " + errs[i]);
+    b200pt_ctx* root = m->ctx[0];
+    int rc = ensure_reduced(root);
+    if (rc) return rc;
+    const size_t count = 3 * (size_t)root->width * root->height;
+#ifdef B200PT_EMULATE
+    std::memset(root->reduced, 0, count * sizeof(float));
+    for (int i = 0; i < n; ++i) for (size_t k = 0; k < count; ++k) root->reduced[k] += m->ctx[i]->acc[k];
+#else
+    int nr = g_nccl.GroupStart();
+    for (int i = 0; i < n && !nr; ++i) {
+        cudaSetDevice(m->ctx[i]->device);
+        nr = g_nccl.Reduce(m->ctx[i]->acc, i == 0 ? root->reduced : nullptr, count, kNcclFloat32, kNcclSum, 0, m->ctx[i]->comm, m->ctx[i]->stream);
+    }
+    int ne = g_nccl.GroupEnd();
+    if (nr || ne) return nccl_fail(nr ? nr : ne, "ncclReduce (group)");
+    for (int i = 1; i < n; ++i) { cudaSetDevice(m->ctx[i]->device); CK(cudaStreamSynchronize(m->ctx[i]->stream)); }
+    CK(cudaSetDevice(root->device));
+#endif
+    rc = finish_reduced(root, first_iter + spp - 1, output, output_is_device);
+    if (rc) return rc;
+    double agg[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        double s5[5]; b200pt_stats(m->ctx[i], s5);
+        agg[0] += s5[0]; agg[1] += s5[1]; agg[2] += s5[2]; agg[3] = std::max(agg[3], s5[3]); agg[4] = std::max(agg[4], s5[4]);
+    }
+    std::memcpy(m->stats, agg, sizeof(agg));
+    return 0;
+}
+extern "C" int b200pt_multi_get_accum(b200pt_multi* m, float* dst_host) {
+    if (!m || !dst_host) return fail(B200PT_EINVAL, "null argument");
+    if (m->ctx.size() == 1) return b200pt_get_accum(m->ctx[0], dst_host, 0);
+    return b200pt_reduced_accum(m->ctx[0], dst_host, 0);
+}
+extern "C" int b200pt_multi_stats(b200pt_multi* m, double* out5) {
+    if (!m || !out5) return fail(B200PT_EINVAL, "null argument");
+    std::memcpy(out5, m->stats, sizeof(m->stats));
     return 0;
 }
 

@@ -189,10 +189,13 @@ __device__ __forceinline__ f3 hg_sample(float g, float pa, float pb) {
     return mk3(sintheta * cosphi, costheta, sintheta * sinphi);
 }
 
-template <uint32_t MATS, bool FUSED>
+// QUEUED: the query goes into the ray queue (global wavefront: k_trace / k_trace_small pull it).  Otherwise the caller
+// traces it itself right away (warp-local stepping of the CTA-local kernel, k_wave.cuh) and gets its kind in `posted`
+// (0 none, 1 path ray = queue kind 0, 2 secondary query = queue kind 2).
+template <uint32_t MATS, bool FUSED, bool QUEUED>
 __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, const RayQueue& q, const uint32_t parity,
                                          uint32_t* cta_retired, uint32_t* cta_busy, const uint32_t slot, const uint32_t gslot,
-                                         const uint32_t pool_n, const unsigned long long next_snapshot) {
+                                         const uint32_t pool_n, const unsigned long long next_snapshot, uint32_t& posted) {
     const SceneDev& sc = a.sc;
     const uint32_t lane = pt_lane(), lt = (1u << lane) - 1u;
     const float4 df = pool.d_flags[slot], orng = pool.o_rng[slot], lt4 = pool.li_t[slot];
@@ -458,17 +461,20 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
         }
     }
     // ---- post the query: one aggregated queue reservation per warp
-    const uint32_t mp = __ballot_sync(kFullMask, post != 0u);
-    uint32_t qbase = 0u;
-    if (lane == 0u && mp) qbase = atomicAdd(&q.ctl->tail[parity & 1u], (uint32_t)__popc(mp));
-    qbase = __shfl_sync(kFullMask, qbase, 0);
-    if (post) q.entries[qbase + (uint32_t)__popc(mp & lt)] = slot | ((post == 2u ? 2u : 0u) << kKindShift);
+    posted = post;
+    if (QUEUED) {
+        const uint32_t mp = __ballot_sync(kFullMask, post != 0u);
+        uint32_t qbase = 0u;
+        if (lane == 0u && mp) qbase = atomicAdd(&q.ctl->tail[parity & 1u], (uint32_t)__popc(mp));
+        qbase = __shfl_sync(kFullMask, qbase, 0);
+        if (post) q.entries[qbase + (uint32_t)__popc(mp & lt)] = slot | ((post == 2u ? 2u : 0u) << kKindShift);
+    }
     if (!now_alive && !alive) {
         // stayed dead; keep kdone (the dynamic hand-out may have consumed nothing)
         if (want_new) st_rec<FUSED>(pool.li_t + slot, make_float4(0.f, 0.f, 0.f, __uint_as_float(kdone)));
         return;
     }
-    if (FUSED) *cta_busy = 1u;
+    if (FUSED && cta_busy) *cta_busy = 1u;
     uint32_t nf = now_alive ? H_ALIVE : 0u;
     if (specular) nf |= H_SPECULAR;
     nf |= ((uint32_t)bounces & 0x7fu) << kBounceShift;
@@ -485,7 +491,8 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
 template <uint32_t MATS>
 __global__ void __launch_bounds__(128, 6) k_het_shade(const ShadeArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;      // the pool size is a multiple of the block size
-    het_slot<MATS, false>(a, a.pool, a.q, a.parity, nullptr, nullptr, slot, slot, (uint32_t)a.pool.n, a.counters->next_sample);
+    uint32_t posted;
+    het_slot<MATS, false, true>(a, a.pool, a.q, a.parity, nullptr, nullptr, slot, slot, (uint32_t)a.pool.n, a.counters->next_sample, posted);
 }
 
 }  // namespace pt

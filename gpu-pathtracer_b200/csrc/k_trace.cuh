@@ -418,13 +418,46 @@ __device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const Pool& 
         float tn, best_t = INFINITY;
         int best = -1;
         if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
-            for (int l = 0; l < n_leaves; ++l) {
-                const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
-                if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
-                    mask |= 1ull << l;
-                    if (tn < best_t) { best_t = tn; best = l; }
+            // BBox::Intersect (src/bbox.h:77-96) on every group box, with the min / max of each axis' two plane distances
+            // replaced by a SELECTION: (plane - o) * (1/d) is monotonic in `plane`, so for a finite 1/d the smaller of
+            // the two distances belongs to the plane the sign of d picks — bit-identical tmin / tmax, but the near and far
+            // planes come from two 4-byte shared-memory loads at a per-lane offset and the 6 two-input min / max per box
+            // are gone (the loop was 35 % of the kernel's instructions, profiles/r02d_wave_c2_lines.txt).  A direction
+            // with a zero or denormal component (1/d infinite: the reference's test then leans on NaN-dropping fminf /
+            // fmaxf) takes the literal form.
+            // (A cheaper conservative test with one fused multiply-add per plane was tried and dropped: it needs grown
+            // boxes, and a box that is hit where the reference's is not lets the exact primitive test accept a grazing hit
+            // the reference culls — 1 sample in 12 288 of the 64 x 64 vol_caustic image, a direct view of the emitter.)
+            const bool fast = fabsf(inv.x) < INFINITY && fabsf(inv.y) < INFINITY && fabsf(inv.z) < INFINITY;
+            uint32_t m0 = 0u, m1 = 0u;
+            if (fast) {
+                const int nx = inv.x >= 0.f ? 0 : 3, ny = inv.y >= 0.f ? 1 : 4, nz = inv.z >= 0.f ? 2 : 5;      // word of the near plane
+                const float* lw = reinterpret_cast<const float*>(leaves);
+#define PT_BOX_TEST(l_, bit_, m_)                                                                                     \
+                {                                                                                                     \
+                    const int l = (l_);                                                                               \
+                    const float* g_ = lw + 8 * l;                                                                     \
+                    const float tnear = fmaxf(fmaxf((g_[nx] - o.x) * inv.x, (g_[ny] - o.y) * inv.y), (g_[nz] - o.z) * inv.z);          \
+                    const float tfar = fminf(fminf((g_[3 - nx] - o.x) * inv.x, (g_[5 - ny] - o.y) * inv.y), (g_[7 - nz] - o.z) * inv.z); \
+                    if (!(tfar <= 0.00001f) && !(tnear > tfar) && !(tnear > tmax)) {                                  \
+                        m_ |= 1u << (bit_);                                                                           \
+                        if (tnear < best_t) { best_t = tnear; best = l; }                                             \
+                    }                                                                                                 \
+                }
+                const int n0 = n_leaves < 32 ? n_leaves : 32;
+                for (int i = 0; i < n0; ++i) PT_BOX_TEST(i, i, m0)
+                for (int i = 32; i < n_leaves; ++i) PT_BOX_TEST(i, i - 32, m1)
+#undef PT_BOX_TEST
+            } else {
+                for (int l = 0; l < n_leaves; ++l) {
+                    const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
+                    if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
+                        if (l < 32) m0 |= 1u << l; else m1 |= 1u << (l - 32);
+                        if (tn < best_t) { best_t = tn; best = l; }
+                    }
                 }
             }
+            mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
         }
         // ---- flat primitive loop over the hit groups: nearest group first, then the others in index order; once
         // a closest hit is known, a group is re-tested against the shrunken interval before its primitives are

@@ -115,6 +115,38 @@ __global__ void __launch_bounds__(kWaveThreads, (VOL || MATS != kMatsLambertOnly
     RayQueue Q; Q.entries = s_queue; Q.ctl = &s_ctl;
     const uint32_t pool_n = gridDim.x * (uint32_t)kWaveThreads;
 
+    if (HET) {
+        // Heterogeneous media: every live slot posts exactly ONE closest-hit query per step, so there is nothing to compact
+        // — each lane traces its own query right after the glue and the warps step independently (no CTA barrier: a lane
+        // deep in a tracking loop holds up its warp, not the CTA).  Glue diverges, the traversal re-converges: all lanes of
+        // the warp enter trace_small_ray together, where the sequential per-thread form of this integrator reaches its
+        // traversal from three call sites inside divergent control flow.
+        PT_WAVE_FOR_THREADS(t) {
+#ifdef B200PT_EMULATE
+            threadIdx.x = t;
+#endif
+            uint32_t nrays = 0;
+            for (;;) {
+                const unsigned long long snap = *(volatile unsigned long long*)&sa.counters->next_sample;
+                uint32_t posted = 0u;
+                het_slot<MATS, true, false>(sa, P, Q, 0u, &s_retired, nullptr, t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, snap, posted);
+#ifndef B200PT_EMULATE
+                if (!__any_sync(kFullMask, posted != 0u)) break;
+#else
+                if (!posted) break;
+#endif
+                if (posted) trace_small_ray<VOL>(ta, P, prims, leaves, t | ((posted == 2u ? 2u : 0u) << kKindShift), nrays);
+#ifndef B200PT_EMULATE
+                __syncwarp();
+#endif
+            }
+#ifndef B200PT_EMULATE
+            for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
+#endif
+            if (pt_lane() == 0u && nrays) atomicAdd(&s_rays, nrays);
+        }
+        PT_WAVE_SYNC();
+    } else
     for (uint32_t step = 0;; ++step) {
         const uint32_t par = step & 1u;
         // ---- shade phase
@@ -122,12 +154,9 @@ __global__ void __launch_bounds__(kWaveThreads, (VOL || MATS != kMatsLambertOnly
 #ifdef B200PT_EMULATE
             threadIdx.x = t;
 #endif
-            if (HET) het_slot<MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, s_next);
-            else {
-                SlotRec r;
-                load_slot<VOL>(P, t, r);
-                shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, r, s_next);
-            }
+            SlotRec r;
+            load_slot<VOL>(P, t, r);
+            shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, r, s_next);
         }
         PT_WAVE_SYNC();
         const uint32_t tail = s_ctl.tail[par];

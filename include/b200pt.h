@@ -122,6 +122,37 @@ int b200pt_set_option(b200pt_ctx* ctx, const char* name, int64_t value);
 /* Replaces EndRender (src/pathtracer.cu:2697); frees ALL device memory of the context. */
 int b200pt_destroy(b200pt_ctx* ctx);
 
+/* ---- multi-GPU: the image's screen tiles are sharded over the GPUs of one box; after every spp batch
+ * the float3 accumulation framebuffers are summed onto one GPU by ONE NCCL reduce over NVLink, inside the library.
+ * The reference has no multi-GPU path (one process, one GPU: src/pathtracer.cu:2568); these entry points are what a
+ * caller of BeginRender / Render adds to use the whole box.  NCCL is loaded at run time (libnccl.so.2).
+ *
+ * (1) one process per GPU (torchrun / MPI style): every rank creates its context with shard = {rank, n_ranks, 32, 32},
+ *     rank 0 calls b200pt_comm_unique_id and ships the 128 bytes to the others by any means, every rank calls
+ *     b200pt_comm_init (collective), then b200pt_render_reduce per batch (collective): this rank's shard is rendered,
+ *     the accumulation buffers are reduced onto `root`, and on `root` `output` receives the tonemapped FULL image
+ *     (NULL / ignored elsewhere).  Disjoint tiles => one non-zero contributor per pixel => bit-identical to one GPU. */
+#define B200PT_COMM_ID_BYTES 128
+int b200pt_comm_unique_id(void* id128);
+int b200pt_comm_init(b200pt_ctx* ctx, int n_ranks, int rank, const void* id128);
+int b200pt_render_reduce(b200pt_ctx* ctx, const void* camera, uint32_t first_iter, uint32_t spp, int reset, int root,
+                         float* output, int output_is_device);
+/* root only: the reduced linear accumulation image of the last b200pt_render_reduce (w*h float3, host or device). */
+int b200pt_reduced_accum(b200pt_ctx* ctx, float* dst, int dst_is_device);
+
+/* (2) one process, n_gpus GPUs (what the BeginRender / Render / EndRender adapter uses when B200PT_GPUS > 1):
+ *     b200pt_create_multi makes one sharded context per device (devices == NULL: 0 .. n_gpus-1) and the NCCL
+ *     communicators (ncclCommInitAll); b200pt_multi_render renders all shards concurrently, reduces onto the first
+ *     device and writes the tonemapped full image to `output` (host, or device memory of the first device). */
+typedef struct b200pt_multi b200pt_multi;
+int b200pt_create_multi(const b200pt_scene_view* scene, uint32_t width, uint32_t height, float epsilon,
+                        int n_gpus, const int* devices, b200pt_multi** out_multi);
+int b200pt_multi_render(b200pt_multi* m, const void* camera, uint32_t first_iter, uint32_t spp, int reset,
+                        float* output, int output_is_device);
+int b200pt_multi_get_accum(b200pt_multi* m, float* dst_host);
+int b200pt_multi_stats(b200pt_multi* m, double* out5);      /* as b200pt_stats; samples / launches / rays summed, ms = max */
+int b200pt_multi_destroy(b200pt_multi* m);
+
 const char* b200pt_last_error(void);
 int b200pt_version(void);
 

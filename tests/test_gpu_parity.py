@@ -42,19 +42,18 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def _check_parity(name, acc, ref_acc, spp):
-    """The north_star criterion — per-channel RMSE of the linear image <= 1e-4 vs the reference's own CUDA build —
-    with isolated single-sample events accounted for separately.
+def _check_parity(name, acc, ref_acc, spp, allow_events=False):
+    """The north_star criterion: per-channel RMSE of the linear image acc / spp <= 1e-4 against the reference's own CUDA
+    build, RAW — every pixel counts.  (Round 1 had to set "isolated events" aside: single samples that take another
+    discrete decision after a last-bit difference and land on an emitter.  Round 2 read the contraction of the hot
+    expressions off the reference's SASS — barycentric interpolation, sphere discriminant, Fresnel / Reflect / Refract —
+    and pinned it; every BASELINE configuration now passes raw at its stated size with a margin of 25x or more.)
 
-    Both implementations replay the same paths from the same random numbers, but about 1 % of samples differ in the
-    last bit of some intermediate (FMA contraction is chosen per inlining context by nvcc), and
-    roughly 2e-8..1e-6 of samples (scene dependent: silhouette edges per ray, ill-conditioned pdfs) then take a
-    different DISCRETE decision.  When such a sample is a firefly (a lamp of radiance 7000 in C3, the sun in C4, a
-    scatter point in the emitter's plane in C5) it alone exceeds the RMSE budget of the whole image.  Those events are
-    counted — a pixel whose accumulated SUM differs by more than 1.0 (one sample off by a radiance >= 1), or, on small
-    images, by more than half of what a single pixel may contribute before it breaks the budget on its own
-    (0.5 x 1e-4 x spp x sqrt(pixels)) — their number is bounded by 5e-7 x samples (min 2; measured 2e-8 on C5,
-    3e-7 on the 200k-triangle scene), and the RMSE criterion is applied to all other pixels.  Raw RMSE is printed."""
+    `allow_events` — only for the heterogeneous-media widening scenes, where delta / ratio tracking takes a
+    discrete decision behind a logf at every step of every free flight: pixels whose accumulated SUM differs by more than
+    1.0 (one sample off by a radiance >= 1), or on small images by more than half of what one pixel may contribute before
+    it breaks the budget alone, are counted (<= 5e-7 x samples, min 2) and the criterion applies to all other pixels.
+    The number of such events is printed for every scene as a diagnostic."""
     raw = _rmse(acc / spp, ref_acc / spp)
     d = np.abs(acc.astype(np.float64) - ref_acc.astype(np.float64)).max(-1)
     npix = acc.shape[0] * acc.shape[1]
@@ -64,10 +63,12 @@ def _check_parity(name, acc, ref_acc, spp):
     keep = ~outliers
     rmse = np.sqrt((((acc - ref_acc)[keep] / spp).astype(np.float64) ** 2).mean(axis=0))
     same = float((_bits(acc) == _bits(ref_acc)).all(-1).mean())
-    print(f"{name}: raw rmse={raw}  isolated events={int(outliers.sum())} (allowed {allowed})  rmse without them={rmse}  "
-          f"bit-identical pixels={same:.5f}")
-    assert outliers.sum() <= allowed, (int(outliers.sum()), allowed)
-    assert (rmse <= TOL).all(), rmse
+    print(f"{name}: raw rmse={raw}  isolated events={int(outliers.sum())}  rmse without them={rmse}  bit-identical pixels={same:.5f}")
+    if allow_events:
+        assert outliers.sum() <= allowed, (int(outliers.sum()), allowed)
+        assert (rmse <= TOL).all(), rmse
+    else:
+        assert (raw <= TOL).all(), raw
     return raw
 
 
@@ -94,7 +95,9 @@ def test_matches_reference_cuda_integrator(name):
         ref.end()
     acc, tone = _render(s, 1, spp)
     assert ref_acc.mean() / spp > 1e-3
-    _check_parity(name, acc, ref_acc, spp)
+    # (reduced-size veach: a radiance-7000 lamp over 49 k pixels x 32 spp — ONE flipped sample is 1.1e-4 by itself; the
+    # full-size configuration below has to pass raw)
+    _check_parity(name, acc, ref_acc, spp, allow_events=name.startswith("smoke") or name == "veach_c3")
     # tonemapped output of the last iteration: the bulk of the pixels to the last bits, 99 % within 1e-4 (a pixel holding
     # one of the rare flipped samples is off by that sample's radiance / spp)
     dt = np.abs(tone.astype(np.float64) - ref_tone.astype(np.float64))
@@ -228,8 +231,7 @@ def test_full_config_c2_1024spp_matches_reference_cuda():
         for first in range(1, spp + 1, 256):                      # four batched calls, accumulation carried over
             r.render(first, reset=(first == 1), spp=256)
         acc = r.accum()
-    raw = _check_parity("C2 full 1024x1024x1024spp", acc, ref_acc, spp)
-    assert (raw <= TOL).all(), raw                                       # C2 meets the criterion without any exclusion
+    _check_parity("C2 full 1024x1024x1024spp", acc, ref_acc, spp)
 
 
 @pytest.mark.skipif(not refhost.have("libref_cuda.so"), reason="oracle/_ref/libref_cuda.so not present")
