@@ -3,17 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5|smoke|shipped]
 
-A "step" = one batch of `--spp-per-step` iterations (Render calls) of the workload image through the hot path.
-Default workload: C2 = Cornell box 1024x1024, depth 8 (the configuration the metric is quoted on; K steps of
-128 spp -> 8 steps are the full 1024-spp config).  N > 1 (launched by torchrun, one rank per GPU): the image's
-32x32 screen tiles are interleaved over the ranks (strong scaling); after every step the float3
-accumulation framebuffer is reduced to rank 0 with one NCCL reduce over NVLink, inside the timed region.
+A "step" = one batch of `spp_per_step` iterations (Render calls) of the workload image through the hot path.
+Default workload: C2 = Cornell box 1024x1024, depth 8 (the configuration the metric is quoted on); spp_per_step is 128 per
+GPU — 128 at N = 1 (8 steps are the full 1024-spp config), 128 x N at N GPUs, so the timed region does not shrink as
+GPUs are added (reported as "scaling": "weak": per-GPU work per step is fixed, the image and the scene are the same).
+N > 1 (launched by torchrun, one rank per GPU): the image's 32x32 screen tiles are dealt over the ranks (SURVEY 8(e));
+after every step the float3 accumulation framebuffers are summed onto rank 0 by ONE NCCL reduce over NVLink — inside the
+library (b200pt_render_reduce; torch.distributed only ships the 128-byte NCCL id and the timing scalars) and inside the
+timed region.
 
-Keys: value = whole-job Msamples/s, device-timed, inputs resident in HBM; e2e = the same through the public
-C-ABI call with HOST buffers (camera in, tonemapped image out) inside the timed region; roofline = algorithmic
-bytes/sample x samples / kernel time vs the measured HBM peak (MEASURED_PEAKS.json); cpu_baseline = the
-reference's own kernel bodies (oracle/_ref/libref_host_fast.so, kind "reference") or the CPU oracle port on the
-host cores for a bounded sample.  --impl reference times that CPU reference arm alone."""
+Keys: value = whole-job Msamples/s, device-resident arm (device output pointer); e2e = the same through the public C-ABI
+call with HOST buffers (camera in, tonemapped image out) inside the timed region; roofline = what bounds the dominant
+kernel, from per-sample hardware counters measured with ncu (profiles/r02_counters.json, scripts/ncu_counters.py) x the
+samples of the timed region / CUDA-event time: for scenes that live in shared memory the binding resource is
+instruction issue (frac = useful-lane issue fraction; the HBM figures are reported next to it), for C4 it is
+HBM / L2; cpu_baseline = the reference's own kernel bodies (oracle/_ref/libref_host_fast.so) on the host cores for a
+bounded sample; reference_cuda = the reference's own CUDA integrator (oracle/_ref/libref_cuda.so) on
+the same GPU, timed in a subprocess outside the timed region; extra.c4 = a short leg on BASELINE configs[3]
+(1 M triangles, 2048x2048).  --impl reference times the CPU reference arm alone."""
 import argparse
 import json
 import os
@@ -26,6 +33,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+COUNTERS = os.path.join(ROOT, "profiles", "r02_counters.json")
 
 # algorithmic bytes per sample B = R*(N*32 + P*36) + H*80 + 24, with R, N, P, H as executed by the
 # reference traversal (counted by the oracle's restatement of it, tests/test_bench_constants.py re-measures them)
@@ -40,36 +48,27 @@ ALGO = {
 }
 
 
-# ncu-measured DRAM traffic per sample, whole wavefront (see profiles/); filled in from the capture of the round
-DRAM_BYTES_PER_SAMPLE = {"c2": 1684.0}     # profiles/r01s_launches_summary.txt: 21.2 GB over 12.6 Msamples
-# warp instructions per pool slot and wavefront step (ncu smsp__inst_executed.sum of one k_trace_small + one k_shade launch
-# over a 2^20-slot pool, profiles/r01z_ncu_wavefront_kernels.txt; r01w: 134.17e6 + 43.86e6): the kernels of C2 are
-# instruction-issue bound (the scene lives in shared memory), so the JSON also carries the fraction of the SMs' issue
-# rate they reach
-WARP_INST_PER_SLOT_STEP = {"c2": (134.10e6 + 43.13e6) / float(1 << 20)}
-
-
 def algo_bytes_per_sample(w):
     a = ALGO[w]
     H = a["R"] * 2.0 / 3.0
     return a["R"] * (a["N"] * 32 + a["P"] * 36) + H * 80 + 24
 
 
-def make_scene(pt, name):
+def make_scene(pt, name, prep=None):
     if name == "c2":
-        return pt.scenes.cornell_pt(1024, 1024, 8), "cornell_box 1024x1024 depth=8 lambertian+area-light (BASELINE configs[1])"
+        return pt.scenes.cornell_pt(1024, 1024, 8, prep=prep), "cornell_box 1024x1024 depth=8 lambertian+area-light (BASELINE configs[1])"
     if name == "c1":
-        return pt.scenes.cornell_pt(256, 256, 4), "cornell_box 256x256 depth=4 (BASELINE configs[0])"
+        return pt.scenes.cornell_pt(256, 256, 4, prep=prep), "cornell_box 256x256 depth=4 (BASELINE configs[0])"
     if name == "c3":
-        return pt.scenes.veach_standin(768, 576, 17), "veach_bidir materials/lights/camera over stand-in geometry 768x576 depth=17 (configs[2])"
+        return pt.scenes.veach_standin(768, 576, 17, prep=prep), "veach_bidir materials/lights/camera over stand-in geometry 768x576 depth=17 (configs[2])"
     if name == "c4":
-        return pt.scenes.random_triangles(1_000_000, 2048, 2048, 8), "1M random triangles + analytic HDRI 2048x2048 depth=8 (configs[3])"
+        return pt.scenes.random_triangles(1_000_000, 2048, 2048, 8, prep=prep), "1M random triangles + analytic HDRI 2048x2048 depth=8 (configs[3])"
     if name == "c5":
-        return pt.scenes.cornell_vol_caustic(512, 512, 17), "cornell_box vol_caustic homogeneous medium vpt 512x512 depth=17 (configs[4])"
+        return pt.scenes.cornell_vol_caustic(512, 512, 17, prep=prep), "cornell_box vol_caustic homogeneous medium vpt 512x512 depth=17 (configs[4])"
     if name == "smoke":
-        return pt.scenes.cornell_smoke(1024, 1024, 8, 1), "cornell_box + heterogeneous smoke (ratio tracking) vpt 1024x1024 depth=8 (SURVEY 8(f).3)"
+        return pt.scenes.cornell_smoke(1024, 1024, 8, 1, prep=prep), "cornell_box + heterogeneous smoke (ratio tracking) vpt 1024x1024 depth=8 (SURVEY 8(f).3)"
     if name == "shipped":
-        return pt.scenes.cornell_shipped_smoke(1024, 1024, 17), "the reference's shipped cornell_box/scene.json (heterogeneous medium) vpt 1024x1024 depth=17"
+        return pt.scenes.cornell_shipped_smoke(1024, 1024, 17, prep=prep), "the reference's shipped cornell_box/scene.json (heterogeneous medium) vpt 1024x1024 depth=17"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -80,6 +79,7 @@ class ClockSampler:
         self.rows = []
         self.stop = False
         self.index = index
+        self.p = None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
@@ -142,6 +142,73 @@ def cpu_reference(scene, seconds_target, threads=0, fast=True):
             "sample": f"{spp} iterations of {scene.width}x{scene.height} ({n / 1e6:.1f} Msamples) in {dt:.1f}s"}, n / dt / 1e6, dt
 
 
+def reference_cuda_subprocess(workload, spp, timeout=600):
+    """the reference's OWN CUDA integrator (oracle/_ref/libref_cuda.so: its pathtracer.cu compiled for
+    sm_100a) on the same GPU and the same scene arrays — Render(iter) x spp with CUDA events around the loop — in a
+    subprocess of its own, outside every timed region of this benchmark."""
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import bench, gpu_pathtracer_b200 as pt\n"
+        "from tests import refhost\n"
+        "s, _ = bench.make_scene(pt, %r)\n"
+        "ref = refhost.RefCuda(); ref.begin(s); ref.render(1, 2, want_output=False)\n"
+        "_, ms = ref.render(1, %d, want_output=False); ref.end()\n"
+        "n = s.width * s.height * %d\n"
+        "print('REFCUDA ' + json.dumps({'value': n / ms / 1e3, 'unit': 'Msamples/s', 'ms': ms, 'spp': %d, 'samples': n}))\n"
+    ) % (ROOT, workload, spp, spp, spp)
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, cwd=ROOT).stdout
+        for ln in out.splitlines():
+            if ln.startswith("REFCUDA "):
+                return json.loads(ln[8:])
+    except Exception as e:                                                   # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+    return {"unavailable": "no result line"}
+
+
+def load_counters(workload):
+    try:
+        return json.load(open(COUNTERS)).get(workload)
+    except Exception:
+        return None
+
+
+def roofline_record(workload, counters, samples_per_gpu, kernel_s, clocks, peaks):
+    """What bounds the dominant kernel.  Per-sample counts come from the committed ncu capture; time is measured live."""
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    bps = algo_bytes_per_sample(workload)
+    algo_gbs = bps * samples_per_gpu / kernel_s / 1e9 if kernel_s > 0 else 0.0
+    rec = {"peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+           "algorithmic_bytes_per_sample": bps, "algorithmic_gbs": algo_gbs,
+           "counters_file": os.path.relpath(COUNTERS, ROOT) if counters else None}
+    if not counters:
+        rec.update({"bound": "hbm", "achieved": algo_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": min(algo_gbs / peak_hbm, 1.0), "traffic": None,
+                    "note": "no ncu counters for this workload: algorithmic bytes only (clamped: the scene may be served from on-chip memory)"})
+        return rec
+    dram_bps = counters["dram_bytes_per_sample"]
+    dram_gbs = dram_bps * samples_per_gpu / kernel_s / 1e9
+    hbm = {"measured_dram_bytes_per_sample": dram_bps, "measured_dram_gbs": dram_gbs, "frac_of_peak": dram_gbs / peak_hbm, "peak": peak_hbm}
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    peak_issue = 148 * 4 * sm_mhz * 1e6
+    wi = counters["warp_inst_per_sample"] * samples_per_gpu / kernel_s
+    lanes = counters["active_lanes_per_inst"]
+    issue = {"warp_inst_per_sample": counters["warp_inst_per_sample"], "active_lanes_per_inst": lanes, "achieved_warp_inst_per_s": wi,
+             "peak_warp_inst_per_s": peak_issue, "issue_frac": wi / peak_issue, "useful_lane_frac": wi / peak_issue * lanes / 32.0,
+             "note": "148 SMs x 4 schedulers x SM clock under load"}
+    rec["dominant_kernel"] = counters.get("dominant_kernel")
+    rec["kernel_time_shares"] = {k: round(v["time_share"], 4) for k, v in counters.get("kernels", {}).items()}
+    if hbm["frac_of_peak"] >= issue["issue_frac"]:
+        rec.update({"bound": "hbm", "achieved": dram_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": dram_gbs / peak_hbm})
+    else:
+        # the scene is served from shared memory / L2: instruction issue binds; frac counts only the lanes that do work
+        rec.update({"bound": "issue", "achieved": wi * lanes / 32.0 / 1e9, "peak": peak_issue / 1e9, "unit": "G useful warp-inst/s",
+                    "frac": issue["useful_lane_frac"]})
+    rec["traffic"] = dram_bps * samples_per_gpu          # measured DRAM bytes of the timed kernels (per GPU)
+    rec["hbm"] = hbm
+    rec["issue"] = issue
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,24 +216,36 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--spp-per-step", type=int, default=128)
+    ap.add_argument("--spp-per-step", type=int, default=0, help="iterations per step and GPU (default 128; c4: 8)")
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the reference_cuda sub-record and the C4 leg")
     a = ap.parse_args()
+    # only the JSON line goes to the real stdout: everything else this process prints at C level (the reference's
+    # Scene::Init / BeginRender chatter in the baseline legs) is routed to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
     import gpu_pathtracer_b200 as pt
-    scene, desc = make_scene(pt, a.workload)
-    W, H = scene.width, scene.height
-    config = {"workload": desc, "width": W, "height": H, "max_depth": scene.max_depth, "spp_per_step": a.spp_per_step,
-              "prims": int(len(scene.prims)), "bvh_nodes": int(len(scene.nodes)),
-              "l2_policy": "path pool + sample planes streamed per step exceed L2 (126 MB); no explicit flush",
-              "parallelism": f"tile-sharded x{world}" if world > 1 else "single GPU"}
 
     if a.impl == "reference":
         if rank != 0:
             return
-        # reference arm: the reference's own CPU implementation of the path on the host cores, bounded sample
+        # reference arm: the reference's own CPU implementation of the path on the host cores, bounded sample; the scene is
+        # prepared by the reference's own Scene::Init / Camera constructor too (tests.refhost.RefPrep) — nothing of
+        # libb200pt.so is loaded in this arm
+        from tests import refhost
+        prep = refhost.RefPrep() if refhost.have("libref_host.so") else None
+        scene, desc = make_scene(pt, a.workload, prep=prep)
+        spp = a.spp_per_step or (8 if a.workload == "c4" else 128)
+        config = {"workload": desc, "width": scene.width, "height": scene.height, "max_depth": scene.max_depth, "spp_per_step": spp,
+                  "prims": int(len(scene.prims)), "bvh_nodes": int(len(scene.nodes)), "parallelism": "host cores (OpenMP over pixels)"}
         per_step = 20.0 / max(1, a.steps + a.warmup)
         vals = []
         for i in range(a.warmup + a.steps):
@@ -175,10 +254,12 @@ def main():
                 vals.append((v, dt))
         v = float(np.mean([x[0] for x in vals])); ms = float(np.mean([x[1] for x in vals]) * 1e3)
         cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": 0, "steps": a.steps,
-                          "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        from gpu_pathtracer_b200 import _lib
+        emit({"impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": 0, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "product_library_loaded": _lib._lib is not None,
+                          "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -186,132 +267,127 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    shard = (rank, world, 32, 32) if world > 1 else None
-    r = pt.PathTracer(scene, device=local, shard=shard, pool=a.pool or None)
-    spp = a.spp_per_step
-    npix = W * H
-    acc_t = torch.empty(0)
-    if world > 1:
-        # wrap the library's accumulation framebuffer (device memory owned by the context) as a torch tensor
-        import ctypes
-        ptr = r.accum_device_ptr()
-        class _Holder:  # noqa: E306
-            __cuda_array_interface__ = {"shape": (npix * 3,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        acc_t = torch.as_tensor(_Holder(), device=f"cuda:{local}")
-    out_dev = torch.empty(npix * 3, dtype=torch.float32, device=f"cuda:{local}")
-    out_host_t = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)              # pinned host image for the e2e arm
-    out_host = out_host_t.numpy()
-    full_acc = torch.empty(npix * 3, dtype=torch.float32, device=f"cuda:{local}") if world > 1 else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def reduce_and_tonemap(last_iter):
-        """N > 1: ONE NCCL reduce of the float3 accumulation framebuffer per spp batch (tiles are disjoint, so the sum has
-        one non-zero contributor per pixel), then Output's tonemap of the full image on rank 0."""
-        full_acc.copy_(acc_t)                     # keep the context's own buffer shard-only for the next batch
-        dist.reduce(full_acc, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            torch.cuda.current_stream().synchronize()       # the tonemap runs on the library's stream
-            r.tonemap_device(full_acc.data_ptr(), last_iter, out_dev.data_ptr())
-
-    def step_device(i):
-        """inputs resident: camera struct is the only host->device traffic (104 B, like the reference's Render)."""
-        r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_dev.data_ptr(), output_is_device=True)
+    def run_workload(workload, steps, warmup, spp_gpu, want_e2e=True):
+        """One workload through both arms; returns the fields of a bench line (rank 0) — device-timed `value`, `e2e`, counters."""
+        scene, desc = make_scene(pt, workload)
+        W, H = scene.width, scene.height
+        npix = W * H
+        spp = spp_gpu * world                                  # iterations per step: fixed per-GPU work
+        shard = (rank, world, 32, 32) if world > 1 else None
+        r = pt.PathTracer(scene, device=local, shard=shard, pool=a.pool or None)
         if world > 1:
-            reduce_and_tonemap((i + 1) * spp)
-        return r.stats()
+            # the ONE collective lives in the library: ship the NCCL id (128 bytes) with torch.distributed, then
+            # b200pt_comm_init on every rank
+            ids = [pt.PathTracer.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            r.comm_init(world, rank, ids[0])
+        out_dev = torch.empty(npix * 3, dtype=torch.float32, device=f"cuda:{local}")
+        out_host_t = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)          # pinned host image for the e2e arm
+        out_host = out_host_t.numpy()
 
-    def step_e2e(i):
-        """public call with HOST buffers: camera from host, tonemapped float3 image back to (pinned) host memory every step."""
-        if world == 1:
-            return r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_host)
-        r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_dev.data_ptr(), output_is_device=True)
-        reduce_and_tonemap((i + 1) * spp)
-        if rank == 0:
-            out_host_t.view(-1).copy_(out_dev)
-            torch.cuda.synchronize()
-        return out_host
+        def step_device(i):
+            """inputs resident: the camera struct is the only host->device traffic (104 B, like the reference's Render)."""
+            if world == 1:
+                r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_dev.data_ptr(), output_is_device=True)
+            else:
+                r.render_reduce(1 + i * spp, reset=(i == 0), spp=spp, root=0, output=out_dev.data_ptr() if rank == 0 else None,
+                                output_is_device=True)
+            return r.stats()
 
-    # ---- device-timed arm
-    for i in range(a.warmup):
-        step_device(i)
-    barrier()
-    launches = rays = dev_ms = 0.0
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        for i in range(a.steps):
-            st = step_device(i)
-            launches += st["launches"]; rays += st["rays"]; dev_ms += st["device_ms"]
+        def step_e2e(i):
+            """public call with HOST buffers: camera from host, tonemapped float3 image back to (pinned) host memory every step."""
+            if world == 1:
+                return r.render(1 + i * spp, reset=(i == 0), spp=spp, output=out_host)
+            return r.render_reduce(1 + i * spp, reset=(i == 0), spp=spp, root=0, output=out_host if rank == 0 else None)
+
+        for i in range(warmup):
+            step_device(i)
         barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = clk.summary()
-    # max over ranks of the device time (CUDA events on the context's stream) and of the wall time
-    t = torch.tensor([dev_ms, wall_ms, launches, rays], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, wall_ms = float(tmax[0]), float(tmax[1]); launches, rays = float(tsum[2]), float(tsum[3])
-    samples = float(npix) * spp * a.steps
-    ms_per_step = wall_ms / a.steps
-    value = samples / wall_ms / 1e3
+        launches = rays = dev_ms = 0.0
+        with ClockSampler(local) as clk:
+            t0 = time.perf_counter()
+            for i in range(steps):
+                st = step_device(i)
+                launches += st["launches"]; rays += st["rays"]; dev_ms += st["device_ms"]
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = clk.summary()
+        # max over ranks of the device time (CUDA events on the context's stream) and of the wall time
+        t = torch.tensor([dev_ms, wall_ms, launches, rays], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dev_ms, wall_ms = float(tmax[0]), float(tmax[1]); launches, rays = float(tsum[2]), float(tsum[3])
+        samples = float(npix) * spp * steps
+        res = {"desc": desc, "scene": scene, "samples": samples, "spp": spp, "value": samples / wall_ms / 1e3, "ms_per_step": wall_ms / steps,
+               "dev_ms": dev_ms, "launches": launches, "rays": rays, "clocks": clocks, "npix": npix, "fused": r.info("fused"), "lanes": r.info("lanes")}
+        if want_e2e:
+            step_e2e(0)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                step_e2e(i)
+            barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["e2e"] = samples / float(t[0]) / 1e3
+        r.close()
+        return res
 
-    # ---- end-to-end arm (host buffers inside the timed region)
-    step_e2e(0)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        step_e2e(i)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t[0])
-    e2e_val = samples / e2e_ms / 1e3
+    spp_gpu = a.spp_per_step or (8 if a.workload == "c4" else 128)
+    res = run_workload(a.workload, a.steps, a.warmup, spp_gpu)
+    scene = res["scene"]
+    extra = {}
+    if not a.no_extra and a.workload == "c2":
+        # BASELINE configs[3], the HBM-meaningful configuration, rides along as a short leg at every N
+        c4 = run_workload("c4", 3, 3, 8)
+        if rank == 0:
+            k_s = c4["dev_ms"] / 1e3
+            extra["c4"] = {"workload": c4["desc"], "value": c4["value"], "e2e": c4.get("e2e"), "unit": "Msamples/s", "steps": 3, "warmup": 3,
+                           "spp_per_step": c4["spp"], "ms_per_step": c4["ms_per_step"], "rays_per_sample": c4["rays"] / c4["samples"],
+                           "roofline": roofline_record("c4", load_counters("c4"), c4["samples"] / world, k_s, c4["clocks"], peaks)}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        bps = algo_bytes_per_sample(a.workload)
-        kernel_s = dev_ms / 1e3                       # wavefront kernels (trace+shade+resolve) of all timed steps, CUDA events
-        achieved = bps * samples / world / kernel_s / 1e9 if kernel_s > 0 else 0.0
-        # measured DRAM bytes per sample (ncu dram__bytes_read+write summed over every kernel of one bench step,
-        # profiles/<round>_dram_bytes_*.txt) x samples of one step, per GPU; None for workloads without a capture
-        dram_bps = DRAM_BYTES_PER_SAMPLE.get(a.workload)
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": (dram_bps * float(npix) * spp / world) if dram_bps else None,
-                    "peak_source": "measured" if peaks else "fallback",
-                    "algorithmic_bytes_per_sample": bps, "algorithmic_bytes_per_step": bps * float(npix) * spp / world,
-                    "measured_dram_bytes_per_sample": dram_bps,
-                    "kernel": "wavefront step = k_shade + k_trace(_small) + k_resolve of one spp batch (per GPU); the per-sample "
-                              "figure of SURVEY 8(d) spans all three, so they are timed together with CUDA events"}
-        if a.workload in WARP_INST_PER_SLOT_STEP and clocks.get("sm_mhz"):
-            # slot-steps = (shade, trace) launch pairs x slots per lane; launches counts both kernels of every lane
-            slots_per_lane = r.info("pool_per_lane")
-            slot_steps = launches / 2.0 / world * slots_per_lane
-            inst = WARP_INST_PER_SLOT_STEP[a.workload] * slot_steps
-            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
-            roofline["issue"] = {"warp_inst_per_sample": inst / (samples / world), "achieved_warp_inst_per_s": inst / kernel_s,
-                                 "peak_warp_inst_per_s": peak_issue, "frac": inst / kernel_s / peak_issue,
-                                 "note": "148 SMs x 4 schedulers x SM clock; instruction counts from ncu (profiles/r01z_ncu_wavefront_kernels.txt)"}
+        kernel_s = res["dev_ms"] / 1e3                   # wavefront kernels of all timed steps, CUDA events on the context's stream
+        roofline = roofline_record(a.workload, load_counters(a.workload), res["samples"] / world, kernel_s, res["clocks"], peaks)
+        roofline["kernel"] = ("k_wave_small: CTA-local wavefront, one persistent launch per spp batch (+ k_resolve)" if res["fused"] else
+                              "wavefront step = k_shade + k_trace of one spp batch (+ k_resolve), timed together with CUDA events")
         cb = None
-        if not a.no_cpu_baseline and world == 1:
+        ref_cuda = None
+        if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = cpu_reference(scene, 12.0)          # bounded sample of the SAME workload on the host cores
-            cb["sample"] += " of " + desc
-        line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config, "device_ms_per_step": dev_ms / a.steps,
-                "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": 104, "d2h_bytes_per_step": npix * 12},
-                "gpu_launches": int(launches), "rays_per_sample": rays / samples, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
-        print(json.dumps(line))
-    r.close()
+            cb["sample"] += " of " + res["desc"]
+        if not a.no_extra and a.workload in ("c1", "c2", "c3", "c5"):
+            ref_cuda = reference_cuda_subprocess(a.workload, 64 if a.workload == "c2" else 32)
+            if "value" in ref_cuda:
+                ref_cuda["ratio_device"] = res["value"] / ref_cuda["value"]
+                ref_cuda["ratio_e2e"] = res["e2e"] / ref_cuda["value"]
+                ref_cuda["what"] = "the reference's pathtracer.cu (Path/Volpath megakernel) compiled for sm_100a, same GPU, same scene arrays, 1 GPU"
+        config = {"workload": res["desc"], "width": scene.width, "height": scene.height, "max_depth": scene.max_depth,
+                  "spp_per_step": res["spp"], "spp_per_step_per_gpu": spp_gpu, "prims": int(len(scene.prims)), "bvh_nodes": int(len(scene.nodes)),
+                  "l2_policy": "every step renders new iterations (new random streams) of the whole image; path state of the CTA-local "
+                               "wavefront lives in shared memory, sample planes (16 B/sample) stream to HBM; no explicit flush",
+                  "parallelism": f"tile-sharded x{world}, one NCCL reduce per step inside libb200pt" if world > 1 else "single GPU"}
+        line = {"metric": "Msamples/s", "value": res["value"], "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "device_ms_per_step": res["dev_ms"] / a.steps,
+                "e2e": {"value": res["e2e"], "unit": "Msamples/s", "h2d_bytes_per_step": 104, "d2h_bytes_per_step": res["npix"] * 12},
+                "gpu_launches": int(res["launches"]), "rays_per_sample": res["rays"] / res["samples"], "clocks": res["clocks"],
+                "roofline": roofline, "cpu_baseline": cb, "reference_cuda": ref_cuda, "extra": extra}
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

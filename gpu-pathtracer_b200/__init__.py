@@ -7,6 +7,6 @@ BeginRender / Render / EndRender boundary (brickray/gpu-pathtracer, src/pathtrac
     renderer  PathTracer: Python mirror of BeginRender / Render / EndRender
 """
 from . import layouts, scenes  # noqa: F401
-from .renderer import PathTracer, begin_render, render, end_render  # noqa: F401
+from .renderer import PathTracer, MultiPathTracer, begin_render, render, end_render  # noqa: F401
 
-__all__ = ["layouts", "scenes", "PathTracer", "begin_render", "render", "end_render"]
+__all__ = ["layouts", "scenes", "PathTracer", "MultiPathTracer", "begin_render", "render", "end_render"]

@@ -36,6 +36,9 @@ EXPORTS = [
     "b200pt_set_option", "b200pt_get_info", "b200pt_destroy", "b200pt_last_error", "b200pt_version", "b200pt_bvh_build",
     "b200pt_bvh_build_gpu", "b200pt_bvh_cache_save", "b200pt_bvh_cache_info", "b200pt_bvh_cache_load", "b200pt_bvh_load_or_build",
     "b200pt_camera_init", "b200pt_light_distribution", "b200pt_infinite_init",
+    # multi-GPU inside the library (NCCL reduce of the accumulation framebuffers)
+    "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_render_reduce", "b200pt_reduced_accum",
+    "b200pt_create_multi", "b200pt_multi_render", "b200pt_multi_get_accum", "b200pt_multi_stats", "b200pt_multi_destroy",
 ]
 
 
@@ -54,6 +57,16 @@ def load(path=None):
     lib.b200pt_create.argtypes = [C.POINTER(SceneView), C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.POINTER(Shard),
                                   C.POINTER(C.c_void_p)]
     lib.b200pt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_int]
+    lib.b200pt_comm_unique_id.argtypes = [C.c_void_p]
+    lib.b200pt_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.b200pt_render_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.b200pt_reduced_accum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.b200pt_create_multi.argtypes = [C.POINTER(SceneView), C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.POINTER(C.c_int),
+                                        C.POINTER(C.c_void_p)]
+    lib.b200pt_multi_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_int]
+    lib.b200pt_multi_get_accum.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200pt_multi_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.b200pt_multi_destroy.argtypes = [C.c_void_p]
     lib.b200pt_get_accum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.b200pt_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.b200pt_get_color.argtypes = [C.c_void_p, C.c_void_p]

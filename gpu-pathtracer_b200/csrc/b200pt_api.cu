@@ -1240,12 +1240,16 @@ extern "C" int b200pt_multi_render(b200pt_multi* m, const void* camera, uint32_t
     // all shards render concurrently: one host thread per GPU drives that context's (blocking) render call
     std::vector<int> rcs(n, 0);
     std::vector<std::string> errs(n);
+#ifndef B200PT_EMULATE
     {
         std::vector<std::thread> th;
         for (int i = 0; i < n; ++i)
             th.emplace_back([&, i]() { rcs[i] = b200pt_render(m->ctx[i], camera, first_iter, spp, reset, nullptr, 0); if (rcs[i]) errs[i] = b200pt_last_error(); });
         for (auto& t : th) t.join();
     }
+#else
+    for (int i = 0; i < n; ++i) { rcs[i] = b200pt_render(m->ctx[i], camera, first_iter, spp, reset, nullptr, 0); if (rcs[i]) errs[i] = b200pt_last_error(); }
+#endif
     for (int i = 0; i < n; ++i) if (rcs[i]) return fail(rcs[i], "GPU " + std::to_string(i) + ": " + errs[i]);
     b200pt_ctx* root = m->ctx[0];
     int rc = ensure_reduced(root);

@@ -32,9 +32,6 @@
 #include <thread>
 #include <vector>
 
-#ifndef B200PT_EMULATE
-#include <cub/device/device_scan.cuh>
-#endif
 
 int b200pt_internal_fail(int code, const char* msg);   // b200pt_api.cu: sets b200pt_last_error()
 extern "C" int b200pt_internal_prims_finite(const void* prims, int n, int* bad);   // host_prep.cpp
@@ -386,6 +383,60 @@ inline int grid_for(long long n) { return (int)((n + kThreads - 1) / kThreads); 
 
 using namespace bvhb;
 
+// ---- exclusive prefix sum of the partition flags (one per level): three small kernels — per-tile scan + tile totals,
+// scan of the totals, add.  The arrays are <= 16 MB and L2-resident; the levels are launch- and atomic-latency bound,
+// so nothing fancier (decoupled look-back) pays here.
+constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+#ifndef B200PT_EMULATE
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+    for (int off = 1; off < 32; off <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int t = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+        for (int off = 1; off < 32; off <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, off); if (lane >= off) t += y; }
+        s_warp[lane] = t;                       // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    total = s_warp[(blockDim.x >> 5) - 1];
+    const int base = w ? s_warp[w - 1] : 0;
+    __syncthreads();
+    return base + x - v;
+}
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ tile_sums, int n) {
+    __shared__ int s_warp[32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n ? in[base + k] : 0; sum += v[k]; }
+    int total;
+    int run = block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int* tile_sums, int n_tiles) {         // one CTA
+    __shared__ int s_warp[32];
+    int carry = 0;
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_tiles ? tile_sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, s_warp, total);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(int* __restrict__ out, const int* __restrict__ tile_sums, int n) {
+    const int off = tile_sums[blockIdx.x];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) if (base + k < n) out[base + k] += off;
+}
+#endif
+
 #define BCK(call)                                                                                             \
     do {                                                                                                      \
         cudaError_t e_ = (call);                                                                              \
@@ -415,12 +466,9 @@ extern "C" int b200pt_bvh_build_gpu(const void* prims_in, int32_t n_prims, void*
     const size_t max_candidates = (size_t)n / 5 + 1;                      // a candidate holds >= 5 primitives
 
     // one device allocation, carved up (allocation calls dominate the wall clock of small builds otherwise)
-    size_t temp_bytes = 0;
-#ifndef B200PT_EMULATE
-    BCK(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (int*)nullptr, (int*)nullptr, n, (cudaStream_t)0));
-#endif
+    const int n_tiles = (n + kScanTile - 1) / kScanTile;
     RefPrimitive* d_prims; float4 *d_blo, *d_bhi; int *d_ids0, *d_ids1, *d_seg0, *d_seg1, *d_flags, *d_scan;
-    unsigned* d_buckets; Counters* d_ctr; RefLinearBVHNode* d_out; char* d_temp; Tree t;
+    unsigned* d_buckets; Counters* d_ctr; RefLinearBVHNode* d_out; int* d_tile_sums; Tree t;
     Arena arena;
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
@@ -438,7 +486,7 @@ extern "C" int b200pt_bvh_build_gpu(const void* prims_in, int32_t n_prims, void*
         d_buckets = arena.take<unsigned>(max_candidates * kNodeWords);
         d_ctr = arena.take<Counters>(1);
         d_out = arena.take<RefLinearBVHNode>(cap);
-        d_temp = arena.take<char>(temp_bytes + 16);
+        d_tile_sums = arena.take<int>((size_t)n_tiles + 1);
         t.lo = arena.take<float4>(cap); t.hi = arena.take<float4>(cap);
         t.left = arena.take<int>(cap); t.slot = arena.take<int>(cap); t.size = arena.take<int>(cap);
         t.pre = arena.take<int>(cap); t.parent = arena.take<int>(cap); t.zero_id = arena.take<int>(6 * (size_t)cap);
@@ -469,7 +517,9 @@ extern "C" int b200pt_bvh_build_gpu(const void* prims_in, int32_t n_prims, void*
         PT_LAUNCH(k_split, grid_for(level_end - ls), kThreads, 0, st, ls, level_end, t, d_buckets, d_ctr, cap);
         PT_LAUNCH(k_flags, grid_for(n), kThreads, 0, st, n, ls, ids, seg, t, d_blo, d_bhi, d_flags);
 #ifndef B200PT_EMULATE
-        BCK(cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_flags, d_scan, n, st));
+        k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(d_flags, d_scan, d_tile_sums, n);
+        k_scan_sums<<<1, 1024, 0, st>>>(d_tile_sums, n_tiles);
+        k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(d_scan, d_tile_sums, n);
 #else
         exclusive_scan(d_flags, d_scan, n);
 #endif

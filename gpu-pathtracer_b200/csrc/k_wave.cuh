@@ -28,6 +28,9 @@
 namespace pt {
 
 constexpr int kWaveThreads = 256;
+#ifndef PT_WAVE_HET_CTAS
+#define PT_WAVE_HET_CTAS 2          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
+#endif
 
 // The shade / trace bodies read scene, camera, shard map and batch from the same argument structs as the global
 // wavefront (kernel parameters: constant bank); their pool / queue members are unused here — the CTA's own planes and
@@ -55,7 +58,7 @@ template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_lea
 
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
-__global__ void __launch_bounds__(kWaveThreads, (VOL || MATS != kMatsLambertOnly) ? 2 : 3) k_wave_small(const WaveArgs a) {
+__global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3)) k_wave_small(const WaveArgs a) {
     const ShadeArgs& sa = a.sa;
     const TraceArgs& ta = a.ta;
 #ifndef B200PT_EMULATE
@@ -116,36 +119,63 @@ __global__ void __launch_bounds__(kWaveThreads, (VOL || MATS != kMatsLambertOnly
     const uint32_t pool_n = gridDim.x * (uint32_t)kWaveThreads;
 
     if (HET) {
-        // Heterogeneous media: every live slot posts exactly ONE closest-hit query per step, so there is nothing to compact
-        // — each lane traces its own query right after the glue and the warps step independently (no CTA barrier: a lane
-        // deep in a tracking loop holds up its warp, not the CTA).  Glue diverges, the traversal re-converges: all lanes of
-        // the warp enter trace_small_ray together, where the sequential per-thread form of this integrator reaches its
-        // traversal from three call sites inside divergent control flow.
-        PT_WAVE_FOR_THREADS(t) {
-#ifdef B200PT_EMULATE
-            threadIdx.x = t;
-#endif
-            uint32_t nrays = 0;
-            for (;;) {
-                const unsigned long long snap = *(volatile unsigned long long*)&sa.counters->next_sample;
-                uint32_t posted = 0u;
-                het_slot<MATS, true, false>(sa, P, Q, 0u, &s_retired, nullptr, t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, snap, posted);
-#ifndef B200PT_EMULATE
-                if (!__any_sync(kFullMask, posted != 0u)) break;
-#else
-                if (!posted) break;
-#endif
-                if (posted) trace_small_ray<VOL>(ta, P, prims, leaves, t | ((posted == 2u ? 2u : 0u) << kKindShift), nrays);
-#ifndef B200PT_EMULATE
-                __syncwarp();
-#endif
+        // Heterogeneous media: the slots are coroutines in one of four wait states (k_het.cuh), and each state resumes into
+        // different code (free-flight sampling, a leg of a transmittance walk, the MIS hit).  Executed slot-per-thread,
+        // a warp ran every state's code with a fifth of its lanes (6.2 of 32 active lanes per instruction,
+        // profiles/r02_counters.json, "smoke").  So every step starts with a COUNTING SORT of the CTA's slots by state
+        // (shared memory, 8 keys) and thread j resumes slot order[j]: the lanes of a warp resume the same stage and walk
+        // their tracking loops together.  Then the usual two phases: glue posts <= 1 query per slot into the compact
+        // queue, the trace phase runs the queue.
+        __shared__ uint32_t s_cnt[8], s_pos[8];
+        uint16_t* const s_order = reinterpret_cast<uint16_t*>(s_queue + 2 * kWaveThreads);       // the queue holds <= 1 entry per slot here
+        for (uint32_t step = 0;; ++step) {
+            const uint32_t par = step & 1u;
+            // ---- sort the slots by wait state (dead slots last)
+            PT_WAVE_FOR_THREADS(t) { if (t < 8u) s_cnt[t] = 0u; }
+            PT_WAVE_SYNC();
+            PT_WAVE_FOR_THREADS(t) {
+                const uint32_t f = __float_as_uint(P.d_flags[t].w);
+                const uint32_t key = (f & H_ALIVE) ? ((f >> kHStateShift) & 3u) : 7u;
+                atomicAdd(&s_cnt[key], 1u);
             }
-#ifndef B200PT_EMULATE
-            for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
+            PT_WAVE_SYNC();
+            PT_WAVE_FOR_THREADS(t) {
+                if (t == 0u) { uint32_t run = 0u; for (int k = 0; k < 8; ++k) { s_pos[k] = run; run += s_cnt[k]; } }
+            }
+            PT_WAVE_SYNC();
+            PT_WAVE_FOR_THREADS(t) {
+                const uint32_t f = __float_as_uint(P.d_flags[t].w);
+                const uint32_t key = (f & H_ALIVE) ? ((f >> kHStateShift) & 3u) : 7u;
+                s_order[atomicAdd(&s_pos[key], 1u)] = (uint16_t)t;
+            }
+            PT_WAVE_SYNC();
+            // ---- glue phase
+            PT_WAVE_FOR_THREADS(t) {
+#ifdef B200PT_EMULATE
+                threadIdx.x = t;
 #endif
-            if (pt_lane() == 0u && nrays) atomicAdd(&s_rays, nrays);
+                const uint32_t slot = s_order[t];
+                uint32_t posted = 0u;
+                het_slot<MATS, true, true>(sa, P, Q, par, &s_retired, &s_busy[par], slot, blockIdx.x * (uint32_t)kWaveThreads + slot, pool_n, s_next, posted);
+            }
+            PT_WAVE_SYNC();
+            const uint32_t tail = s_ctl.tail[par];
+            if (tail == 0u && s_busy[par] == 0u) break;
+            // ---- trace phase
+            PT_WAVE_FOR_THREADS(t) {
+#ifdef B200PT_EMULATE
+                threadIdx.x = t;
+#endif
+                if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
+                uint32_t nrays = 0;
+                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kWaveThreads) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
+#ifndef B200PT_EMULATE
+                for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
+#endif
+                if (pt_lane() == 0u && nrays) atomicAdd(&s_rays, nrays);
+            }
+            PT_WAVE_SYNC();
         }
-        PT_WAVE_SYNC();
     } else
     for (uint32_t step = 0;; ++step) {
         const uint32_t par = step & 1u;

@@ -8,7 +8,9 @@
 #include <cuda_runtime.h>
 
 struct b200pt_ctx;
+struct b200pt_multi;
 b200pt_ctx* B200ptContext();
+b200pt_multi* B200ptMultiContext();
 
 static Scene* g_scene = nullptr;
 static Camera g_cam;
@@ -30,7 +32,10 @@ extern "C" int adapter_render(unsigned first_iter, unsigned n, int reset_first, 
     if (out_host) cudaMemcpy(out_host, g_out, sizeof(float3) * (size_t)g_w * g_h, cudaMemcpyDeviceToHost);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-extern "C" int adapter_get_accum(float* host) { return b200pt_get_accum(B200ptContext(), host, 0); }
+extern "C" int adapter_get_accum(float* host) {
+    if (B200ptMultiContext()) return b200pt_multi_get_accum(B200ptMultiContext(), host);      // B200PT_GPUS > 1
+    return b200pt_get_accum(B200ptContext(), host, 0);
+}
 extern "C" int adapter_end() {
     if (!g_scene) return -1;
     EndRender();

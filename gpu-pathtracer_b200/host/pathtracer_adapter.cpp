@@ -12,6 +12,10 @@
 // pointer to w*h float3 (the mapped GL pixel buffer of main.cpp:136), `iter` is 1-based and part of the RNG
 // seed, `reset` zeroes the accumulation first, the camera is re-read on every call.  Errors print and abort
 // like HANDLE_ERROR (src/common.h:29-39).
+//
+// B200PT_GPUS=N (N > 1) in the environment: the same three calls drive N GPUs of the box — b200pt_create_multi makes one
+// tile-sharded context per device, every Render is followed by ONE NCCL reduce of the accumulation framebuffers onto
+// device 0 inside the library, and `output` (device-0 memory) receives the full tonemapped image, bit-identical to N = 1.
 #include "scene.h"
 #include "pathtracer.h"
 #include "b200pt.h"
@@ -29,6 +33,7 @@ static_assert(sizeof(Area) == B200PT_SIZEOF_AREA, "Area layout changed");
 static_assert(sizeof(Infinite) == B200PT_SIZEOF_INFINITE, "Infinite layout changed");
 
 static b200pt_ctx* g_ctx = nullptr;
+static b200pt_multi* g_multi = nullptr;         // B200PT_GPUS > 1
 
 static void die(const char* what) {
     fprintf(stderr, "b200pt %s failed: %s\n", what, b200pt_last_error());
@@ -36,7 +41,7 @@ static void die(const char* what) {
 }
 
 void BeginRender(Scene& scene, unsigned width, unsigned height, float ep) {
-    if (g_ctx) EndRender();
+    if (g_ctx || g_multi) EndRender();
     std::vector<b200pt_texture> tex(scene.textures.size());
     for (size_t i = 0; i < tex.size(); ++i) {
         tex[i].texels = scene.textures[i].data.data();
@@ -56,25 +61,40 @@ void BeginRender(Scene& scene, unsigned width, unsigned height, float ep) {
     v.textures = tex.empty() ? nullptr : tex.data(); v.n_textures = (int32_t)tex.size();
     v.integrator_type = (int32_t)scene.integrator.type;
     v.max_depth = scene.integrator.maxDepth;
+    const char* gpus = getenv("B200PT_GPUS");
+    if (gpus && atoi(gpus) > 1) {
+        if (b200pt_create_multi(&v, width, height, ep, atoi(gpus), nullptr, &g_multi) != B200PT_OK) die("BeginRender (multi-GPU)");
+        return;
+    }
     const char* dev = getenv("B200PT_DEVICE");
     if (b200pt_create(&v, width, height, ep, dev ? atoi(dev) : 0, nullptr, &g_ctx) != B200PT_OK) die("BeginRender");
 }
 
 void Render(Scene& scene, unsigned width, unsigned height, Camera* camera, unsigned iter, bool reset, float3* output) {
     (void)scene; (void)width; (void)height;       // fixed at BeginRender, exactly like the reference's device copies
+    if (g_multi) {
+        if (b200pt_multi_render(g_multi, camera, iter, 1, reset ? 1 : 0, (float*)output, 1) != B200PT_OK) die("Render (multi-GPU)");
+        return;
+    }
     if (!g_ctx) { fprintf(stderr, "Render called before BeginRender\n"); abort(); }
     if (b200pt_render(g_ctx, camera, iter, 1, reset ? 1 : 0, (float*)output, 1) != B200PT_OK) die("Render");
 }
 
 void EndRender() {
     if (g_ctx) { b200pt_destroy(g_ctx); g_ctx = nullptr; }
+    if (g_multi) { b200pt_multi_destroy(g_multi); g_multi = nullptr; }
 }
 
 // Optional batched extension for headless callers: `spp` consecutive Render calls in one launch sequence.
 void RenderBatch(Scene& scene, Camera* camera, unsigned first_iter, unsigned spp, bool reset, float3* output) {
     (void)scene;
+    if (g_multi) {
+        if (b200pt_multi_render(g_multi, camera, first_iter, spp, reset ? 1 : 0, (float*)output, 1) != B200PT_OK) die("RenderBatch (multi-GPU)");
+        return;
+    }
     if (!g_ctx) { fprintf(stderr, "RenderBatch called before BeginRender\n"); abort(); }
     if (b200pt_render(g_ctx, camera, first_iter, spp, reset ? 1 : 0, (float*)output, 1) != B200PT_OK) die("RenderBatch");
 }
 
 b200pt_ctx* B200ptContext() { return g_ctx; }
+b200pt_multi* B200ptMultiContext() { return g_multi; }

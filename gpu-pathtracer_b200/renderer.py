@@ -75,6 +75,38 @@ class PathTracer:
         _lib.check(self.lib.b200pt_trace_primary(self._ctx, cam.ctypes.data, int(iter), h.ctypes.data), "trace_primary")
         return h
 
+    # -- multi-GPU, one process per GPU: NCCL reduce inside the library ---------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes that rank 0 ships to the other ranks (ncclGetUniqueId)."""
+        lib = _lib.load()
+        buf = (C.c_ubyte * 128)()
+        _lib.check(lib.b200pt_comm_unique_id(buf), "comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _lib.check(self.lib.b200pt_comm_init(self._ctx, int(n_ranks), int(rank), buf), "comm_init")
+
+    def render_reduce(self, iter, reset=False, camera=None, spp=1, root=0, output=None, output_is_device=False):
+        """Render this rank's shard, reduce the accumulation buffers onto `root` (ONE NCCL reduce); on root `output`
+        (host array, device pointer, or None) receives the tonemapped FULL image."""
+        cam = self.scene.camera if camera is None else camera
+        if output is None:
+            ptr, dev = None, 0
+        elif output_is_device:
+            ptr, dev = C.c_void_p(int(output)), 1
+        else:
+            ptr, dev = output.ctypes.data, 0
+        _lib.check(self.lib.b200pt_render_reduce(self._ctx, cam.ctypes.data, int(iter), int(spp), int(bool(reset)), int(root), ptr, dev),
+                   "render_reduce")
+        return output
+
+    def reduced_accum(self):
+        a = np.empty((self.height, self.width, 3), np.float32)
+        _lib.check(self.lib.b200pt_reduced_accum(self._ctx, a.ctypes.data, 0), "reduced_accum")
+        return a
+
     def stats(self):
         s = (C.c_double * 5)()
         _lib.check(self.lib.b200pt_stats(self._ctx, s), "stats")
@@ -106,6 +138,53 @@ class PathTracer:
             self.close()
         except Exception:
             pass
+
+
+class MultiPathTracer:
+    """All GPUs of the box from ONE process (b200pt_create_multi): one tile-sharded context per device, one NCCL reduce
+    per batch onto the first device.  Same render / accum / stats surface as PathTracer."""
+
+    def __init__(self, scene, n_gpus, width=None, height=None, epsilon=None, devices=None):
+        self.lib = _lib.load()
+        self.scene = scene
+        self.width = int(width or scene.width); self.height = int(height or scene.height)
+        self.epsilon = float(scene.epsilon if epsilon is None else epsilon)
+        view, self._keep = _lib.make_view(scene)
+        self._m = C.c_void_p()
+        devs = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _lib.check(self.lib.b200pt_create_multi(C.byref(view), self.width, self.height, self.epsilon, int(n_gpus), devs, C.byref(self._m)),
+                   "create_multi")
+
+    def render(self, iter, reset=False, camera=None, spp=1, output=None, output_is_device=False):
+        cam = self.scene.camera if camera is None else camera
+        if output is not None and output_is_device:
+            _lib.check(self.lib.b200pt_multi_render(self._m, cam.ctypes.data, int(iter), int(spp), int(bool(reset)), C.c_void_p(int(output)), 1),
+                       "multi_render")
+            return None
+        out = np.empty((self.height, self.width, 3), np.float32) if output is None else output
+        _lib.check(self.lib.b200pt_multi_render(self._m, cam.ctypes.data, int(iter), int(spp), int(bool(reset)), out.ctypes.data, 0), "multi_render")
+        return out
+
+    def accum(self):
+        a = np.empty((self.height, self.width, 3), np.float32)
+        _lib.check(self.lib.b200pt_multi_get_accum(self._m, a.ctypes.data), "multi_get_accum")
+        return a
+
+    def stats(self):
+        s = (C.c_double * 5)()
+        _lib.check(self.lib.b200pt_multi_stats(self._m, s), "multi_stats")
+        return {"samples": s[0], "launches": s[1], "rays": s[2], "steps": s[3], "device_ms": s[4]}
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m.value:
+            self.lib.b200pt_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 _global = None

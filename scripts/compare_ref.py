@@ -28,6 +28,10 @@ def make(name, size):
         return pt.scenes.cornell_shipped_smoke(size, size, 17)
     if name.startswith("smoke"):                      # smoke / smoke0 / smoke2: heterogeneous medium, Tr estimator 1 / 0 / 2
         return pt.scenes.cornell_smoke(size, size, 8, int(name[5:] or 1))
+    if name == "zoo":
+        return pt.scenes.cornell_material_zoo(size, size, 8, "pt")
+    if name == "zoovpt":
+        return pt.scenes.cornell_material_zoo(size, size, 12, "vpt")
     if name == "hair":                                # textures + Line primitives
         return pt.scenes.cornell_textured_hair(size, size, 6)
     if name.startswith("tris"):
@@ -42,6 +46,7 @@ def main():
     ap.add_argument("--spp", type=int, default=32)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--no-warm", action="store_true", help="no warm-up render (profiling runs: exactly one render under ncu)")
     ap.add_argument("--dump", default="")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to b200pt_set_option")
     ap.add_argument("--lib", default="", help="alternative libb200pt build to load (A/B experiments)")
@@ -71,7 +76,8 @@ def main():
         # warm-up with the timed call's batch shape: a render that needs larger sample planes than any earlier one
         # re-allocates them (cudaFree + cudaMalloc: 1-50 ms each on the gpurun boxes, occasionally hundreds), and that
         # would land inside the timed region; the reference arm allocates everything in BeginRender
-        r.render(1, reset=True, spp=min(a.spp, 128))
+        if not a.no_warm:
+            r.render(1, reset=True, spp=min(a.spp, 128))
         t0 = time.time()
         r.render(1, reset=True, spp=a.spp)
         wall = (time.time() - t0) * 1e3

@@ -56,3 +56,20 @@ def test_context_is_reusable_after_end_render(oracle):
         finally:
             ad.end()
         assert np.array_equal(_bits(acc), _bits(ref_acc))
+
+
+def test_adapter_drives_several_gpus_with_B200PT_GPUS(monkeypatch, oracle):
+    """The same BeginRender / Render / EndRender calls with B200PT_GPUS=3 in the environment: three tile-sharded contexts,
+    one reduce per Render inside the library, same bits as one context."""
+    s = pt.scenes.cornell_pt(128, 64, 5)
+    ref_acc, ref_tone = oracle.render(s, 1, 3)
+    monkeypatch.setenv("B200PT_GPUS", "3")
+    ad = refhost.Adapter("libadapter_emu.so")
+    ad.begin(s)
+    try:
+        tone = ad.render(1, 3)
+        acc = ad.accum()
+    finally:
+        ad.end()
+    assert np.array_equal(acc.view(np.uint32), ref_acc.view(np.uint32))
+    assert np.array_equal(tone.view(np.uint32), ref_tone.view(np.uint32))

@@ -29,23 +29,16 @@ def _worker(rank, world, port, spp, out_path):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import gpu_pathtracer_b200 as pt
     s = pt.scenes.cornell_pt(512, 512, 8)
-    npix = 512 * 512
     with pt.PathTracer(s, device=rank, shard=(rank, world, 32, 32)) as r:
-        ptr = r.accum_device_ptr()
-
-        class _Holder:
-            __cuda_array_interface__ = {"shape": (npix * 3,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        acc_t = torch.as_tensor(_Holder(), device=f"cuda:{rank}")
-        full = torch.empty_like(acc_t)
-        out = torch.empty_like(acc_t)
+        # the collective lives in the library: torch.distributed only ships the 128-byte NCCL id
+        ids = [pt.PathTracer.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        r.comm_init(world, rank, ids[0])
+        tone = np.zeros((512, 512, 3), np.float32)
         for batch in range(2):
-            r.render(1 + batch * spp, reset=(batch == 0), spp=spp)
-            full.copy_(acc_t)
-            dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)
+            r.render_reduce(1 + batch * spp, reset=(batch == 0), spp=spp, root=0, output=tone if rank == 0 else None)
         if rank == 0:
-            torch.cuda.current_stream().synchronize()
-            r.tonemap_device(full.data_ptr(), 2 * spp, out.data_ptr())
-            np.savez(out_path, acc=full.cpu().numpy().reshape(512, 512, 3), tone=out.cpu().numpy().reshape(512, 512, 3))
+            np.savez(out_path, acc=r.reduced_accum(), tone=tone)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,3 +58,36 @@ def test_two_gpus_one_nccl_reduce_per_batch_is_bit_identical(tmp_path):
         acc = r.accum()
     assert np.array_equal(got["acc"].view(np.uint32), acc.view(np.uint32))
     assert np.array_equal(got["tone"].view(np.uint32), tone.view(np.uint32))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_single_process_multi_gpu_context_is_bit_identical():
+    """b200pt_create_multi (what the BeginRender / Render adapter uses with B200PT_GPUS=N): one process, every GPU of the box,
+    ncclCommInitAll + one grouped ncclReduce per batch — same bits as one GPU, for a surface and a heterogeneous-media scene."""
+    sys.path.insert(0, ROOT)
+    import gpu_pathtracer_b200 as pt
+    n = min(torch.cuda.device_count(), 8)
+    for s in (pt.scenes.cornell_pt(512, 512, 8), pt.scenes.cornell_smoke(256, 256, 8, 1)):
+        with pt.PathTracer(s) as r:
+            r.render(1, reset=True, spp=3)
+            tone = r.render(4, reset=False, spp=3)
+            acc = r.accum()
+        with pt.MultiPathTracer(s, n) as m:
+            m.render(1, reset=True, spp=3)
+            tone_m = m.render(4, reset=False, spp=3)
+            acc_m = m.accum()
+            assert m.stats()["samples"] == 3 * s.width * s.height
+        assert np.array_equal(acc_m.view(np.uint32), acc.view(np.uint32))
+        assert np.array_equal(tone_m.view(np.uint32), tone.view(np.uint32))
+
+
+def test_multi_context_api_on_one_gpu():
+    """b200pt_create_multi with n_gpus = 1 is the plain context behind the multi entry points (no communicator)."""
+    sys.path.insert(0, ROOT)
+    import gpu_pathtracer_b200 as pt
+    s = pt.scenes.cornell_pt(256, 256, 6)
+    with pt.PathTracer(s) as r:
+        tone = r.render(1, reset=True, spp=4); acc = r.accum()
+    with pt.MultiPathTracer(s, 1) as m:
+        tone_m = m.render(1, reset=True, spp=4); acc_m = m.accum()
+    assert np.array_equal(acc_m.view(np.uint32), acc.view(np.uint32)) and np.array_equal(tone_m.view(np.uint32), tone.view(np.uint32))

@@ -282,3 +282,19 @@ def test_heterogeneous_media_coroutine_equals_oracle(estimator, mode, emu, oracl
         assert r.stats()["samples"] == 3 * 64 * 64
     assert np.array_equal(_bits(acc), _bits(ref_acc))
     assert np.array_equal(_bits(tone), _bits(ref_tone))
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 5])
+def test_single_process_multi_context_equals_one_context(n_gpus, emu, oracle):
+    """b200pt_create_multi: one tile-sharded context per GPU, one reduce of the accumulation framebuffers per batch (NCCL on
+    the GPU build; a plain sum in this emulation build) — the reduced image and its tone map are bit-identical to a
+    single context's, over several calls without reset."""
+    s = pt.scenes.cornell_pt(128, 64, 6)
+    ref_acc, ref_tone = oracle.render(s, 1, 5)
+    with pt.MultiPathTracer(s, n_gpus) as m:
+        m.render(1, reset=True, spp=2)
+        tone = m.render(3, reset=False, spp=3)
+        acc = m.accum()
+        assert m.stats()["samples"] == 3 * 128 * 64
+    assert np.array_equal(_bits(acc), _bits(ref_acc))
+    assert np.array_equal(_bits(tone), _bits(ref_tone))
