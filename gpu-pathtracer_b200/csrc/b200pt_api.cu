@@ -468,8 +468,9 @@ template <class F> static void with_wave_kernel(const b200pt_ctx* c, F&& f) {
         else f(k_wave_small<false, kMatsAll, false>, false);
     }
 }
+static int wave_threads(const b200pt_ctx* c) { return c->het ? WaveThreads<true>::value : WaveThreads<false>::value; }
 static size_t wave_smem(const b200pt_ctx* c) {
-    return c->vol ? wave_smem_bytes<true>(c->small_prim_bytes, c->n_leaves) : wave_smem_bytes<false>(c->small_prim_bytes, c->n_leaves);
+    return c->vol ? wave_smem_bytes<true>(c->small_prim_bytes, c->n_leaves, wave_threads(c)) : wave_smem_bytes<false>(c->small_prim_bytes, c->n_leaves, wave_threads(c));
 }
 static void free_pool(Lane& L) {
     for (void* p : L.pool_allocs) cudaFree(p);
@@ -642,7 +643,7 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
 #ifndef B200PT_EMULATE
             we = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
 #endif
-            if (we == cudaSuccess) we = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wave_per_sm, kernel, kWaveThreads, wsmem);
+            if (we == cudaSuccess) we = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wave_per_sm, kernel, wave_threads(c), wsmem);
         });
         if (we != cudaSuccess || wave_per_sm <= 0) { c->fused = false; cudaGetLastError(); }      // does not fit: global wavefront
         else {
@@ -740,7 +741,7 @@ static void launch_shade(b200pt_ctx* c, const Lane& L, const ShadeArgs& sa) {
 }
 static void launch_wave(b200pt_ctx* c, const Lane& L, const WaveArgs& wa) {
     const size_t smem = wave_smem(c);
-    with_wave_kernel(c, [&](auto kernel, bool) { PT_LAUNCH_CTA(kernel, c->wave_blocks, kWaveThreads, smem, L.stream, wa); });
+    with_wave_kernel(c, [&](auto kernel, bool) { PT_LAUNCH_CTA(kernel, c->wave_blocks, wave_threads(c), smem, L.stream, wa); });
 }
 static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
     if (c->small_scene) {
@@ -782,7 +783,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
         if (c->fused) {
             // CTA-local wavefront: the whole batch of this lane is ONE persistent launch (slots, queue and scene in shared
             // memory); ~3/4 of the samples are handed out statically per slot, the rest from the global counter
-            const unsigned long long P = (unsigned long long)c->wave_blocks * kWaveThreads;
+            const unsigned long long P = (unsigned long long)c->wave_blocks * wave_threads(c);
             bp.k_static = (uint32_t)((need - need / 4) / P);
             L.h_init[0] = (unsigned long long)bp.k_static * P; L.h_init[1] = 0ull;
             CK(cudaMemcpyAsync(L.counters, L.h_init, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, L.stream));

@@ -386,23 +386,83 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
 #undef STK_PUSH
 #undef STK_POP
 
+// All group boxes of a small scene against one ray, warp-uniform: the hit groups as a 64-bit mask and the group the ray
+// enters first.
+__device__ __forceinline__ void small_ray_boxes(const TraceArgs& a, const float4* __restrict__ leaves, const f3 o, const f3 inv, const float tmax,
+                                                unsigned long long& mask, int& best) {
+    const int n_leaves = a.n_leaves;
+    mask = 0ull;
+    float tn, best_t = INFINITY;
+    best = -1;
+    if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
+        // BBox::Intersect (src/bbox.h:77-96) on every group box, with the min / max of each axis' two plane distances
+        // replaced by a SELECTION: (plane - o) * (1/d) is monotonic in `plane`, so for a finite 1/d the smaller of
+        // the two distances belongs to the plane the sign of d picks — bit-identical tmin / tmax, but the near and far
+        // planes come from two 4-byte shared-memory loads at a per-lane offset and the 6 two-input min / max per box
+        // are gone (the loop was 35 % of the kernel's instructions, profiles/r02d_wave_c2_lines.txt).  A direction
+        // with a zero or denormal component (1/d infinite: the reference's test then leans on NaN-dropping fminf /
+        // fmaxf) takes the literal form.
+        // (A cheaper conservative test with one fused multiply-add per plane was tried and dropped: it needs grown
+        // boxes, and a box that is hit where the reference's is not lets the exact primitive test accept a grazing hit
+        // the reference culls — 1 sample in 12 288 of the 64 x 64 vol_caustic image, a direct view of the emitter.)
+        const bool fast = fabsf(inv.x) < INFINITY && fabsf(inv.y) < INFINITY && fabsf(inv.z) < INFINITY;
+        uint32_t m0 = 0u, m1 = 0u;
+        if (fast) {
+            const int nx = inv.x >= 0.f ? 0 : 3, ny = inv.y >= 0.f ? 1 : 4, nz = inv.z >= 0.f ? 2 : 5;      // word of the near plane
+            const float* lw = reinterpret_cast<const float*>(leaves);
+#define PT_BOX_TEST(l_, bit_, m_)                                                                                     \
+            {                                                                                                     \
+                const int l = (l_);                                                                               \
+                const float* g_ = lw + 8 * l;                                                                     \
+                const float tnear = fmaxf(fmaxf((g_[nx] - o.x) * inv.x, (g_[ny] - o.y) * inv.y), (g_[nz] - o.z) * inv.z);          \
+                const float tfar = fminf(fminf((g_[3 - nx] - o.x) * inv.x, (g_[5 - ny] - o.y) * inv.y), (g_[7 - nz] - o.z) * inv.z); \
+                if (!(tfar <= 0.00001f) && !(tnear > tfar) && !(tnear > tmax)) {                                  \
+                    m_ |= 1u << (bit_);                                                                           \
+                    if (tnear < best_t) { best_t = tnear; best = l; }                                             \
+                }                                                                                                 \
+            }
+            const int n0 = n_leaves < 32 ? n_leaves : 32;
+            for (int i = 0; i < n0; ++i) PT_BOX_TEST(i, i, m0)
+            for (int i = 32; i < n_leaves; ++i) PT_BOX_TEST(i, i - 32, m1)
+#undef PT_BOX_TEST
+        } else {
+            for (int l = 0; l < n_leaves; ++l) {
+                const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
+                if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
+                    if (l < 32) m0 |= 1u << l; else m1 |= 1u << (l - 32);
+                    if (tn < best_t) { best_t = tn; best = l; }
+                }
+            }
+        }
+        mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+    }
+}
+
+// The ray a queue entry stands for: origin, direction, tmax (continuation / MIS rays are unbounded).
+__device__ __forceinline__ void small_ray_fetch(const TraceArgs& a, const Pool& pool, const uint32_t entry, f3& o, f3& d, float& tmax) {
+    const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
+    const float4 orng = kind == 0u ? pool.o_rng[slot] : pool.pend_o[slot];             // shadow / MIS rays keep their own origin
+    o = mk3(orng.x, orng.y, orng.z);
+    float4 dv;
+    if (kind == 0u) { dv = pool.d_flags[slot]; dv.w = INFINITY; }
+    else if (kind == 1u) dv = pool.shd[slot];
+    else { dv = pool.misd[slot]; if (!a.sec_tmax) dv.w = INFINITY; }
+    d = mk3(dv.x, dv.y, dv.z);
+    tmax = dv.w;
+}
+
 // One ray of the flat small-scene traversal (see k_trace_small below): fetch the ray of queue entry `entry` from the
 // pool planes, test all group boxes, run the flat primitive loop, write the hit / visibility back.  `prims` / `leaves`
 // point at the staged (shared-memory) copies; the pool planes are global (k_trace_small) or shared (k_wave.cuh).
 template <bool VOL>
 __device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const Pool& pool, const WPrim* __restrict__ prims,
-                                                const float4* __restrict__ leaves, const uint32_t entry, uint32_t& nrays) {
+                                                const float4* __restrict__ leaves, const uint32_t entry, uint32_t& nrays,
+                                                bool have_first = false, const unsigned long long first_mask = 0ull, const int first_best = -1) {
     const float eps = a.sc.eps;
-    const int n_leaves = a.n_leaves;
     const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
-    const float4 orng = kind == 0u ? pool.o_rng[slot] : pool.pend_o[slot];             // shadow / MIS rays keep their own origin
-    f3 o = mk3(orng.x, orng.y, orng.z);
-    float4 dv;
-    if (kind == 0u) { dv = pool.d_flags[slot]; dv.w = INFINITY; }
-    else if (kind == 1u) dv = pool.shd[slot];
-    else { dv = pool.misd[slot]; if (!a.sec_tmax) dv.w = INFINITY; }
-    const f3 d = mk3(dv.x, dv.y, dv.z);
-    float tmax = dv.w;
+    f3 o, d;
+    float tmax;
+    small_ray_fetch(a, pool, entry, o, d, tmax);
     const bool anyhit = !VOL && kind == 1u;
     f3 tr = mk3(1, 1, 1);
     float remain = tmax;
@@ -413,52 +473,13 @@ __device__ __forceinline__ void trace_small_ray(const TraceArgs& a, const Pool& 
     for (;;) {                                   // one pass per ray; vpt shadow rays repeat it per segment (Tr())
         ++nrays;
         hprim = -1;
-        // ---- all group boxes, warp-uniform; remember the group the ray enters first
-        unsigned long long mask = 0ull;
-        float tn, best_t = INFINITY;
-        int best = -1;
-        if (slab(a.sc.root_min[0], a.sc.root_min[1], a.sc.root_min[2], a.sc.root_max[0], a.sc.root_max[1], a.sc.root_max[2], o, inv, tmax, tn)) {
-            // BBox::Intersect (src/bbox.h:77-96) on every group box, with the min / max of each axis' two plane distances
-            // replaced by a SELECTION: (plane - o) * (1/d) is monotonic in `plane`, so for a finite 1/d the smaller of
-            // the two distances belongs to the plane the sign of d picks — bit-identical tmin / tmax, but the near and far
-            // planes come from two 4-byte shared-memory loads at a per-lane offset and the 6 two-input min / max per box
-            // are gone (the loop was 35 % of the kernel's instructions, profiles/r02d_wave_c2_lines.txt).  A direction
-            // with a zero or denormal component (1/d infinite: the reference's test then leans on NaN-dropping fminf /
-            // fmaxf) takes the literal form.
-            // (A cheaper conservative test with one fused multiply-add per plane was tried and dropped: it needs grown
-            // boxes, and a box that is hit where the reference's is not lets the exact primitive test accept a grazing hit
-            // the reference culls — 1 sample in 12 288 of the 64 x 64 vol_caustic image, a direct view of the emitter.)
-            const bool fast = fabsf(inv.x) < INFINITY && fabsf(inv.y) < INFINITY && fabsf(inv.z) < INFINITY;
-            uint32_t m0 = 0u, m1 = 0u;
-            if (fast) {
-                const int nx = inv.x >= 0.f ? 0 : 3, ny = inv.y >= 0.f ? 1 : 4, nz = inv.z >= 0.f ? 2 : 5;      // word of the near plane
-                const float* lw = reinterpret_cast<const float*>(leaves);
-#define PT_BOX_TEST(l_, bit_, m_)                                                                                     \
-                {                                                                                                     \
-                    const int l = (l_);                                                                               \
-                    const float* g_ = lw + 8 * l;                                                                     \
-                    const float tnear = fmaxf(fmaxf((g_[nx] - o.x) * inv.x, (g_[ny] - o.y) * inv.y), (g_[nz] - o.z) * inv.z);          \
-                    const float tfar = fminf(fminf((g_[3 - nx] - o.x) * inv.x, (g_[5 - ny] - o.y) * inv.y), (g_[7 - nz] - o.z) * inv.z); \
-                    if (!(tfar <= 0.00001f) && !(tnear > tfar) && !(tnear > tmax)) {                                  \
-                        m_ |= 1u << (bit_);                                                                           \
-                        if (tnear < best_t) { best_t = tnear; best = l; }                                             \
-                    }                                                                                                 \
-                }
-                const int n0 = n_leaves < 32 ? n_leaves : 32;
-                for (int i = 0; i < n0; ++i) PT_BOX_TEST(i, i, m0)
-                for (int i = 32; i < n_leaves; ++i) PT_BOX_TEST(i, i - 32, m1)
-#undef PT_BOX_TEST
-            } else {
-                for (int l = 0; l < n_leaves; ++l) {
-                    const float4 q0 = leaves[2 * l], q1 = leaves[2 * l + 1];
-                    if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, tmax, tn)) {
-                        if (l < 32) m0 |= 1u << l; else m1 |= 1u << (l - 32);
-                        if (tn < best_t) { best_t = tn; best = l; }
-                    }
-                }
-            }
-            mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
-        }
+        // ---- all group boxes, warp-uniform; remember the group the ray enters first (the CTA-local kernel has done this
+        // pass for the ray's first leg already and sorted the rays by its result: k_wave.cuh)
+        unsigned long long mask;
+        int best;
+        float tn;
+        if (have_first) { mask = first_mask; best = first_best; have_first = false; }
+        else small_ray_boxes(a, leaves, o, inv, tmax, mask, best);
         // ---- flat primitive loop over the hit groups: nearest group first, then the others in index order; once
         // a closest hit is known, a group is re-tested against the shrunken interval before its primitives are
         // (the `tmin > ray.tmax` rejection of BBox::Intersect, src/bbox.h:93)

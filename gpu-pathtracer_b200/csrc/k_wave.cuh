@@ -27,9 +27,13 @@
 
 namespace pt {
 
-constexpr int kWaveThreads = 256;
+constexpr int kWaveThreads = 256;                 // slots (= threads) per CTA of the surface / homogeneous-medium wavefront
+#ifndef PT_WAVE_HET_THREADS
+#define PT_WAVE_HET_THREADS 128                   // heterogeneous media: smaller CTAs — the glue's tracking loops make the CTA barrier
+#endif                                            // the top stall (6 warps per issue slot at 256), and 4 x 128 threads wait less than 2 x 256
+template <bool HET> struct WaveThreads { static constexpr int value = HET ? PT_WAVE_HET_THREADS : kWaveThreads; };
 #ifndef PT_WAVE_HET_CTAS
-#define PT_WAVE_HET_CTAS 2          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
+#define PT_WAVE_HET_CTAS 4          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
 #endif
 
 // The shade / trace bodies read scene, camera, shard map and batch from the same argument structs as the global
@@ -42,9 +46,10 @@ struct WaveArgs {
 
 // Shared-memory footprint of one CTA: scene (primitive records + group boxes) + path planes + ray queue.
 template <bool VOL> struct WavePlanes { static constexpr int value = VOL ? 15 : 14; };
-template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_leaves) {
-    return (size_t)((prim_bytes + (uint32_t)n_leaves * 32u + 127u) & ~127u) + (size_t)WavePlanes<VOL>::value * kWaveThreads * sizeof(float4) +
-           (size_t)3 * kWaveThreads * sizeof(uint32_t);
+// ... + the per-ray box results of the sorted trace phase: hit-group mask (8 B), order (2 B) and nearest group (1 B) per queue entry
+template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_leaves, int threads) {
+    return (size_t)((prim_bytes + (uint32_t)n_leaves * 32u + 127u) & ~127u) + (size_t)WavePlanes<VOL>::value * threads * sizeof(float4) +
+           (size_t)3 * threads * sizeof(uint32_t) + (size_t)3 * threads * (sizeof(unsigned long long) + sizeof(uint16_t) + 2);
 }
 
 #ifndef B200PT_EMULATE
@@ -52,13 +57,39 @@ template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_lea
 #define PT_WAVE_SYNC() __syncthreads()
 #else
 // CPU emulation of the test suite: one host thread plays a whole CTA, phase by phase
-#define PT_WAVE_FOR_THREADS(t) for (uint32_t t = 0; t < (uint32_t)kWaveThreads; ++t)
+#define PT_WAVE_FOR_THREADS(t) for (uint32_t t = 0; t < (uint32_t)kT; ++t)
 #define PT_WAVE_SYNC() do { } while (0)
 #endif
 
+// The trace phase of the CTA-local wavefront runs in two passes (PT_WAVE_SORT): the box pass of every queued ray (the same
+// work for every ray: full SIMT width), a counting sort of the rays by (kind of query, number of hit groups) in shared
+// memory, and the primitive pass in that order — every ray needs a different number of Moeller-Trumbore tests, and in queue
+// order the primitive loop ran at 5-10 of 32 lanes (profiles/r02d_wave_c2_lines.txt).
+#ifndef PT_WAVE_SORT
+#define PT_WAVE_SORT 1
+#endif
+template <bool VOL> __device__ __forceinline__ uint32_t wave_sort_key(uint32_t entry, unsigned long long mask) {
+    const uint32_t kind = entry >> kKindShift;
+    const uint32_t n = (uint32_t)__popc((uint32_t)mask) + (uint32_t)__popc((uint32_t)(mask >> 32));
+    const uint32_t any = (!VOL && kind == 1u) ? 16u : 0u;             // any-hit queries after the closest-hit ones
+    return any + 15u - (n < 15u ? n : 15u);                           // most hit groups first
+}
+
+// Sort key of a heterogeneous-media slot: wait state, and whether the stage it resumes into runs a tracking loop (the path
+// ray / walk leg lies in a medium) — lanes that will track sit next to each other.  Dead slots last.
+__device__ __forceinline__ uint32_t het_sort_key(const Pool& P, uint32_t slot) {
+    const uint32_t f = __float_as_uint(P.d_flags[slot].w);
+    if (!(f & H_ALIVE)) return 15u;
+    const uint32_t st = (f >> kHStateShift) & 3u;
+    uint32_t med = (f >> kMediumShift) & 0xffu;                                      // medium of the path ray + 1
+    if (st == HS_WALK_MED || st == HS_WALK_SURF) med = __float_as_uint(P.vis[slot].w);   // medium of the walk's current leg + 1
+    return st * 2u + (med != 0u ? 1u : 0u);
+}
+
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
-__global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3)) k_wave_small(const WaveArgs a) {
+__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3)) k_wave_small(const WaveArgs a) {
+    constexpr int kT = WaveThreads<HET>::value;
     const ShadeArgs& sa = a.sa;
     const TraceArgs& ta = a.ta;
 #ifndef B200PT_EMULATE
@@ -66,16 +97,19 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
     __shared__ uint64_t bar;
 #else
     static thread_local std::vector<unsigned char> smem_vec;
-    smem_vec.assign(wave_smem_bytes<VOL>(ta.small_prim_bytes, ta.n_leaves) + 128, 0);
+    smem_vec.assign(wave_smem_bytes<VOL>(ta.small_prim_bytes, ta.n_leaves, kT) + 128, 0);
     unsigned char* smem_raw = smem_vec.data();
 #endif
-    __shared__ uint32_t s_busy[2], s_retired, s_rays;
+    __shared__ uint32_t s_busy[2], s_retired, s_rays, s_hist[32];
     __shared__ QueueCtl s_ctl;
     __shared__ unsigned long long s_next;
 
     const uint32_t scene_bytes = (ta.small_prim_bytes + (uint32_t)ta.n_leaves * 32u + 127u) & ~127u;
     float4* const planes = reinterpret_cast<float4*>(smem_raw + scene_bytes);
-    uint32_t* const s_queue = reinterpret_cast<uint32_t*>(planes + (size_t)WavePlanes<VOL>::value * kWaveThreads);
+    uint32_t* const s_queue = reinterpret_cast<uint32_t*>(planes + (size_t)WavePlanes<VOL>::value * kT);
+    unsigned long long* const s_mask = reinterpret_cast<unsigned long long*>(s_queue + 3 * kT);
+    uint16_t* const s_sorted = reinterpret_cast<uint16_t*>(s_mask + 3 * kT);
+    signed char* const s_best = reinterpret_cast<signed char*>(s_sorted + 3 * kT);
     const WPrim* prims = ta.sc.prims;
     const float4* leaves = ta.leaves;
 
@@ -97,7 +131,7 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
             tma_bulk_g2s(smem_raw + ta.small_prim_bytes, ta.leaves, lb, &bar);
         }
         // all slots start dead with no static sample consumed (the flags word and li_t.w are what shade_slot looks at)
-        for (int k = 0; k < WavePlanes<VOL>::value; ++k) planes[(size_t)k * kWaveThreads + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < WavePlanes<VOL>::value; ++k) planes[(size_t)k * kT + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(&bar, 0);
         prims = reinterpret_cast<const WPrim*>(smem_raw);
         leaves = reinterpret_cast<const float4*>(smem_raw + ta.small_prim_bytes);
@@ -110,43 +144,37 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
 #endif
 
     Pool P;
-    P.o_rng = planes; P.d_flags = planes + 1 * kWaveThreads; P.beta_s = planes + 2 * kWaveThreads; P.li_t = planes + 3 * kWaveThreads;
-    P.shd = planes + 4 * kWaveThreads; P.misd = planes + 5 * kWaveThreads; P.ldl = planes + 6 * kWaveThreads; P.misf = planes + 7 * kWaveThreads;
-    P.beta_old = planes + 8 * kWaveThreads; P.hit0 = planes + 9 * kWaveThreads; P.hit1 = planes + 10 * kWaveThreads; P.vis = planes + 11 * kWaveThreads;
-    P.pend_o = planes + 12 * kWaveThreads; P.carry = planes + 13 * kWaveThreads; P.aux = planes + (VOL ? 14 : 0) * kWaveThreads;
-    P.n = kWaveThreads;
+    P.o_rng = planes; P.d_flags = planes + 1 * kT; P.beta_s = planes + 2 * kT; P.li_t = planes + 3 * kT;
+    P.shd = planes + 4 * kT; P.misd = planes + 5 * kT; P.ldl = planes + 6 * kT; P.misf = planes + 7 * kT;
+    P.beta_old = planes + 8 * kT; P.hit0 = planes + 9 * kT; P.hit1 = planes + 10 * kT; P.vis = planes + 11 * kT;
+    P.pend_o = planes + 12 * kT; P.carry = planes + 13 * kT; P.aux = planes + (VOL ? 14 : 0) * kT;
+    P.n = kT;
     RayQueue Q; Q.entries = s_queue; Q.ctl = &s_ctl;
-    const uint32_t pool_n = gridDim.x * (uint32_t)kWaveThreads;
+    const uint32_t pool_n = gridDim.x * (uint32_t)kT;
 
     if (HET) {
         // Heterogeneous media: the slots are coroutines in one of four wait states (k_het.cuh), and each state resumes into
         // different code (free-flight sampling, a leg of a transmittance walk, the MIS hit).  Executed slot-per-thread,
         // a warp ran every state's code with a fifth of its lanes (6.2 of 32 active lanes per instruction,
         // profiles/r02_counters.json, "smoke").  So every step starts with a COUNTING SORT of the CTA's slots by state
-        // (shared memory, 8 keys) and thread j resumes slot order[j]: the lanes of a warp resume the same stage and walk
+        // (shared memory; key = state x "the resumed stage walks a medium") and thread j resumes slot order[j]: the lanes of a warp resume the same stage and walk
         // their tracking loops together.  Then the usual two phases: glue posts <= 1 query per slot into the compact
         // queue, the trace phase runs the queue.
-        __shared__ uint32_t s_cnt[8], s_pos[8];
-        uint16_t* const s_order = reinterpret_cast<uint16_t*>(s_queue + 2 * kWaveThreads);       // the queue holds <= 1 entry per slot here
+        __shared__ uint32_t s_cnt[16], s_pos[16];
+        uint16_t* const s_order = reinterpret_cast<uint16_t*>(s_queue + 2 * kT);       // the queue holds <= 1 entry per slot here
+        PT_WAVE_FOR_THREADS(t) { if (t < 16u) { s_cnt[t] = 0u; s_pos[t] = 0u; } }
+        PT_WAVE_SYNC();
         for (uint32_t step = 0;; ++step) {
             const uint32_t par = step & 1u;
-            // ---- sort the slots by wait state (dead slots last)
-            PT_WAVE_FOR_THREADS(t) { if (t < 8u) s_cnt[t] = 0u; }
+            // ---- sort the slots by wait state (dead slots last): count, then scatter (every thread sums the counts below
+            // its key itself — 16 broadcast reads instead of a prefix phase and its barrier)
+            PT_WAVE_FOR_THREADS(t) { atomicAdd(&s_cnt[het_sort_key(P, t)], 1u); }
             PT_WAVE_SYNC();
             PT_WAVE_FOR_THREADS(t) {
-                const uint32_t f = __float_as_uint(P.d_flags[t].w);
-                const uint32_t key = (f & H_ALIVE) ? ((f >> kHStateShift) & 3u) : 7u;
-                atomicAdd(&s_cnt[key], 1u);
-            }
-            PT_WAVE_SYNC();
-            PT_WAVE_FOR_THREADS(t) {
-                if (t == 0u) { uint32_t run = 0u; for (int k = 0; k < 8; ++k) { s_pos[k] = run; run += s_cnt[k]; } }
-            }
-            PT_WAVE_SYNC();
-            PT_WAVE_FOR_THREADS(t) {
-                const uint32_t f = __float_as_uint(P.d_flags[t].w);
-                const uint32_t key = (f & H_ALIVE) ? ((f >> kHStateShift) & 3u) : 7u;
-                s_order[atomicAdd(&s_pos[key], 1u)] = (uint16_t)t;
+                const uint32_t key = het_sort_key(P, t);
+                uint32_t base = 0u;
+                for (uint32_t k = 0; k < key; ++k) base += s_cnt[k];
+                s_order[base + atomicAdd(&s_pos[key], 1u)] = (uint16_t)t;
             }
             PT_WAVE_SYNC();
             // ---- glue phase
@@ -156,7 +184,7 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
 #endif
                 const uint32_t slot = s_order[t];
                 uint32_t posted = 0u;
-                het_slot<MATS, true, true>(sa, P, Q, par, &s_retired, &s_busy[par], slot, blockIdx.x * (uint32_t)kWaveThreads + slot, pool_n, s_next, posted);
+                het_slot<MATS, true, true>(sa, P, Q, par, &s_retired, &s_busy[par], slot, blockIdx.x * (uint32_t)kT + slot, pool_n, s_next, posted);
             }
             PT_WAVE_SYNC();
             const uint32_t tail = s_ctl.tail[par];
@@ -167,8 +195,9 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
                 threadIdx.x = t;
 #endif
                 if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
+                if (t < 16u) { s_cnt[t] = 0u; s_pos[t] = 0u; }                      // re-arm the sort counters for the next step
                 uint32_t nrays = 0;
-                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kWaveThreads) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
+                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
 #ifndef B200PT_EMULATE
                 for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
 #endif
@@ -186,7 +215,7 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
 #endif
             SlotRec r;
             load_slot<VOL>(P, t, r);
-            shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kWaveThreads + t, pool_n, r, s_next);
+            shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kT + t, pool_n, r, s_next);
         }
         PT_WAVE_SYNC();
         const uint32_t tail = s_ctl.tail[par];
@@ -197,8 +226,46 @@ __global__ void __launch_bounds__(kWaveThreads, HET ? PT_WAVE_HET_CTAS : ((VOL |
             threadIdx.x = t;
 #endif
             if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
+#if PT_WAVE_SORT
+            // box pass: every ray against all group boxes (uniform work), result kept per queue entry; histogram of the sort key
+            if (t < 32u) s_hist[t] = 0u;
+        }
+        PT_WAVE_SYNC();
+        PT_WAVE_FOR_THREADS(t) {
+            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) {
+                const uint32_t entry = s_queue[idx];
+                f3 o, d; float tmax;
+                small_ray_fetch(ta, P, entry, o, d, tmax);
+                unsigned long long mask; int best;
+                small_ray_boxes(ta, leaves, o, mk3(1.f / d.x, 1.f / d.y, 1.f / d.z), tmax, mask, best);
+                s_mask[idx] = mask; s_best[idx] = (signed char)best;
+                atomicAdd(&s_hist[wave_sort_key<VOL>(entry, mask)], 1u);
+            }
+        }
+        PT_WAVE_SYNC();
+        PT_WAVE_FOR_THREADS(t) {
+            if (t == 0u) { uint32_t run = 0u; for (int k = 0; k < 32; ++k) { const uint32_t c = s_hist[k]; s_hist[k] = run; run += c; } }
+        }
+        PT_WAVE_SYNC();
+        PT_WAVE_FOR_THREADS(t) {
+            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT)
+                s_sorted[atomicAdd(&s_hist[wave_sort_key<VOL>(s_queue[idx], s_mask[idx])], 1u)] = (uint16_t)idx;
+        }
+        PT_WAVE_SYNC();
+        // primitive pass in sorted order: the lanes of a warp carry rays of one kind with (nearly) the same number of hit groups
+        PT_WAVE_FOR_THREADS(t) {
+#ifdef B200PT_EMULATE
+            threadIdx.x = t;
+#endif
             uint32_t nrays = 0;
-            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kWaveThreads) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
+            for (uint32_t j = t; j < tail; j += (uint32_t)kT) {
+                const uint32_t idx = s_sorted[j];
+                trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays, true, s_mask[idx], (int)s_best[idx]);
+            }
+#else
+            uint32_t nrays = 0;
+            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
+#endif
 #ifndef B200PT_EMULATE
             for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
 #endif
