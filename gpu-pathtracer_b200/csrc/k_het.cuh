@@ -149,6 +149,90 @@ __device__ __noinline__ f3 medium_sample(const SceneDev& sc, int medium, f3 o, f
     return mk3(1.f, 1.f, 1.f);
 }
 
+// ---- the same two loops, resumable: at most `max_steps` tracking steps per call ------------------------------------------------
+// The trip count of a tracking loop is data dependent (the free path through the majorant), and inside the CTA-local
+// wavefront a lane that tracks for 200 steps keeps its whole CTA at the barrier.  So the coroutine runs a walk through a
+// heterogeneous medium in CHUNKS: the loop state (distance so far, running transmittance, remaining iteration budget) is
+// saved in the slot, the slot stays in its wait state without posting a query, and the next step — after the slots have
+// been re-sorted — continues where it stopped.  Same operations on the same values in the same order as het_tr /
+// medium_sample above (the random-number stream is the path's own and is saved with the slot).
+struct TrackState { float dist, tr; int iter; };
+__device__ __forceinline__ bool het_tr_chunk(const WMedium& M, const WHetero& H, f3 o, f3 dir, float tmax, uint32_t& rng, TrackState& k,
+                                             int max_steps, f3& result) {
+    float sigma = dot(ld3(M.sigmaT), mk3(0.212671f, 0.715160f, 0.072169f));
+    const f3 p0 = ld3(H.p0);
+    f3 d = ld3(H.p1) - p0;
+    if (H.evalTransmittanceType == 0) {
+        for (int s_ = 0; s_ < max_steps; ++s_) {
+            k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
+            if (k.dist >= tmax) { result = mk3(k.tr, k.tr, k.tr); return true; }
+            f3 p = o + dir * k.dist;
+            p = (p - p0) / d;
+            if (het_density(H, p) * H.invMaxDensity > rng_next(rng)) { result = mk3(0.f, 0.f, 0.f); return true; }
+            if (--k.iter == 0) { result = mk3(0.f, 0.f, 0.f); return true; }
+        }
+        return false;
+    }
+    if (H.evalTransmittanceType == 1) {
+        for (int s_ = 0; s_ < max_steps; ++s_) {
+            k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
+            if (k.dist >= tmax) { result = mk3(k.tr, k.tr, k.tr); return true; }
+            f3 p = o + dir * k.dist;
+            p = (p - p0) / d;
+            k.tr *= 1.f - het_density(H, p) * H.invMaxDensity;
+            if (k.tr < 0.1f) {
+                float q = 1.f - k.tr;
+                if (rng_next(rng) < q) { result = mk3(0.f, 0.f, 0.f); return true; }
+                k.tr = 1;
+            }
+            if (--k.iter == 0) { result = mk3(k.tr, k.tr, k.tr); return true; }
+        }
+        return false;
+    }
+    float maxDensity = 1 / H.invMaxDensity;
+    float ce = 0.5f * maxDensity;
+    for (int s_ = 0; s_ < max_steps; ++s_) {
+        bool end = false;
+        k.dist += -logf(rng_next(rng)) * (1 / (maxDensity - ce) / sigma);
+        if (k.dist >= tmax) end = true;
+        else {
+            f3 p = o + dir * k.dist;
+            p = (p - p0) / d;
+            k.tr *= 1.f - (het_density(H, p) - ce) / (maxDensity - ce);
+            if (k.tr < 0.1f) {
+                float q = 1.f - k.tr;
+                if (rng_next(rng) < q) { result = mk3(0.f, 0.f, 0.f); return true; }
+                k.tr /= (1.f - q);
+            }
+            if (--k.iter == 0) end = true;
+        }
+        if (end) {
+            float tc = expf(-tmax * ce * sigma);
+            const float r = k.tr * tc;
+            result = mk3(r, r, r);
+            return true;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ bool het_sample_chunk(const WMedium& M, const WHetero& H, f3 o, f3 dir, float tmax, uint32_t& rng, TrackState& k,
+                                                 int max_steps, float& t, bool& sampled, f3& weight) {
+    f3 sigmaT = ld3(M.sigmaT), sigmaS = ld3(M.sigmaS);
+    float sigma = dot(sigmaT, mk3(0.212671f, 0.715160f, 0.072169f));
+    const f3 p0 = ld3(H.p0);
+    f3 d = ld3(H.p1) - p0;
+    for (int s_ = 0; s_ < max_steps; ++s_) {
+        k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
+        if (k.dist >= tmax) { t = k.dist; sampled = false; weight = mk3(1.f, 1.f, 1.f); return true; }
+        f3 p = o + dir * k.dist;
+        p = (p - p0) / d;
+        if (het_density(H, p) * H.invMaxDensity > rng_next(rng)) { t = k.dist; sampled = true; weight = sigmaS / sigmaT; return true; }
+        if (--k.iter == 0) { t = k.dist; sampled = false; weight = mk3(1.f, 1.f, 1.f); return true; }
+    }
+    return false;
+}
+constexpr int kTrackChunk = 16;                  // tracking steps per wavefront step and slot (CTA-local kernel)
+
 // ---- the coroutine ------------------------------------------------------------------------------------------------------
 // Slot record (the wavefront's own planes, re-used):
 //   o_rng     path ray origin, rng state             d_flags   path ray direction, state word (below)
@@ -160,6 +244,7 @@ __device__ __noinline__ f3 medium_sample(const SceneDev& sc, int medium, f3 o, f
 //   misf      BSDF value (light-sample evaluation / MIS sample), its pdf
 //   beta_old  direct light Ld of this bounce so far, free-flight distance of a medium scatter
 //   aux       |cos| of the MIS direction, -, -, -
+//   carry     tracking loop in progress (CHUNKED): distance so far, running transmittance, iterations left (bits), 1 / 0
 constexpr uint32_t H_ALIVE = 1u << 0, H_SPECULAR = 1u << 1;
 constexpr int kHStateShift = 24;                 // bits 24..26: what the slot is waiting for
 enum { HS_MAIN = 0, HS_WALK_MED = 1, HS_WALK_SURF = 2, HS_MIS = 3 };
@@ -236,7 +321,22 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                 }
                 reconstruct_hit(sc, o, d, h0.x, __float_as_int(h0.y), h0.z, h0.w, h); have_h = true;
                 float sampledDist = 0.f; bool sampledMedium = false;
-                if (medium >= 0) beta *= medium_sample(sc, medium, o, d, h0.x, rng, sampledDist, sampledMedium);
+                if (medium >= 0) {
+                    const WMedium& M_ = sc.mediums[medium];
+                    if (FUSED && M_.type != 0) {                 // heterogeneous, CTA-local kernel: free flight in chunks
+                        const float4 cy = pool.carry[slot];
+                        TrackState tk;
+                        if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
+                        else { tk.dist = 0.f; tk.tr = 1.f; tk.iter = sc.het[medium].iterMax; }
+                        f3 w_;
+                        if (!het_sample_chunk(M_, sc.het[medium], o, d, h0.x, rng, tk, kTrackChunk, sampledDist, sampledMedium, w_)) {
+                            st_rec<FUSED>(pool.carry + slot, make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), 1.f));
+                            state = HS_MAIN; post = 0u; g = G_OUT; continue;          // resume here next step
+                        }
+                        if (cy.w != 0.f) st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
+                        beta *= w_;
+                    } else beta *= medium_sample(sc, medium, o, d, h0.x, rng, sampledDist, sampledMedium);
+                }
                 if (is_black(beta)) { finished = true; g = G_OUT; continue; }                    // :1070
                 if (sampledMedium) {                                                            // :1071-1088: light sample, then Tr()
                     float u = rng_next(rng);
@@ -297,12 +397,28 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                 f3 tr = mk3(pv.x, pv.y, pv.z);
                 int mw = (int)__float_as_uint(pv.w) - 1;
                 const bool invisible = h1.x >= 0.f;
-                bool again = false;
+                bool again = false, walk_paused = false;
                 if (invisible && sc.shade[__float_as_int(h1.y)].matIdx != -1) tr = mk3(0, 0, 0);
                 else {
                     const float seg = invisible ? h1.x : remain;
-                    if (mw >= 0) tr *= medium_tr(sc, mw, ow, dw, seg, rng);
-                    if (invisible) {
+                    if (mw >= 0) {
+                        const WMedium& M_ = sc.mediums[mw];
+                        if (FUSED && M_.type != 0) {             // heterogeneous, CTA-local kernel: this leg's transmittance in chunks
+                            const float4 cy = pool.carry[slot];
+                            TrackState tk;
+                            if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
+                            else { tk.dist = 0.f; tk.tr = 1.f; tk.iter = sc.het[mw].iterMax; }
+                            f3 r_;
+                            if (!het_tr_chunk(M_, sc.het[mw], ow, dw, seg, rng, tk, kTrackChunk, r_)) {
+                                st_rec<FUSED>(pool.carry + slot, make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), 1.f));
+                                post = 0u; g = G_OUT; walk_paused = true;
+                            } else {
+                                if (cy.w != 0.f) st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
+                                tr *= r_;
+                            }
+                        } else tr *= medium_tr(sc, mw, ow, dw, seg, rng);
+                    }
+                    if (!walk_paused && invisible) {
                         const int prim = __float_as_int(h1.y);
                         const WShade& s = sc.shade[prim];
                         f3 nor;
@@ -317,6 +433,7 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                         again = true;
                     }
                 }
+                if (walk_paused) continue;                                                      // same state, no query: resume next step
                 if (again) { post = 2u; g = G_OUT; continue; }                                  // same state: next leg
                 const float4 l = pool.ldl[slot];
                 const f3 radiance = mk3(l.x, l.y, l.z);

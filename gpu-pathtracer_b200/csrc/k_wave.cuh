@@ -29,11 +29,11 @@ namespace pt {
 
 constexpr int kWaveThreads = 256;                 // slots (= threads) per CTA of the surface / homogeneous-medium wavefront
 #ifndef PT_WAVE_HET_THREADS
-#define PT_WAVE_HET_THREADS 128                   // heterogeneous media: smaller CTAs — the glue's tracking loops make the CTA barrier
-#endif                                            // the top stall (6 warps per issue slot at 256), and 4 x 128 threads wait less than 2 x 256
+#define PT_WAVE_HET_THREADS 256                   // heterogeneous media (128-thread CTAs measured slower: smoke 113 vs 146 Msamples/s)
+#endif
 template <bool HET> struct WaveThreads { static constexpr int value = HET ? PT_WAVE_HET_THREADS : kWaveThreads; };
 #ifndef PT_WAVE_HET_CTAS
-#define PT_WAVE_HET_CTAS 4          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
+#define PT_WAVE_HET_CTAS 2          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
 #endif
 
 // The shade / trace bodies read scene, camera, shard map and batch from the same argument structs as the global
@@ -222,50 +222,51 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
         if (tail == 0u && s_busy[par] == 0u) break;          // no ray in flight, no slot alive, no sample left
         // ---- trace phase (thread 0 also refreshes the sample-counter snapshot and re-arms the other control set)
         PT_WAVE_FOR_THREADS(t) {
-#ifdef B200PT_EMULATE
-            threadIdx.x = t;
-#endif
             if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
-#if PT_WAVE_SORT
-            // box pass: every ray against all group boxes (uniform work), result kept per queue entry; histogram of the sort key
             if (t < 32u) s_hist[t] = 0u;
         }
-        PT_WAVE_SYNC();
-        PT_WAVE_FOR_THREADS(t) {
-            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) {
-                const uint32_t entry = s_queue[idx];
-                f3 o, d; float tmax;
-                small_ray_fetch(ta, P, entry, o, d, tmax);
-                unsigned long long mask; int best;
-                small_ray_boxes(ta, leaves, o, mk3(1.f / d.x, 1.f / d.y, 1.f / d.z), tmax, mask, best);
-                s_mask[idx] = mask; s_best[idx] = (signed char)best;
-                atomicAdd(&s_hist[wave_sort_key<VOL>(entry, mask)], 1u);
+        // (measured, profiles/r02i_sort_ab.txt: sorted passes +3.4 % on C2, +2.4 % on C1, +5 % on the material zoo; -5 % on C5,
+        // whose shadow queries are multi-leg transmittance walks — `vpt` keeps the single pass)
+        constexpr bool kSort = (PT_WAVE_SORT != 0) && !VOL;
+        if (kSort) {
+            PT_WAVE_SYNC();
+            // box pass: every ray against all group boxes (uniform work), result kept per queue entry; histogram of the sort key
+            PT_WAVE_FOR_THREADS(t) {
+                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) {
+                    const uint32_t entry = s_queue[idx];
+                    f3 o, d; float tmax;
+                    small_ray_fetch(ta, P, entry, o, d, tmax);
+                    unsigned long long mask; int best;
+                    small_ray_boxes(ta, leaves, o, mk3(1.f / d.x, 1.f / d.y, 1.f / d.z), tmax, mask, best);
+                    s_mask[idx] = mask; s_best[idx] = (signed char)best;
+                    atomicAdd(&s_hist[wave_sort_key<VOL>(entry, mask)], 1u);
+                }
             }
+            PT_WAVE_SYNC();
+            PT_WAVE_FOR_THREADS(t) {
+                if (t == 0u) { uint32_t run = 0u; for (int k = 0; k < 32; ++k) { const uint32_t c = s_hist[k]; s_hist[k] = run; run += c; } }
+            }
+            PT_WAVE_SYNC();
+            PT_WAVE_FOR_THREADS(t) {
+                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT)
+                    s_sorted[atomicAdd(&s_hist[wave_sort_key<VOL>(s_queue[idx], s_mask[idx])], 1u)] = (uint16_t)idx;
+            }
+            PT_WAVE_SYNC();
         }
-        PT_WAVE_SYNC();
-        PT_WAVE_FOR_THREADS(t) {
-            if (t == 0u) { uint32_t run = 0u; for (int k = 0; k < 32; ++k) { const uint32_t c = s_hist[k]; s_hist[k] = run; run += c; } }
-        }
-        PT_WAVE_SYNC();
-        PT_WAVE_FOR_THREADS(t) {
-            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT)
-                s_sorted[atomicAdd(&s_hist[wave_sort_key<VOL>(s_queue[idx], s_mask[idx])], 1u)] = (uint16_t)idx;
-        }
-        PT_WAVE_SYNC();
-        // primitive pass in sorted order: the lanes of a warp carry rays of one kind with (nearly) the same number of hit groups
+        // primitive pass — in sorted order the lanes of a warp carry rays of one kind with (nearly) the same number of hit groups
         PT_WAVE_FOR_THREADS(t) {
 #ifdef B200PT_EMULATE
             threadIdx.x = t;
 #endif
             uint32_t nrays = 0;
-            for (uint32_t j = t; j < tail; j += (uint32_t)kT) {
-                const uint32_t idx = s_sorted[j];
-                trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays, true, s_mask[idx], (int)s_best[idx]);
+            if (kSort) {
+                for (uint32_t j = t; j < tail; j += (uint32_t)kT) {
+                    const uint32_t idx = s_sorted[j];
+                    trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays, true, s_mask[idx], (int)s_best[idx]);
+                }
+            } else {
+                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
             }
-#else
-            uint32_t nrays = 0;
-            for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
-#endif
 #ifndef B200PT_EMULATE
             for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
 #endif
