@@ -7,7 +7,7 @@ A "step" = one batch of `spp_per_step` iterations (Render calls) of the workload
 Default workload: C2 = Cornell box 1024x1024, depth 8 (the configuration the metric is quoted on); spp_per_step is 128 per
 GPU — 128 at N = 1 (8 steps are the full 1024-spp config), 128 x N at N GPUs, so the timed region does not shrink as
 GPUs are added (reported as "scaling": "weak": per-GPU work per step is fixed, the image and the scene are the same).
-N > 1 (launched by torchrun, one rank per GPU): the image's 32x32 screen tiles are dealt over the ranks (SURVEY 8(e));
+N > 1 (launched by torchrun, one rank per GPU): the image's 16x16 screen tiles are dealt over the ranks (SURVEY 8(e));
 after every step the float3 accumulation framebuffers are summed onto rank 0 by ONE NCCL reduce over NVLink — inside the
 library (b200pt_render_reduce; torch.distributed only ships the 128-byte NCCL id and the timing scalars) and inside the
 timed region.
@@ -284,7 +284,7 @@ def main():
         W, H = scene.width, scene.height
         npix = W * H
         spp = spp_gpu * world                                  # iterations per step: fixed per-GPU work
-        shard = (rank, world, 32, 32) if world > 1 else None
+        shard = (rank, world, 16, 16) if world > 1 else None      # small tiles: every rank sees a fair sample of the image
         r = pt.PathTracer(scene, device=local, shard=shard, pool=a.pool or None)
         if world > 1:
             # the ONE collective lives in the library: ship the NCCL id (128 bytes) with torch.distributed, then

@@ -67,6 +67,8 @@ struct b200pt_ctx {
     bool lambert_only = false;             // every referenced material is lambertian -> specialised shade kernel
     uint32_t mats_used = 0;                // MaterialTypes referenced by primitives (picks the k_shade instantiation)
     float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
+    bool wide = false;                     // tree kernel walks four-child nodes (WNode4)
+    int n_nodes4 = 0;
     bool small_scene = false;              // use k_trace_small
     bool fused = false;                    // CTA-local wavefront (k_wave_small): one persistent launch per batch and lane
     int wave_blocks = 0;
@@ -248,6 +250,50 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         w.link.y = R.is_leaf ? ~R.start : inner_id[r];
         w.link.z = 0; w.link.w = 0;
     }
+    // -- four-child nodes (opt-in, B200PT_WIDE=1): collapse every other level of the reference tree.  A slot holds a
+    // (grand)child's own box from the reference's array; an inner child is replaced by its two children while slots are
+    // free, largest box first.  Bit-identical images, but measured SLOWER than the two-child records on every scene
+    // (C4 97 vs 101 Msamples/s, C3 405 vs 432, hair 356 vs 368: profiles/r02m_wide.txt) — the traversal is bound by
+    // instruction issue, not by dependent node fetches, and four exact slab tests per visit test ~1.4x the boxes.
+    std::vector<WNode4> wn4;
+    const char* wide_env = getenv("B200PT_WIDE");
+    if (n_inner > 0 && wide_env && atoi(wide_env) != 0) {
+        auto area_of = [&](int i) {
+            const double dx = (double)nodes[i].fmax[0] - nodes[i].fmin[0], dy = (double)nodes[i].fmax[1] - nodes[i].fmin[1], dz = (double)nodes[i].fmax[2] - nodes[i].fmin[2];
+            return dx * dy + dy * dz + dz * dx;
+        };
+        std::vector<int> q4{0};                         // reference indices of the inner nodes that become WNode4 records, BFS
+        std::vector<int> id4(v->n_nodes, -1);
+        id4[0] = 0;
+        for (size_t hq = 0; hq < q4.size(); ++hq) {
+            const int i = q4[hq];
+            int kids[4] = {i + 1, nodes[i].second_child_offset, -1, -1};
+            int nk = 2;
+            while (nk < 4) {
+                int pick = -1; double best = -1.0;
+                for (int k = 0; k < nk; ++k)
+                    if (!nodes[kids[k]].is_leaf) { const double ar = area_of(kids[k]); if (ar > best) { best = ar; pick = k; } }
+                if (pick < 0) break;
+                const int e = kids[pick];
+                kids[pick] = e + 1; kids[nk++] = nodes[e].second_child_offset;
+            }
+            WNode4 w;
+            std::memset(&w, 0, sizeof(w));
+            float* mn[3] = {&w.minx.x, &w.miny.x, &w.minz.x}; float* mx[3] = {&w.maxx.x, &w.maxy.x, &w.maxz.x};
+            int* lk = &w.link.x;
+            for (int k = 0; k < 4; ++k) {
+                if (k >= nk) { lk[k] = kEmptyChild; continue; }
+                const RefLinearBVHNode& ch = nodes[kids[k]];
+                for (int ax = 0; ax < 3; ++ax) { mn[ax][k] = ch.fmin[ax]; mx[ax][k] = ch.fmax[ax]; }
+                if (ch.is_leaf) lk[k] = ~ch.start;
+                else { id4[kids[k]] = (int)q4.size(); lk[k] = (int)q4.size(); q4.push_back(kids[k]); }
+            }
+            wn4.push_back(w);
+        }
+        // (links were assigned in BFS order, records were appended in BFS order: record j describes q4[j])
+    }
+    c->n_nodes4 = (int)wn4.size();
+
     // primitive groups for k_trace_small (<= 256 primitives): greedy agglomeration of tight primitive boxes under the
     // cost model  cost(group) = C_BOX + P(ray hits box) * C_PRIM * |group|,  P ~ surface area of the box / root's
     if (v->n_prims <= 256) {
@@ -325,6 +371,13 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     if ((rc = dev_upload(c, &d_prims, wp.data(), wp.size()))) return rc;
     if ((rc = dev_upload(c, &d_shade, ws.data(), ws.size()))) return rc;
     sc.nodes = d_nodes; sc.prims = d_prims; sc.shade = d_shade;
+    sc.nodes4 = nullptr;
+    if (!wn4.empty()) {
+        WNode4* d_nodes4;
+        if ((rc = dev_upload(c, &d_nodes4, wn4.data(), wn4.size()))) return rc;
+        sc.nodes4 = d_nodes4;
+    }
+    c->wide = sc.nodes4 != nullptr;
     PT_LAUNCH(k_prepare_shade, (v->n_prims + 255) / 256, 256, 0, c->stream, d_shade, d_prims, v->n_prims);
 
     // -- lights
@@ -440,7 +493,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
 
     // staging of the acceleration structure into shared memory (TMA bulk copy): only when small
     // (TMA bulk copy): everything when the scene is small, else the top of the breadth-first node array
-    size_t nb = (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
+    size_t nb = c->wide ? (size_t)c->n_nodes4 * sizeof(WNode4) : (size_t)n_inner * sizeof(WNode), pb = (size_t)v->n_prims * sizeof(WPrim);
     // (k_trace also keeps 24 KB of traversal stack in shared memory; 20 KB of structure keeps 5 CTAs per SM resident)
     if (const char* env = getenv("B200PT_STAGE_BYTES")) c->stage_top_bytes = (size_t)std::max(0, atoi(env));
     c->stage_top_bytes = std::min<size_t>(c->stage_top_bytes, 200 * 1024 - kTraceStackBytes) & ~(size_t)63;   // 227 KB per CTA on sm_100
@@ -452,6 +505,11 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     return 0;
 }
 
+// k_trace instantiation for this context (volumetric or not, two- or four-child nodes)
+template <class F> static void with_trace_kernel(const b200pt_ctx* c, F&& f) {
+    if (c->vol) { if (c->wide) f(k_trace<true, true>); else f(k_trace<true, false>); }
+    else { if (c->wide) f(k_trace<false, true>); else f(k_trace<false, false>); }
+}
 // k_wave_small instantiation for this context (volumetric or not, referenced material set, heterogeneous media)
 template <class F> static void with_wave_kernel(const b200pt_ctx* c, F&& f) {
     const bool ldc = (c->mats_used & ~kMatsLDC) == 0u;
@@ -622,15 +680,13 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
         smem = (size_t)c->small_prim_bytes + (size_t)c->n_leaves * 32;
         if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_small<true>, kTraceThreads, smem);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_small<false>, kTraceThreads, smem);
-    } else if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
+    } else with_trace_kernel(c, [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceThreads, smem); });
 #ifndef B200PT_EMULATE
     if (smem > 48 * 1024) {      // above the default dynamic shared-memory limit: opt in, then ask again
-        cudaError_t e = c->vol ? cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                               : cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaSuccess;
+        with_trace_kernel(c, [&](auto kernel) { e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         if (e != cudaSuccess) return bail(fail(B200PT_ECUDA, std::string("shared-memory opt-in failed: ") + cudaGetErrorString(e)));
-        if (c->vol) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceThreads, smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, smem);
+        with_trace_kernel(c, [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceThreads, smem); });
     }
 #endif
     if (per_sm <= 0) per_sm = 1;
@@ -672,6 +728,8 @@ extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_val
     else if (n == "small_kernel") *out_value = c->small_scene ? 1 : 0;
     else if (n == "lambert_only") *out_value = c->lambert_only ? 1 : 0;
     else if (n == "fused") *out_value = c->fused ? 1 : 0;
+    else if (n == "wide") *out_value = c->wide ? 1 : 0;
+    else if (n == "nodes4") *out_value = c->n_nodes4;
     else if (n == "wave_blocks") *out_value = c->wave_blocks;
     else return fail(B200PT_EINVAL, "unknown info " + n);
     return 0;
@@ -751,8 +809,7 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
         return;
     }
     const size_t smem = (size_t)c->stage_nodes + c->stage_prims + kTraceStackBytes;
-    if (c->vol) PT_LAUNCH(k_trace<true>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
-    else PT_LAUNCH(k_trace<false>, c->trace_blocks, kTraceThreads, smem, L.stream, ta);
+    with_trace_kernel(c, [&](auto kernel) { PT_LAUNCH(kernel, c->trace_blocks, kTraceThreads, smem, L.stream, ta); });
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;

@@ -148,9 +148,11 @@ constexpr size_t kTraceStackBytes = (size_t)kSmemStack * kTraceThreads * 8;
 // Nodes are numbered breadth-first; the first `stage_bytes_nodes / 64` of them (the top of the tree, or the whole
 // tree for small scenes) and, when they fit, all primitive records are staged into shared memory by one TMA bulk
 // copy per CTA.  Everything else is read from L2/HBM with 16-byte vector loads.
-template <bool VOL>
+// WIDE: four-child nodes (WNode4) instead of two-child ones.
+template <bool VOL, bool WIDE>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
     const WNode* __restrict__ gnodes = a.sc.nodes;
+    const WNode4* __restrict__ gnodes4 = a.sc.nodes4;
     const WPrim* __restrict__ gprims = a.sc.prims;
     int n_staged = 0;
     bool prims_staged = false;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const WNode* s_nodes = reinterpret_cast<const WNode*>(smem_raw);
+    const WNode4* s_nodes4 = reinterpret_cast<const WNode4*>(smem_raw);
     const WPrim* s_prims = reinterpret_cast<const WPrim*>(smem_raw + a.stage_bytes_nodes);
     if (a.stage_bytes_nodes + a.stage_bytes_prims > 0) {
         if (threadIdx.x == 0) {
@@ -167,11 +170,11 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, a.stage_bytes_nodes + a.stage_bytes_prims);
-            if (a.stage_bytes_nodes) tma_bulk_g2s(smem_raw, a.sc.nodes, a.stage_bytes_nodes, &bar);
+            if (a.stage_bytes_nodes) tma_bulk_g2s(smem_raw, WIDE ? (const void*)a.sc.nodes4 : (const void*)a.sc.nodes, a.stage_bytes_nodes, &bar);
             if (a.stage_bytes_prims) tma_bulk_g2s(smem_raw + a.stage_bytes_nodes, a.sc.prims, a.stage_bytes_prims, &bar);
         }
         mbar_wait(&bar, 0);
-        n_staged = (int)(a.stage_bytes_nodes / sizeof(WNode));
+        n_staged = (int)(a.stage_bytes_nodes / (WIDE ? sizeof(WNode4) : sizeof(WNode)));
         prims_staged = a.stage_bytes_prims > 0;
     }
 #endif
@@ -259,7 +262,30 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                 // reaches is POSTPONED and the lane keeps descending speculatively while any other lane of the warp
                 // is still looking for its leaf, so the (expensive) primitive tests start with most lanes on board.
                 for (;;) {
-                    if (cur >= 0) {
+                    if (WIDE && cur >= 0) {
+                        // four child boxes per 128-B record: the reference's slab test on each, hits ordered near to far,
+                        // the far ones pushed (farthest first), the nearest visited next
+                        const float4* np = reinterpret_cast<const float4*>(gnodes4 + cur);
+#ifndef B200PT_EMULATE
+                        if (cur < n_staged) np = reinterpret_cast<const float4*>(s_nodes4 + cur);
+#endif
+                        const float4 mnx = np[0], mny = np[1], mnz = np[2], mxx = np[3], mxy = np[4], mxz = np[5];
+                        const int4 lk = *reinterpret_cast<const int4*>(np + 6);
+                        float t0 = INFINITY, t1 = INFINITY, t2 = INFINITY, t3 = INFINITY, tn;
+                        int c0 = lk.x, c1 = lk.y, c2 = lk.z, c3 = lk.w, n = 0;
+                        if (lk.x != kEmptyChild && slab(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, tmax, tn)) { t0 = fminf(tn, 3.0e38f); ++n; }
+                        if (lk.y != kEmptyChild && slab(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, tmax, tn)) { t1 = fminf(tn, 3.0e38f); ++n; }
+                        if (lk.z != kEmptyChild && slab(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, tmax, tn)) { t2 = fminf(tn, 3.0e38f); ++n; }
+                        if (lk.w != kEmptyChild && slab(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, tmax, tn)) { t3 = fminf(tn, 3.0e38f); ++n; }
+#define PT_CAS(ta, ca, tb, cb) { if (tb < ta) { const float f_ = ta; ta = tb; tb = f_; const int i_ = ca; ca = cb; cb = i_; } }
+                        PT_CAS(t0, c0, t1, c1) PT_CAS(t2, c2, t3, c3) PT_CAS(t0, c0, t2, c2) PT_CAS(t1, c1, t3, c3) PT_CAS(t1, c1, t2, c2)
+#undef PT_CAS
+                        if (n > 3) STK_PUSH(c3, t3);
+                        if (n > 2) STK_PUSH(c2, t2);
+                        if (n > 1) STK_PUSH(c1, t1);
+                        cur = n ? c0 : kPop;
+                    }
+                    if (!WIDE && cur >= 0) {
                         float4 q0, q1, q2; int2 link;
 #ifndef B200PT_EMULATE
                         if (cur < n_staged) {

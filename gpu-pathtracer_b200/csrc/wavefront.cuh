@@ -22,6 +22,14 @@ struct WNode { float4 q0, q1, q2; int4 link; };
 static_assert(sizeof(WNode) == 64, "WNode");
 constexpr int kEmptyChild = 0x7fffffff;
 
+// Four-child node, 128 B: the boxes of up to four (grand)children of a reference node, structure-of-arrays so that each
+// plane is one 16-byte load, plus their links (same encoding as WNode).  Built by collapsing every other level of the
+// reference's binary tree (b200pt_api.cu: build_scene): a child box is inside its parent's box and BBox::Intersect is
+// monotonic in the box, so a ray that passes a grandchild's test passes the skipped child's test as well — the SAME
+// primitives reach the exact primitive test, with half the dependent node fetches per ray.
+struct WNode4 { float4 minx, miny, minz, maxx, maxy, maxz; int4 link; int4 _pad; };
+static_assert(sizeof(WNode4) == 128, "WNode4");
+
 // Intersection record per primitive (leaf order), 48 B: v0, e1 = v1-v0, e2 = v2-v0 for Moeller-Trumbore
 // (src/mesh.h:45-66 recomputes the edges per test from a 176-B Primitive), or centre+radius for a sphere, or the
 // end points and radii of a hair segment (src/line.h:8).
@@ -68,7 +76,7 @@ struct WInfinite {                  // src/infinite.h:6 with a device texel poin
 };
 
 struct SceneDev {
-    const WNode* nodes; const WPrim* prims; const WShade* shade; const WLight* lights;
+    const WNode* nodes; const WNode4* nodes4; const WPrim* prims; const WShade* shade; const WLight* lights;
     const Material* mats; const WMedium* mediums; const float* cdf;
     const unsigned char* texels;    // all uchar4 textures back to back (src/texture.h:9)
     const int4* tex_info;           // per texture: {first texel, width, height, -}
@@ -183,10 +191,11 @@ struct ShardMap {
     const uint32_t* tiles;          // [n_local_tiles] (device memory); unused when n_shards == 1
 };
 // Owner of tile k (row-major tile index).  Every group of n consecutive tiles holds one tile of each shard, and the
-// assignment inside a group rotates by 3 from group to group: a shard's tiles are spread over columns AND rows.
-// (Plain k % n gave each of 8 ranks four fixed COLUMNS of a 32-tile-wide image — shard 3 of the Cornell box needed
-// 9 % longer than shard 0, which was most of the 1 -> 8 GPU scaling loss of round 1, profiles/r02b_shard_tax.txt.)
-PT_HD int shard_owner(int k, int n) { return (k % n + (k / n) * 3) % n; }
+// assignment inside a group is rotated by a HASH of the group index: a shard's tiles are scattered over the image
+// without any period.  (Plain k % n gave each of 8 ranks four fixed COLUMNS of a 32-tile-wide image — shard 3 of the
+// Cornell box needed 9 % longer than shard 0, most of the 1 -> 8 GPU scaling loss of round 1; a fixed rotation of 3 per
+// group still left a two-row period and 3 %: profiles/r02b_shard_tax.txt, r02l_shard_balance.txt.)
+PT_HD int shard_owner(int k, int n) { return (int)(((uint32_t)(k % n) + wang_hash((uint32_t)(k / n)) % (uint32_t)n) % (uint32_t)n); }
 // local pixel index -> global pixel (x, y). Local order: tile-major, row-major inside the tile.
 __device__ __forceinline__ void local_to_xy(const ShardMap& m, uint32_t local, uint32_t& x, uint32_t& y) {
     if (m.n_shards == 1) { x = local % (uint32_t)m.width; y = local / (uint32_t)m.width; return; }

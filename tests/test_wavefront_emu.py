@@ -263,6 +263,23 @@ def test_cta_local_and_global_wavefront_give_the_same_bits(name, emu, monkeypatc
         assert a[3] == b[3] and 0 <= b[2] - a[2] <= 0.2 * a[2]           # (the global wavefront traces spare rays for slots that die on an exhausted batch)
 
 
+@pytest.mark.parametrize("name", ["veach", "random_tris", "textured_hair"])
+def test_four_child_nodes_give_the_same_bits(name, emu, oracle, monkeypatch):
+    """B200PT_WIDE=1: the tree kernel walks four-child records (every other level of the reference's tree collapsed).  The
+    slab test is monotone in the box, so the same primitives reach the exact primitive test: same bits."""
+    s = SCENES[name]()
+    ref_acc, _ = oracle.render(s, 1, 3)
+    rays = []
+    for wide in (0, 1):
+        monkeypatch.setenv("B200PT_WIDE", str(wide))
+        with pt.PathTracer(s) as r:
+            assert r.info("wide") == wide and (r.info("nodes4") > 0) == bool(wide)
+            r.render(1, reset=True, spp=3)
+            assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+            rays.append(r.stats()["rays"])
+    assert abs(rays[0] - rays[1]) <= 0.01 * rays[0]       # (spare rays of slots that die on an exhausted batch depend on the CTA schedule)
+
+
 @pytest.mark.parametrize("estimator", [0, 1, 2])
 @pytest.mark.parametrize("mode", ["cta_local", "global_small", "global_tree"])
 def test_heterogeneous_media_coroutine_equals_oracle(estimator, mode, emu, oracle, monkeypatch):
