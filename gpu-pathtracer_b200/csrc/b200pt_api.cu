@@ -68,6 +68,7 @@ struct b200pt_ctx {
     uint32_t mats_used = 0;                // MaterialTypes referenced by primitives (picks the k_shade instantiation)
     float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
     bool wide = false;                     // tree kernel walks four-child nodes (WNode4)
+    bool bin_materials = false;            // k_shade sorts its tile's records by material (scenes with more than one BSDF)
     int n_nodes4 = 0;
     bool small_scene = false;              // use k_trace_small
     bool fused = false;                    // CTA-local wavefront (k_wave_small): one persistent launch per batch and lane
@@ -406,6 +407,23 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
         if (m >= 0) c->mats_used |= 1u << (mats[m].type & 31);
     }
     c->lambert_only = (c->mats_used & ~kMatsLambertOnly) == 0u;
+    {   // shade-stage sort key per primitive (k_shade's material binning)
+        std::vector<unsigned char> key((size_t)std::max(v->n_prims, 1));
+        for (int i = 0; i < v->n_prims; ++i) {
+            const int m = ws[i].matIdx;
+            key[i] = (unsigned char)((m < 0 ? 7 : std::min(mats[m].type & 31, 6)) + (ws[i].lightIdx >= 0 ? 8 : 0));
+        }
+        unsigned char* d_key;
+        if ((rc = dev_upload(c, &d_key, key.data(), key.size()))) return rc;
+        sc.prim_key = d_key;
+    }
+    // measured (profiles/r02n_bin_chunk.txt): six BSDFs in one scene 102 -> 221 Msamples/s (`pt`), 120 -> 214 (`vpt`) in the
+    // CTA-local kernel; with two BSDFs (C5: lambertian walls + one glass sphere) the sort costs 5 %; the HBM-pool k_shade
+    // of C3 / the hair scene is bound by its pool round trip, not by divergence, and does not move (426 vs 425, 368 vs 368)
+    int n_types = 0;
+    for (uint32_t m = c->mats_used; m; m &= m - 1u) ++n_types;
+    c->bin_materials = n_types >= 3;
+    if (const char* env = getenv("B200PT_BIN_MATERIALS")) c->bin_materials = !c->lambert_only && atoi(env) != 0;
     std::vector<WMedium> wm(std::max(v->n_mediums, 1));
     std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
     const RefMedium* med = (const RefMedium*)v->mediums;
@@ -728,6 +746,7 @@ extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_val
     else if (n == "small_kernel") *out_value = c->small_scene ? 1 : 0;
     else if (n == "lambert_only") *out_value = c->lambert_only ? 1 : 0;
     else if (n == "fused") *out_value = c->fused ? 1 : 0;
+    else if (n == "bin_materials") *out_value = c->bin_materials ? 1 : 0;
     else if (n == "wide") *out_value = c->wide ? 1 : 0;
     else if (n == "nodes4") *out_value = c->n_nodes4;
     else if (n == "wave_blocks") *out_value = c->wave_blocks;
@@ -773,6 +792,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
     if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr; if (!c->small_scene) c->fused = false; return 0; }
+    if (n == "bin_materials") { c->bin_materials = value != 0 && !c->lambert_only; return 0; }
     if (n == "fused") { c->fused = value != 0 && c->small_scene && c->wave_blocks > 0; return 0; }
     if (n == "wave_ctas_per_sm") { if (value < 1 || value > 8) return fail(B200PT_EINVAL, "wave_ctas_per_sm out of range"); c->wave_blocks = c->num_sms * (int)value; return 0; }
     if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; c->fused = false; } return 0; }
@@ -813,7 +833,7 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
     ShadeArgs& sa = L.sa; TraceArgs& ta = L.ta;
-    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0;
+    sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0; sa.bin_materials = c->bin_materials ? 1 : 0;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
     ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves; ta.sec_tmax = c->het ? 1 : 0;
 }

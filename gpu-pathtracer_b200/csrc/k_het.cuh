@@ -231,7 +231,10 @@ __device__ __forceinline__ bool het_sample_chunk(const WMedium& M, const WHetero
     }
     return false;
 }
-constexpr int kTrackChunk = 16;                  // tracking steps per wavefront step and slot (CTA-local kernel)
+#ifndef PT_TRACK_CHUNK
+#define PT_TRACK_CHUNK 16
+#endif
+constexpr int kTrackChunk = PT_TRACK_CHUNK;                  // tracking steps per wavefront step and slot (CTA-local kernel)
 
 // ---- the coroutine ------------------------------------------------------------------------------------------------------
 // Slot record (the wavefront's own planes, re-used):

@@ -29,6 +29,7 @@ struct ShadeArgs {
     BatchParams batch;
     const FrameParams* frame;  // non-null inside a captured frame: camera and first_iter come from here
     int32_t drain_hint;        // the host saw the sample counter exhausted: dead tiles may leave early
+    int32_t bin_materials;     // k_shade: thread j takes the j-th record of the CTA's tile in material order (see k_shade)
 };
 
 // One slot's record as the shade stage reads it (13 planes, 14 for vpt).
@@ -221,6 +222,7 @@ template <bool FUSED> __device__ __forceinline__ void st_rec(float4* p, float4 v
 constexpr uint32_t kMatsLambertOnly = 1u << MT_LAMBERTIAN;
 constexpr uint32_t kMatsLDC = (1u << MT_LAMBERTIAN) | (1u << MT_DIELECTRIC) | (1u << MT_ROUGHCONDUCTOR);   // e.g. veach_bidir
 constexpr uint32_t kMatsAll = 0x3fu;
+constexpr uint32_t kShadeKeys = 18u;       // k_shade's sort keys: dead, miss, 2 + SceneDev::prim_key (0..15)
 
 // SampleBSDF / Fr restricted to the material types in MATS: each enabled type is dispatched with a compile-time
 // constant, so the switch inside sample_bsdf / eval_bsdf folds to that one case and the others are never emitted.
@@ -683,17 +685,45 @@ __global__ void __launch_bounds__(128, (VOL || MATS == kMatsAll) ? 6 : 8) k_shad
     }
     __syncthreads();                       // the barrier object is initialised before anyone polls it
     mbar_wait(&bar, 0);
+    // ---------------------------------------------------------------- material binning (north_star's "sorted by BSDF"):
+    // a scene with several BSDFs runs every material's code in every warp, each with a fraction of the lanes, and the
+    // instruction stream of the all-materials kernel does not fit the instruction cache (`no_instruction` stalls).  The
+    // tile's 128 records are already in shared memory, so a counting sort costs three barriers: key = dead / miss /
+    // material type of the hit primitive (+ emitter), one byte per primitive prepared by the host (SceneDev::prim_key —
+    // a single gather, not the primitive -> material -> type chain), and thread j shades the j-th record in key order.
+    // The slot a record belongs to — its pool address, sample and random-number stream — does not change; only which lane runs it.
+    uint32_t t = threadIdx.x;
+    if (MATS != kMatsLambertOnly && a.bin_materials) {
+        __shared__ uint32_t s_cnt[kShadeKeys];
+        __shared__ unsigned char s_order[128];
+        if (threadIdx.x < kShadeKeys) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t f = __float_as_uint(s_rec[0][t].w);
+        const float4 h0 = s_rec[4][t];
+        const uint32_t prim = __float_as_uint(h0.y);
+        uint32_t key = 0u;                                                               // dead: regenerate or idle
+        if (f & F_ALIVE) key = (h0.x < 0.f || prim >= (uint32_t)a.sc.n_prims) ? 1u : 2u + a.sc.prim_key[prim];
+        const uint32_t rank = atomicAdd(&s_cnt[key], 1u);
+        __syncthreads();
+        uint32_t base = 0u;
+        for (uint32_t k = 0; k < key; ++k) base += s_cnt[k];
+        s_order[base + rank] = (unsigned char)t;
+        __syncthreads();
+        t = s_order[threadIdx.x];
+    }
+    const uint32_t my = blockIdx.x * blockDim.x + t;
     SlotRec r;
-    r.df = s_rec[0][threadIdx.x]; r.orng = s_rec[1][threadIdx.x]; r.bs = s_rec[2][threadIdx.x]; r.lt4 = s_rec[3][threadIdx.x];
-    r.h0 = s_rec[4][threadIdx.x]; r.bo = s_rec[5][threadIdx.x]; r.pv = s_rec[6][threadIdx.x]; r.pl = s_rec[7][threadIdx.x];
-    r.pmd = s_rec[8][threadIdx.x]; r.pmf = s_rec[9][threadIdx.x]; r.h1 = s_rec[10][threadIdx.x];
-    r.po = s_rec[11][threadIdx.x]; r.cy = s_rec[12][threadIdx.x];
-    r.pax = VOL ? s_rec[kArrays - 1][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.df = s_rec[0][t]; r.orng = s_rec[1][t]; r.bs = s_rec[2][t]; r.lt4 = s_rec[3][t];
+    r.h0 = s_rec[4][t]; r.bo = s_rec[5][t]; r.pv = s_rec[6][t]; r.pl = s_rec[7][t];
+    r.pmd = s_rec[8][t]; r.pmf = s_rec[9][t]; r.h1 = s_rec[10][t];
+    r.po = s_rec[11][t]; r.cy = s_rec[12][t];
+    r.pax = VOL ? s_rec[kArrays - 1][t] : make_float4(0.f, 0.f, 0.f, 0.f);
 #else
+    const uint32_t my = slot;
     SlotRec r;
-    load_slot<VOL>(a.pool, slot, r);
+    load_slot<VOL>(a.pool, my, r);
 #endif
-    shade_slot<VOL, MATS, false>(a, a.pool, a.q, a.parity, nullptr, nullptr, slot, slot, (uint32_t)a.pool.n, r, a.counters->next_sample);
+    shade_slot<VOL, MATS, false>(a, a.pool, a.q, a.parity, nullptr, nullptr, my, my, (uint32_t)a.pool.n, r, a.counters->next_sample);
 }
 
 // ---- Output (src/pathtracer.cu:2516-2531) over a whole batch of iterations -------------------------------

@@ -86,6 +86,20 @@ __device__ __forceinline__ uint32_t het_sort_key(const Pool& P, uint32_t slot) {
     return st * 2u + (med != 0u ? 1u : 0u);
 }
 
+// Sort key of a slot for the shade phase of a scene with several BSDFs (material binning, see k_shade): dead slots, misses,
+// then the material class of the hit primitive; `vpt` paths inside a medium (free-flight sampling, phase function) form
+// a second set of classes.
+template <bool VOL>
+__device__ __forceinline__ uint32_t wave_shade_key(const Pool& P, const SceneDev& sc, uint32_t slot) {
+    const uint32_t f = __float_as_uint(P.d_flags[slot].w);
+    if (!(f & F_ALIVE)) return 0u;
+    const float4 h0 = P.hit0[slot];
+    const uint32_t prim = __float_as_uint(h0.y);
+    uint32_t key = (h0.x < 0.f || prim >= (uint32_t)sc.n_prims) ? 1u : 2u + (sc.prim_key[prim] & 7u);
+    if (VOL && ((f >> kMediumShift) & 0xffu) != 0u) key = (key == 1u ? 9u : key) + 8u;
+    return key;
+}
+
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
 __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3)) k_wave_small(const WaveArgs a) {
@@ -205,17 +219,37 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
             }
             PT_WAVE_SYNC();
         }
-    } else
+    } else {
+    // material binning (scenes with several BSDFs): thread j shades the j-th slot in material order — same counting sort
+    __shared__ uint32_t s_mcnt[kShadeKeys], s_mpos[kShadeKeys];
+    __shared__ uint16_t s_morder[kT];
+    const bool bin = MATS != kMatsLambertOnly && sa.bin_materials != 0;
+    if (bin) {
+        PT_WAVE_FOR_THREADS(t) { if (t < kShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; } }
+        PT_WAVE_SYNC();
+    }
     for (uint32_t step = 0;; ++step) {
         const uint32_t par = step & 1u;
+        if (bin) {
+            PT_WAVE_FOR_THREADS(t) { atomicAdd(&s_mcnt[wave_shade_key<VOL>(P, sa.sc, t)], 1u); }
+            PT_WAVE_SYNC();
+            PT_WAVE_FOR_THREADS(t) {
+                const uint32_t key = wave_shade_key<VOL>(P, sa.sc, t);
+                uint32_t base = 0u;
+                for (uint32_t k = 0; k < key; ++k) base += s_mcnt[k];
+                s_morder[base + atomicAdd(&s_mpos[key], 1u)] = (uint16_t)t;
+            }
+            PT_WAVE_SYNC();
+        }
         // ---- shade phase
         PT_WAVE_FOR_THREADS(t) {
 #ifdef B200PT_EMULATE
             threadIdx.x = t;
 #endif
+            const uint32_t slot = bin ? (uint32_t)s_morder[t] : t;
             SlotRec r;
-            load_slot<VOL>(P, t, r);
-            shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], t, blockIdx.x * (uint32_t)kT + t, pool_n, r, s_next);
+            load_slot<VOL>(P, slot, r);
+            shade_slot<VOL, MATS, true>(sa, P, Q, par, &s_retired, &s_busy[par], slot, blockIdx.x * (uint32_t)kT + slot, pool_n, r, s_next);
         }
         PT_WAVE_SYNC();
         const uint32_t tail = s_ctl.tail[par];
@@ -224,6 +258,7 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
         PT_WAVE_FOR_THREADS(t) {
             if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
             if (t < 32u) s_hist[t] = 0u;
+            if (bin && t < kShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; }
         }
         // (measured, profiles/r02i_sort_ab.txt: sorted passes +3.4 % on C2, +2.4 % on C1, +5 % on the material zoo; -5 % on C5,
         // whose shadow queries are multi-leg transmittance walks — `vpt` keeps the single pass)
@@ -273,6 +308,7 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
             if (pt_lane() == 0u && nrays) atomicAdd(&s_rays, nrays);
         }
         PT_WAVE_SYNC();
+    }
     }
     // ---- per-CTA statistics: one atomic each
     PT_WAVE_FOR_THREADS(t) {

@@ -86,6 +86,7 @@ struct SceneDev {
     int32_t root_leaf_count;        // > 0 when the whole scene is a single leaf (no inner node)
     int32_t integrator, max_depth;
     float eps;
+    const unsigned char* prim_key;  // per primitive: shade-stage sort key (material type, +8 for an emitter; 7 = no material)
     const WHetero* het;             // non-null when some medium is heterogeneous (then k_volpath_seq renders the scene)
 };
 

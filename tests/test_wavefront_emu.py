@@ -263,6 +263,24 @@ def test_cta_local_and_global_wavefront_give_the_same_bits(name, emu, monkeypatc
         assert a[3] == b[3] and 0 <= b[2] - a[2] <= 0.2 * a[2]           # (the global wavefront traces spare rays for slots that die on an exhausted batch)
 
 
+@pytest.mark.parametrize("name", ["material_zoo_pt", "material_zoo_vpt", "vol_caustic", "veach"])
+def test_material_binning_does_not_change_the_image(name, emu, oracle, monkeypatch):
+    """The shade stage may run a CTA's slots in material order (counting sort by dead / miss / BSDF class of the hit
+    primitive): which lane runs a slot changes, the slot's sample, random-number stream and arithmetic do not.  On by
+    default for scenes with three or more BSDF types."""
+    s = SCENES[name]()
+    ref_acc, _ = oracle.render(s, 1, 3)
+    monkeypatch.delenv("B200PT_BIN_MATERIALS", raising=False)
+    with pt.PathTracer(s) as r:
+        assert r.info("bin_materials") == (0 if name == "vol_caustic" else 1)
+    for on in (0, 1):
+        monkeypatch.setenv("B200PT_BIN_MATERIALS", str(on))
+        with pt.PathTracer(s) as r:
+            assert r.info("bin_materials") == on
+            r.render(1, reset=True, spp=3)
+            assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+
+
 @pytest.mark.parametrize("name", ["veach", "random_tris", "textured_hair"])
 def test_four_child_nodes_give_the_same_bits(name, emu, oracle, monkeypatch):
     """B200PT_WIDE=1: the tree kernel walks four-child records (every other level of the reference's tree collapsed).  The
