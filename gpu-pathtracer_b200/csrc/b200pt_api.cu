@@ -423,7 +423,7 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     int n_types = 0;
     for (uint32_t m = c->mats_used; m; m &= m - 1u) ++n_types;
     c->bin_materials = n_types >= 3;
-    if (const char* env = getenv("B200PT_BIN_MATERIALS")) c->bin_materials = !c->lambert_only && atoi(env) != 0;
+    if (const char* env = getenv("B200PT_BIN_MATERIALS")) c->bin_materials = atoi(env) != 0;
     std::vector<WMedium> wm(std::max(v->n_mediums, 1));
     std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
     const RefMedium* med = (const RefMedium*)v->mediums;
@@ -792,7 +792,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
     if (n == "trace_ctas_per_sm") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "trace_ctas_per_sm out of range"); c->trace_blocks = c->num_sms * (int)value; return 0; }
     if (n == "refill_below") { if (value < 1 || value > 32) return fail(B200PT_EINVAL, "refill_below must be in [1, 32]"); c->refill_below = (int)value; return 0; }
     if (n == "small_kernel") { c->small_scene = value != 0 && c->leaves != nullptr; if (!c->small_scene) c->fused = false; return 0; }
-    if (n == "bin_materials") { c->bin_materials = value != 0 && !c->lambert_only; return 0; }
+    if (n == "bin_materials") { c->bin_materials = value != 0; return 0; }
     if (n == "fused") { c->fused = value != 0 && c->small_scene && c->wave_blocks > 0; return 0; }
     if (n == "wave_ctas_per_sm") { if (value < 1 || value > 8) return fail(B200PT_EINVAL, "wave_ctas_per_sm out of range"); c->wave_blocks = c->num_sms * (int)value; return 0; }
     if (n == "stage_smem") { if (!value) { c->stage_nodes = c->stage_prims = 0; c->small_scene = false; c->fused = false; } return 0; }

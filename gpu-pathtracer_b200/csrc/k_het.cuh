@@ -157,79 +157,55 @@ __device__ __noinline__ f3 medium_sample(const SceneDev& sc, int medium, f3 o, f
 // been re-sorted — continues where it stopped.  Same operations on the same values in the same order as het_tr /
 // medium_sample above (the random-number stream is the path's own and is saved with the slot).
 struct TrackState { float dist, tr; int iter; };
-__device__ __forceinline__ bool het_tr_chunk(const WMedium& M, const WHetero& H, f3 o, f3 dir, float tmax, uint32_t& rng, TrackState& k,
-                                             int max_steps, f3& result) {
+// Both loops as ONE: mode 0 = free-flight sampling (medium_sample's loop), 1 + evalTransmittanceType = transmittance
+// (het_tr's three estimators).  The distance update, the grid lookup and the iteration budget — 4/5 of a tracking
+// step's instructions — are the same code for every mode, so slots that track for different reasons (the path's free
+// flight, a shadow leg, a medium-scatter shadow leg) share the lanes of a warp; what a mode does with the density is a
+// few instructions behind a branch.  Same operations on the same values in the same order as het_tr / medium_sample above.
+// `reason` on return: 0 = budget of this call used up (resume later), 1 = reached tmax, 2 = collision / roulette kill,
+// 3 = iteration limit of the medium.
+enum { TRK_SAMPLE = 0, TRK_TR0 = 1, TRK_TR1 = 2, TRK_TR2 = 3 };
+__device__ __forceinline__ int het_track_chunk(const WMedium& M, const WHetero& H, const int mode, f3 o, f3 dir, float tmax, uint32_t& rng,
+                                               TrackState& k, int max_steps) {
     float sigma = dot(ld3(M.sigmaT), mk3(0.212671f, 0.715160f, 0.072169f));
     const f3 p0 = ld3(H.p0);
     f3 d = ld3(H.p1) - p0;
-    if (H.evalTransmittanceType == 0) {
-        for (int s_ = 0; s_ < max_steps; ++s_) {
-            k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
-            if (k.dist >= tmax) { result = mk3(k.tr, k.tr, k.tr); return true; }
-            f3 p = o + dir * k.dist;
-            p = (p - p0) / d;
-            if (het_density(H, p) * H.invMaxDensity > rng_next(rng)) { result = mk3(0.f, 0.f, 0.f); return true; }
-            if (--k.iter == 0) { result = mk3(0.f, 0.f, 0.f); return true; }
-        }
-        return false;
-    }
-    if (H.evalTransmittanceType == 1) {
-        for (int s_ = 0; s_ < max_steps; ++s_) {
-            k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
-            if (k.dist >= tmax) { result = mk3(k.tr, k.tr, k.tr); return true; }
-            f3 p = o + dir * k.dist;
-            p = (p - p0) / d;
-            k.tr *= 1.f - het_density(H, p) * H.invMaxDensity;
-            if (k.tr < 0.1f) {
-                float q = 1.f - k.tr;
-                if (rng_next(rng) < q) { result = mk3(0.f, 0.f, 0.f); return true; }
-                k.tr = 1;
-            }
-            if (--k.iter == 0) { result = mk3(k.tr, k.tr, k.tr); return true; }
-        }
-        return false;
-    }
     float maxDensity = 1 / H.invMaxDensity;
     float ce = 0.5f * maxDensity;
     for (int s_ = 0; s_ < max_steps; ++s_) {
-        bool end = false;
-        k.dist += -logf(rng_next(rng)) * (1 / (maxDensity - ce) / sigma);
-        if (k.dist >= tmax) end = true;
-        else {
-            f3 p = o + dir * k.dist;
-            p = (p - p0) / d;
-            k.tr *= 1.f - (het_density(H, p) - ce) / (maxDensity - ce);
-            if (k.tr < 0.1f) {
-                float q = 1.f - k.tr;
-                if (rng_next(rng) < q) { result = mk3(0.f, 0.f, 0.f); return true; }
-                k.tr /= (1.f - q);
-            }
-            if (--k.iter == 0) end = true;
-        }
-        if (end) {
-            float tc = expf(-tmax * ce * sigma);
-            const float r = k.tr * tc;
-            result = mk3(r, r, r);
-            return true;
-        }
-    }
-    return false;
-}
-__device__ __forceinline__ bool het_sample_chunk(const WMedium& M, const WHetero& H, f3 o, f3 dir, float tmax, uint32_t& rng, TrackState& k,
-                                                 int max_steps, float& t, bool& sampled, f3& weight) {
-    f3 sigmaT = ld3(M.sigmaT), sigmaS = ld3(M.sigmaS);
-    float sigma = dot(sigmaT, mk3(0.212671f, 0.715160f, 0.072169f));
-    const f3 p0 = ld3(H.p0);
-    f3 d = ld3(H.p1) - p0;
-    for (int s_ = 0; s_ < max_steps; ++s_) {
-        k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
-        if (k.dist >= tmax) { t = k.dist; sampled = false; weight = mk3(1.f, 1.f, 1.f); return true; }
+        if (mode == TRK_TR2) k.dist += -logf(rng_next(rng)) * (1 / (maxDensity - ce) / sigma);
+        else k.dist += -logf(rng_next(rng)) * H.invMaxDensity / sigma;
+        if (k.dist >= tmax) return 1;
         f3 p = o + dir * k.dist;
         p = (p - p0) / d;
-        if (het_density(H, p) * H.invMaxDensity > rng_next(rng)) { t = k.dist; sampled = true; weight = sigmaS / sigmaT; return true; }
-        if (--k.iter == 0) { t = k.dist; sampled = false; weight = mk3(1.f, 1.f, 1.f); return true; }
+        const float dens = het_density(H, p);
+        if (mode <= TRK_TR0) {
+            if (dens * H.invMaxDensity > rng_next(rng)) return 2;
+        } else {
+            if (mode == TRK_TR1) k.tr *= 1.f - dens * H.invMaxDensity;
+            else k.tr *= 1.f - (dens - ce) / (maxDensity - ce);
+            if (k.tr < 0.1f) {
+                float q = 1.f - k.tr;
+                if (rng_next(rng) < q) return 2;
+                if (mode == TRK_TR1) k.tr = 1;
+                else k.tr /= (1.f - q);
+            }
+        }
+        if (--k.iter == 0) return 3;
     }
-    return false;
+    return 0;
+}
+// what a finished transmittance run is worth (the tails of het_tr's three loops)
+__device__ __forceinline__ f3 het_track_tr_result(const WMedium& M, const WHetero& H, const int mode, const int reason, const TrackState& k, float tmax) {
+    if (reason == 2) return mk3(0.f, 0.f, 0.f);
+    if (mode == TRK_TR0) { const float r = reason == 1 ? k.tr : 0.f; return mk3(r, r, r); }
+    if (mode == TRK_TR1) return mk3(k.tr, k.tr, k.tr);
+    float sigma = dot(ld3(M.sigmaT), mk3(0.212671f, 0.715160f, 0.072169f));
+    float maxDensity = 1 / H.invMaxDensity;
+    float ce = 0.5f * maxDensity;
+    float tc = expf(-tmax * ce * sigma);
+    const float r = k.tr * tc;
+    return mk3(r, r, r);
 }
 #ifndef PT_TRACK_CHUNK
 #define PT_TRACK_CHUNK 16
@@ -309,6 +285,38 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
         // stages of one bounce; a stage either falls through to a later one, posts a query, or ends the path
         enum { G_MAIN, G_WALK, G_AFTER_NEE, G_MIS, G_CONT, G_BOUNCE_END, G_OUT };
         int g = state == HS_MAIN ? G_MAIN : (state == HS_MIS ? G_MIS : G_WALK);
+        // ---- tracking prelude (CTA-local kernel): the walk through a heterogeneous medium the resumed stage starts with —
+        // the path's free flight up to the hit (G_MAIN) or the transmittance of a shadow leg (G_WALK) — runs HERE, in one
+        // loop for every mode, before the stages diverge; the stage then only consumes the result.  (Both stages draw their
+        // first random number inside that walk, so the stream is consumed in the reference's order.)  At most kTrackChunk
+        // steps per call: an unfinished walk is saved in `carry`, the slot keeps its state and posts nothing.
+        int trk_mode = -1, trk_reason = 0, trk_med = -1;
+        TrackState tk; tk.dist = 0.f; tk.tr = 1.f; tk.iter = 0;
+        float trk_tmax = 0.f;
+        if (FUSED) {
+            f3 to = o, td = d;
+            if (state == HS_MAIN) {
+                if (!(h0.x < 0.f) && medium >= 0 && sc.mediums[medium].type != 0) { trk_mode = TRK_SAMPLE; trk_med = medium; trk_tmax = h0.x; }
+            } else if (state != HS_MIS) {
+                const float4 h1 = pool.hit1[slot], po = pool.pend_o[slot], md = pool.misd[slot];
+                const int mw = (int)__float_as_uint(pool.vis[slot].w) - 1;
+                const bool invisible = h1.x >= 0.f;
+                if (!(invisible && sc.shade[__float_as_int(h1.y)].matIdx != -1) && mw >= 0 && sc.mediums[mw].type != 0) {
+                    trk_mode = TRK_TR0 + sc.het[mw].evalTransmittanceType; trk_med = mw; trk_tmax = invisible ? h1.x : md.w;
+                    to = mk3(po.x, po.y, po.z); td = mk3(md.x, md.y, md.z);
+                }
+            }
+            if (trk_mode >= 0) {
+                const float4 cy = pool.carry[slot];
+                if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
+                else tk.iter = sc.het[trk_med].iterMax;
+                trk_reason = het_track_chunk(sc.mediums[trk_med], sc.het[trk_med], trk_mode, to, td, trk_tmax, rng, tk, kTrackChunk);
+                if (trk_reason == 0) {
+                    st_rec<FUSED>(pool.carry + slot, make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), 1.f));
+                    post = 0u; g = G_OUT;                                                       // same state, no query: resume next step
+                } else if (cy.w != 0.f) st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
         SurfaceHit h;
         bool have_h = false;
         f3 Ld = mk3(0, 0, 0);
@@ -326,18 +334,9 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                 float sampledDist = 0.f; bool sampledMedium = false;
                 if (medium >= 0) {
                     const WMedium& M_ = sc.mediums[medium];
-                    if (FUSED && M_.type != 0) {                 // heterogeneous, CTA-local kernel: free flight in chunks
-                        const float4 cy = pool.carry[slot];
-                        TrackState tk;
-                        if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
-                        else { tk.dist = 0.f; tk.tr = 1.f; tk.iter = sc.het[medium].iterMax; }
-                        f3 w_;
-                        if (!het_sample_chunk(M_, sc.het[medium], o, d, h0.x, rng, tk, kTrackChunk, sampledDist, sampledMedium, w_)) {
-                            st_rec<FUSED>(pool.carry + slot, make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), 1.f));
-                            state = HS_MAIN; post = 0u; g = G_OUT; continue;          // resume here next step
-                        }
-                        if (cy.w != 0.f) st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
-                        beta *= w_;
+                    if (FUSED && M_.type != 0) {                 // heterogeneous, CTA-local kernel: the prelude walked the free flight
+                        sampledDist = tk.dist; sampledMedium = trk_reason == 2;
+                        beta *= sampledMedium ? ld3(M_.sigmaS) / ld3(M_.sigmaT) : mk3(1.f, 1.f, 1.f);
                     } else beta *= medium_sample(sc, medium, o, d, h0.x, rng, sampledDist, sampledMedium);
                 }
                 if (is_black(beta)) { finished = true; g = G_OUT; continue; }                    // :1070
@@ -400,28 +399,16 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                 f3 tr = mk3(pv.x, pv.y, pv.z);
                 int mw = (int)__float_as_uint(pv.w) - 1;
                 const bool invisible = h1.x >= 0.f;
-                bool again = false, walk_paused = false;
+                bool again = false;
                 if (invisible && sc.shade[__float_as_int(h1.y)].matIdx != -1) tr = mk3(0, 0, 0);
                 else {
                     const float seg = invisible ? h1.x : remain;
                     if (mw >= 0) {
                         const WMedium& M_ = sc.mediums[mw];
-                        if (FUSED && M_.type != 0) {             // heterogeneous, CTA-local kernel: this leg's transmittance in chunks
-                            const float4 cy = pool.carry[slot];
-                            TrackState tk;
-                            if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
-                            else { tk.dist = 0.f; tk.tr = 1.f; tk.iter = sc.het[mw].iterMax; }
-                            f3 r_;
-                            if (!het_tr_chunk(M_, sc.het[mw], ow, dw, seg, rng, tk, kTrackChunk, r_)) {
-                                st_rec<FUSED>(pool.carry + slot, make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), 1.f));
-                                post = 0u; g = G_OUT; walk_paused = true;
-                            } else {
-                                if (cy.w != 0.f) st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
-                                tr *= r_;
-                            }
-                        } else tr *= medium_tr(sc, mw, ow, dw, seg, rng);
+                        if (FUSED && M_.type != 0) tr *= het_track_tr_result(M_, sc.het[mw], trk_mode, trk_reason, tk, seg);   // the prelude walked this leg
+                        else tr *= medium_tr(sc, mw, ow, dw, seg, rng);
                     }
-                    if (!walk_paused && invisible) {
+                    if (invisible) {
                         const int prim = __float_as_int(h1.y);
                         const WShade& s = sc.shade[prim];
                         f3 nor;
@@ -436,7 +423,6 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                         again = true;
                     }
                 }
-                if (walk_paused) continue;                                                      // same state, no query: resume next step
                 if (again) { post = 2u; g = G_OUT; continue; }                                  // same state: next leg
                 const float4 l = pool.ldl[slot];
                 const f3 radiance = mk3(l.x, l.y, l.z);

@@ -27,7 +27,10 @@
 
 namespace pt {
 
-constexpr int kWaveThreads = 256;                 // slots (= threads) per CTA of the surface / homogeneous-medium wavefront
+#ifndef PT_WAVE_THREADS
+#define PT_WAVE_THREADS 256                       // 128: C2 -6 %, six-BSDF scene -43 % (smaller sort domain); 64: -20 % (profiles/r02p_cta_size.txt)
+#endif
+constexpr int kWaveThreads = PT_WAVE_THREADS;     // slots (= threads) per CTA of the surface / homogeneous-medium wavefront
 #ifndef PT_WAVE_HET_THREADS
 #define PT_WAVE_HET_THREADS 256                   // heterogeneous media (128-thread CTAs measured slower: smoke 113 vs 146 Msamples/s)
 #endif
@@ -75,15 +78,20 @@ template <bool VOL> __device__ __forceinline__ uint32_t wave_sort_key(uint32_t e
     return any + 15u - (n < 15u ? n : 15u);                           // most hit groups first
 }
 
-// Sort key of a heterogeneous-media slot: wait state, and whether the stage it resumes into runs a tracking loop (the path
-// ray / walk leg lies in a medium) — lanes that will track sit next to each other.  Dead slots last.
-__device__ __forceinline__ uint32_t het_sort_key(const Pool& P, uint32_t slot) {
+// Sort key of a heterogeneous-media slot: slots whose resumed stage starts with a walk through a heterogeneous medium
+// (het_slot's tracking prelude — one loop for all of them) come first, ordered by wait state; then the others by wait
+// state; dead slots last.
+__device__ __forceinline__ uint32_t het_sort_key(const Pool& P, const SceneDev& sc, uint32_t slot) {
     const uint32_t f = __float_as_uint(P.d_flags[slot].w);
     if (!(f & H_ALIVE)) return 15u;
     const uint32_t st = (f >> kHStateShift) & 3u;
+    if (st == HS_MIS) return 6u;
     uint32_t med = (f >> kMediumShift) & 0xffu;                                      // medium of the path ray + 1
-    if (st == HS_WALK_MED || st == HS_WALK_SURF) med = __float_as_uint(P.vis[slot].w);   // medium of the walk's current leg + 1
-    return st * 2u + (med != 0u ? 1u : 0u);
+    bool open = true;
+    if (st == HS_MAIN) open = !(P.hit0[slot].x < 0.f);                               // a miss ends the path: no free flight
+    else med = __float_as_uint(P.vis[slot].w);                                       // medium of the walk's current leg + 1
+    const bool track = open && med != 0u && sc.mediums[med - 1u].type != 0;
+    return st + (track ? 0u : 3u);
 }
 
 // Sort key of a slot for the shade phase of a scene with several BSDFs (material binning, see k_shade): dead slots, misses,
@@ -95,14 +103,15 @@ __device__ __forceinline__ uint32_t wave_shade_key(const Pool& P, const SceneDev
     if (!(f & F_ALIVE)) return 0u;
     const float4 h0 = P.hit0[slot];
     const uint32_t prim = __float_as_uint(h0.y);
-    uint32_t key = (h0.x < 0.f || prim >= (uint32_t)sc.n_prims) ? 1u : 2u + (sc.prim_key[prim] & 7u);
-    if (VOL && ((f >> kMediumShift) & 0xffu) != 0u) key = (key == 1u ? 9u : key) + 8u;
+    uint32_t key = (h0.x < 0.f || prim >= (uint32_t)sc.n_prims) ? 1u : 2u + (sc.prim_key[prim] & 15u);
+    if (VOL && ((f >> kMediumShift) & 0xffu) != 0u) key += 18u;
     return key;
 }
+constexpr uint32_t kWaveShadeKeys = 36u;
 
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
-__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3)) k_wave_small(const WaveArgs a) {
+__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3) * (256 / kWaveThreads)) k_wave_small(const WaveArgs a) {
     constexpr int kT = WaveThreads<HET>::value;
     const ShadeArgs& sa = a.sa;
     const TraceArgs& ta = a.ta;
@@ -182,10 +191,10 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
             const uint32_t par = step & 1u;
             // ---- sort the slots by wait state (dead slots last): count, then scatter (every thread sums the counts below
             // its key itself — 16 broadcast reads instead of a prefix phase and its barrier)
-            PT_WAVE_FOR_THREADS(t) { atomicAdd(&s_cnt[het_sort_key(P, t)], 1u); }
+            PT_WAVE_FOR_THREADS(t) { atomicAdd(&s_cnt[het_sort_key(P, sa.sc, t)], 1u); }
             PT_WAVE_SYNC();
             PT_WAVE_FOR_THREADS(t) {
-                const uint32_t key = het_sort_key(P, t);
+                const uint32_t key = het_sort_key(P, sa.sc, t);
                 uint32_t base = 0u;
                 for (uint32_t k = 0; k < key; ++k) base += s_cnt[k];
                 s_order[base + atomicAdd(&s_pos[key], 1u)] = (uint16_t)t;
@@ -221,11 +230,11 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
         }
     } else {
     // material binning (scenes with several BSDFs): thread j shades the j-th slot in material order — same counting sort
-    __shared__ uint32_t s_mcnt[kShadeKeys], s_mpos[kShadeKeys];
+    __shared__ uint32_t s_mcnt[kWaveShadeKeys], s_mpos[kWaveShadeKeys];
     __shared__ uint16_t s_morder[kT];
-    const bool bin = MATS != kMatsLambertOnly && sa.bin_materials != 0;
+    const bool bin = sa.bin_materials != 0;       // (forced on for a lambertian-only scene it costs 5 %: profiles/r02o_bin_lambert.txt)
     if (bin) {
-        PT_WAVE_FOR_THREADS(t) { if (t < kShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; } }
+        PT_WAVE_FOR_THREADS(t) { if (t < kWaveShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; } }
         PT_WAVE_SYNC();
     }
     for (uint32_t step = 0;; ++step) {
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
         PT_WAVE_FOR_THREADS(t) {
             if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
             if (t < 32u) s_hist[t] = 0u;
-            if (bin && t < kShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; }
+            if (bin && t < kWaveShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; }
         }
         // (measured, profiles/r02i_sort_ab.txt: sorted passes +3.4 % on C2, +2.4 % on C1, +5 % on the material zoo; -5 % on C5,
         // whose shadow queries are multi-leg transmittance walks — `vpt` keeps the single pass)

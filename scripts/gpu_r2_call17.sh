@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# round 2, GPU call 17: unified tracking prelude of the heterogeneous coroutine (one loop for free flight + the three Tr estimators), A/B against the previous build
+set -u
+cd /root/repo
+mkdir -p gpurun_out
+V=gpu-pathtracer_b200/csrc/variants
+{
+for v in "" old256; do
+  lib=""; [ -n "$v" ] && lib="--lib $V/libb200pt_$v.so"
+  echo "== ${v:-unified}"
+  for sc in smoke smoke0 smoke2; do
+    timeout 200 python scripts/perf.py --scene $sc --size 1024 --spp 8 --reps 3 $lib --tag "$sc ${v:-unified}"
+  done
+  timeout 200 python scripts/perf.py --scene shipped --size 1024 --spp 8 --reps 3 $lib --tag "shipped ${v:-unified}"
+  timeout 200 python scripts/perf.py --scene shipped --size 512 --spp 16 --reps 3 $lib --tag "shipped512 ${v:-unified}"
+done
+} 2>&1 | grep -E "==|PERF|rror" > gpurun_out/r02q_het_unified.txt
+cat gpurun_out/r02q_het_unified.txt
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "smoke or het or shipped" 2>&1 | tail -5 > gpurun_out/r02q_het_parity.txt
+cat gpurun_out/r02q_het_parity.txt
+timeout 600 compute-sanitizer --tool racecheck python scripts/compare_ref.py --scene smoke --size 64 --spp 2 --no-ref --no-warm 2>&1 | tail -3 > gpurun_out/r02q_het_racecheck.txt
+cat gpurun_out/r02q_het_racecheck.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_wave_small -c 1 -f -o gpurun_out/r02q_wave_het python scripts/compare_ref.py --scene smoke --size 1024 --spp 2 --no-ref --no-warm > /dev/null 2>&1
+python scripts/ncu_summary.py gpurun_out/r02q_wave_het.ncu-rep > gpurun_out/r02q_wave_het_summary.txt 2>&1
+python scripts/ncu_lines.py gpurun_out/r02q_wave_het.ncu-rep 50 > gpurun_out/r02q_wave_het_lines.txt 2>&1
+head -30 gpurun_out/r02q_wave_het_summary.txt
