@@ -253,6 +253,61 @@ __device__ __forceinline__ f3 hg_sample(float g, float pa, float pb) {
     return mk3(sintheta * cosphi, costheta, sintheta * sinphi);
 }
 
+// The walk through a heterogeneous medium a slot's resumed stage starts with, if any: the path's free flight up to the hit
+// (HS_MAIN) or the transmittance of the current shadow leg (HS_WALK_*).  ONE definition for the three places that must
+// agree on it: the sort key, the glue, and the tracking jobs of the trace phase.
+struct TrackJob { int mode, med; float tmax; f3 o, d; };
+__device__ __forceinline__ bool het_track_job(const SceneDev& sc, const Pool& pool, const uint32_t slot, const int state, const int medium,
+                                              const float h0x, const f3 o, const f3 d, TrackJob& j) {
+    if (state == HS_MAIN) {
+        if (h0x < 0.f || medium < 0 || sc.mediums[medium].type == 0) return false;
+        j.mode = TRK_SAMPLE; j.med = medium; j.tmax = h0x; j.o = o; j.d = d;
+        return true;
+    }
+    if (state == HS_MIS) return false;
+    const float4 h1 = pool.hit1[slot];
+    const int mw = (int)__float_as_uint(pool.vis[slot].w) - 1;
+    const bool invisible = h1.x >= 0.f;
+    if ((invisible && sc.shade[__float_as_int(h1.y)].matIdx != -1) || mw < 0 || sc.mediums[mw].type == 0) return false;
+    const float4 po = pool.pend_o[slot], md = pool.misd[slot];
+    j.mode = TRK_TR0 + sc.het[mw].evalTransmittanceType; j.med = mw; j.tmax = invisible ? h1.x : md.w;
+    j.o = mk3(po.x, po.y, po.z); j.d = mk3(md.x, md.y, md.z);
+    return true;
+}
+#ifndef PT_HET_OVERLAP
+#define PT_HET_OVERLAP 1
+#endif
+// carry.w of a slot: 0 = no walk in progress, 1 = walk in progress (distance, transmittance, iterations left saved),
+// 2 + k = walk finished with reason 1 + k (PT_HET_OVERLAP: the trace phase walks, the next glue consumes)
+// true when the slot waits for (more of) a walk: it is sorted in front, the glue leaves it alone, the trace phase walks it
+__device__ __forceinline__ bool het_slot_tracks(const SceneDev& sc, const Pool& pool, const uint32_t slot) {
+    const float4 df = pool.d_flags[slot];
+    const uint32_t f = __float_as_uint(df.w);
+    if (!(f & H_ALIVE)) return false;
+    const float4 orng = pool.o_rng[slot];
+    TrackJob j;
+    if (!het_track_job(sc, pool, slot, (int)((f >> kHStateShift) & 7u), (int)((f >> kMediumShift) & 0xffu) - 1, pool.hit0[slot].x,
+                       mk3(orng.x, orng.y, orng.z), mk3(df.x, df.y, df.z), j)) return false;
+    return !PT_HET_OVERLAP || pool.carry[slot].w < 2.f;
+}
+// One chunk of a slot's walk, as a work item of the TRACE phase (PT_HET_OVERLAP): the slots that track post no ray, so
+// their walks run next to the other slots' traversals instead of in front of them.
+__device__ __forceinline__ void het_track_step(const SceneDev& sc, const Pool& pool, const uint32_t slot) {
+    const float4 df = pool.d_flags[slot], orng = pool.o_rng[slot];
+    const uint32_t f = __float_as_uint(df.w);
+    uint32_t rng = __float_as_uint(orng.w);
+    TrackJob j;
+    if (!het_track_job(sc, pool, slot, (int)((f >> kHStateShift) & 7u), (int)((f >> kMediumShift) & 0xffu) - 1, pool.hit0[slot].x,
+                       mk3(orng.x, orng.y, orng.z), mk3(df.x, df.y, df.z), j)) return;
+    const float4 cy = pool.carry[slot];
+    TrackState tk;
+    if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
+    else { tk.dist = 0.f; tk.tr = 1.f; tk.iter = sc.het[j.med].iterMax; }
+    const int reason = het_track_chunk(sc.mediums[j.med], sc.het[j.med], j.mode, j.o, j.d, j.tmax, rng, tk, kTrackChunk);
+    pool.carry[slot] = make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), reason == 0 ? 1.f : 1.f + (float)reason);
+    pool.o_rng[slot].w = __uint_as_float(rng);
+}
+
 // QUEUED: the query goes into the ray queue (global wavefront: k_trace / k_trace_small pull it).  Otherwise the caller
 // traces it itself right away (warp-local stepping of the CTA-local kernel, k_wave.cuh) and gets its kind in `posted`
 // (0 none, 1 path ray = queue kind 0, 2 secondary query = queue kind 2).
@@ -290,31 +345,28 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
         // loop for every mode, before the stages diverge; the stage then only consumes the result.  (Both stages draw their
         // first random number inside that walk, so the stream is consumed in the reference's order.)  At most kTrackChunk
         // steps per call: an unfinished walk is saved in `carry`, the slot keeps its state and posts nothing.
-        int trk_mode = -1, trk_reason = 0, trk_med = -1;
+        int trk_mode = -1, trk_reason = 0;
         TrackState tk; tk.dist = 0.f; tk.tr = 1.f; tk.iter = 0;
-        float trk_tmax = 0.f;
         if (FUSED) {
-            f3 to = o, td = d;
-            if (state == HS_MAIN) {
-                if (!(h0.x < 0.f) && medium >= 0 && sc.mediums[medium].type != 0) { trk_mode = TRK_SAMPLE; trk_med = medium; trk_tmax = h0.x; }
-            } else if (state != HS_MIS) {
-                const float4 h1 = pool.hit1[slot], po = pool.pend_o[slot], md = pool.misd[slot];
-                const int mw = (int)__float_as_uint(pool.vis[slot].w) - 1;
-                const bool invisible = h1.x >= 0.f;
-                if (!(invisible && sc.shade[__float_as_int(h1.y)].matIdx != -1) && mw >= 0 && sc.mediums[mw].type != 0) {
-                    trk_mode = TRK_TR0 + sc.het[mw].evalTransmittanceType; trk_med = mw; trk_tmax = invisible ? h1.x : md.w;
-                    to = mk3(po.x, po.y, po.z); td = mk3(md.x, md.y, md.z);
-                }
-            }
-            if (trk_mode >= 0) {
+            TrackJob j;
+            if (het_track_job(sc, pool, slot, state, medium, h0.x, o, d, j)) {
+                trk_mode = j.mode;
                 const float4 cy = pool.carry[slot];
+#if PT_HET_OVERLAP
+                // the walk itself is a work item of the TRACE phase (het_track_step): consume a finished one, else wait
+                if (cy.w >= 2.f) {
+                    tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); trk_reason = (int)cy.w - 1;
+                    st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
+                } else { post = 0u; g = G_OUT; }
+#else
                 if (cy.w != 0.f) { tk.dist = cy.x; tk.tr = cy.y; tk.iter = __float_as_int(cy.z); }
-                else tk.iter = sc.het[trk_med].iterMax;
-                trk_reason = het_track_chunk(sc.mediums[trk_med], sc.het[trk_med], trk_mode, to, td, trk_tmax, rng, tk, kTrackChunk);
+                else tk.iter = sc.het[j.med].iterMax;
+                trk_reason = het_track_chunk(sc.mediums[j.med], sc.het[j.med], j.mode, j.o, j.d, j.tmax, rng, tk, kTrackChunk);
                 if (trk_reason == 0) {
                     st_rec<FUSED>(pool.carry + slot, make_float4(tk.dist, tk.tr, __int_as_float(tk.iter), 1.f));
                     post = 0u; g = G_OUT;                                                       // same state, no query: resume next step
                 } else if (cy.w != 0.f) st_rec<FUSED>(pool.carry + slot, make_float4(0.f, 0.f, 0.f, 0.f));
+#endif
             }
         }
         SurfaceHit h;

@@ -35,6 +35,9 @@ constexpr int kWaveThreads = PT_WAVE_THREADS;     // slots (= threads) per CTA o
 #define PT_WAVE_HET_THREADS 256                   // heterogeneous media (128-thread CTAs measured slower: smoke 113 vs 146 Msamples/s)
 #endif
 template <bool HET> struct WaveThreads { static constexpr int value = HET ? PT_WAVE_HET_THREADS : kWaveThreads; };
+#ifndef PT_WAVE_MATS_CTAS
+#define PT_WAVE_MATS_CTAS 2         // resident CTAs per SM the `vpt` / several-BSDF instantiations are compiled for
+#endif
 #ifndef PT_WAVE_HET_CTAS
 #define PT_WAVE_HET_CTAS 2          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
 #endif
@@ -86,12 +89,7 @@ __device__ __forceinline__ uint32_t het_sort_key(const Pool& P, const SceneDev& 
     if (!(f & H_ALIVE)) return 15u;
     const uint32_t st = (f >> kHStateShift) & 3u;
     if (st == HS_MIS) return 6u;
-    uint32_t med = (f >> kMediumShift) & 0xffu;                                      // medium of the path ray + 1
-    bool open = true;
-    if (st == HS_MAIN) open = !(P.hit0[slot].x < 0.f);                               // a miss ends the path: no free flight
-    else med = __float_as_uint(P.vis[slot].w);                                       // medium of the walk's current leg + 1
-    const bool track = open && med != 0u && sc.mediums[med - 1u].type != 0;
-    return st + (track ? 0u : 3u);
+    return st + (het_slot_tracks(sc, P, slot) ? 0u : 3u);
 }
 
 // Sort key of a slot for the shade phase of a scene with several BSDFs (material binning, see k_shade): dead slots, misses,
@@ -111,7 +109,7 @@ constexpr uint32_t kWaveShadeKeys = 36u;
 
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
-__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? 2 : 3) * (256 / kWaveThreads)) k_wave_small(const WaveArgs a) {
+__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? PT_WAVE_MATS_CTAS : 3) * (256 / kWaveThreads)) k_wave_small(const WaveArgs a) {
     constexpr int kT = WaveThreads<HET>::value;
     const ShadeArgs& sa = a.sa;
     const TraceArgs& ta = a.ta;
@@ -200,6 +198,7 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
                 s_order[base + atomicAdd(&s_pos[key], 1u)] = (uint16_t)t;
             }
             PT_WAVE_SYNC();
+            const uint32_t n_track = PT_HET_OVERLAP ? s_cnt[0] + s_cnt[1] + s_cnt[2] : 0u;       // slots waiting for a walk: first in s_order
             // ---- glue phase
             PT_WAVE_FOR_THREADS(t) {
 #ifdef B200PT_EMULATE
@@ -220,7 +219,10 @@ __global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTA
                 if (t == 0u) { s_ctl.tail[par ^ 1u] = 0u; s_busy[par ^ 1u] = 0u; s_next = *(volatile unsigned long long*)&sa.counters->next_sample; }
                 if (t < 16u) { s_cnt[t] = 0u; s_pos[t] = 0u; }                      // re-arm the sort counters for the next step
                 uint32_t nrays = 0;
-                for (uint32_t idx = t; idx < tail; idx += (uint32_t)kT) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
+                // the first n_track threads walk one chunk of a waiting slot's medium walk (full warps: those slots are
+                // sorted in front), the others trace the queue — tracking slots post no ray, so tail <= kT - n_track
+                if (t < n_track) het_track_step(sa.sc, P, s_order[t]);
+                else for (uint32_t idx = t - n_track; idx < tail; idx += (uint32_t)kT - n_track) trace_small_ray<VOL>(ta, P, prims, leaves, s_queue[idx], nrays);
 #ifndef B200PT_EMULATE
                 for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(kFullMask, nrays, off);
 #endif
