@@ -36,10 +36,12 @@ constexpr int kWaveThreads = PT_WAVE_THREADS;     // slots (= threads) per CTA o
 #endif
 template <bool HET> struct WaveThreads { static constexpr int value = HET ? PT_WAVE_HET_THREADS : kWaveThreads; };
 #ifndef PT_WAVE_MATS_CTAS
-#define PT_WAVE_MATS_CTAS 2         // resident CTAs per SM the `vpt` / several-BSDF instantiations are compiled for
+#define PT_WAVE_MATS_CTAS 3         // resident CTAs per SM the `vpt` / several-BSDF instantiations are compiled for: 80 registers and
+                                    // ~100 B of spills against 96-99 at 2 — C5 662 -> 706 Msamples/s, six-BSDF scenes unchanged (profiles/r02s_ctas3.txt)
 #endif
 #ifndef PT_WAVE_HET_CTAS
-#define PT_WAVE_HET_CTAS 2          // resident CTAs per SM the heterogeneous-media instantiation is compiled for
+#define PT_WAVE_HET_CTAS 2          // resident CTAs per SM the heterogeneous-media instantiation is compiled for (3: 80 registers,
+                                    // 530 B of spills — smoke 141 vs 156, shipped scene 94 vs 125: profiles/r02s_ctas3.txt)
 #endif
 
 // The shade / trace bodies read scene, camera, shard map and batch from the same argument structs as the global
