@@ -19,7 +19,8 @@ samples of the timed region / CUDA-event time: for scenes that live in shared me
 instruction issue (frac = useful-lane issue fraction; the HBM figures are reported next to it), for C4 it is
 HBM / L2; cpu_baseline = the reference's own kernel bodies (oracle/_ref/libref_host_fast.so) on the host cores for a
 bounded sample; reference_cuda = the reference's own CUDA integrator (oracle/_ref/libref_cuda.so) on
-the same GPU, timed in a subprocess outside the timed region; extra.c4 = a short leg on BASELINE configs[3]
+the same GPU, timed in a subprocess outside the timed region; extra.shipped_scene = a short leg on the reference's own
+scene.json (heterogeneous medium); extra.c4 = a short leg on BASELINE configs[3]
 (1 M triangles, 2048x2048).  --impl reference times the CPU reference arm alone."""
 import argparse
 import json
@@ -45,6 +46,7 @@ ALGO = {
     "c5": dict(R=12.92, N=10.68, P=4.01),
     "smoke": dict(R=13.09, N=17.82, P=11.28),      # SURVEY 8(f).3 scenes (heterogeneous media)
     "shipped": dict(R=15.80, N=11.75, P=7.70),
+    "shipped512": dict(R=15.80, N=11.75, P=7.70),
 }
 
 
@@ -69,6 +71,8 @@ def make_scene(pt, name, prep=None):
         return pt.scenes.cornell_smoke(1024, 1024, 8, 1, prep=prep), "cornell_box + heterogeneous smoke (ratio tracking) vpt 1024x1024 depth=8 (SURVEY 8(f).3)"
     if name == "shipped":
         return pt.scenes.cornell_shipped_smoke(1024, 1024, 17, prep=prep), "the reference's shipped cornell_box/scene.json (heterogeneous medium) vpt 1024x1024 depth=17"
+    if name == "shipped512":
+        return pt.scenes.cornell_shipped_smoke(512, 512, 17, prep=prep), "the reference's shipped cornell_box/scene.json (heterogeneous medium) vpt 512x512 depth=17"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -359,6 +363,18 @@ def main():
             extra["c4"] = {"workload": c4["desc"], "value": c4["value"], "e2e": c4.get("e2e"), "unit": "Msamples/s", "steps": 3, "warmup": 3,
                            "spp_per_step": c4["spp"], "ms_per_step": c4["ms_per_step"], "rays_per_sample": c4["rays"] / c4["samples"],
                            "roofline": roofline_record("c4", load_counters("c4"), c4["samples"] / world, k_s, c4["clocks"], peaks)}
+
+        # ... and the scene the reference ships (cornell_box/scene.json: heterogeneous smoke, depth 17), SURVEY 8(f).3
+        het = run_workload("shipped512", 3, 3, 16, want_e2e=False)
+        if rank == 0:
+            extra["shipped_scene"] = {"workload": het["desc"], "value": het["value"], "unit": "Msamples/s", "steps": 3, "warmup": 3,
+                                      "spp_per_step": het["spp"], "ms_per_step": het["ms_per_step"], "rays_per_sample": het["rays"] / het["samples"],
+                                      "roofline": roofline_record("shipped512", load_counters("shipped512"), het["samples"] / world, het["dev_ms"] / 1e3, het["clocks"], peaks)}
+            if world == 1:
+                rc = reference_cuda_subprocess("shipped512", 16)
+                if "value" in rc:
+                    rc["ratio_device"] = het["value"] / rc["value"]
+                extra["shipped_scene"]["reference_cuda"] = rc
 
     if rank == 0:
         kernel_s = res["dev_ms"] / 1e3                   # wavefront kernels of all timed steps, CUDA events on the context's stream

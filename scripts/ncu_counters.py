@@ -28,6 +28,8 @@ WORK = {                         # scene name for scripts/compare_ref.make, size
     "c4": ("tris1000000", 2048, 1),
     "c5": ("vol", 512, 8),
     "smoke": ("smoke", 1024, 2),
+    "shipped512": ("shipped", 512, 4),
+    "zoo": ("zoo", 512, 8),
 }
 
 
