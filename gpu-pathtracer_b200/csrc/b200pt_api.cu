@@ -295,6 +295,22 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     }
     c->n_nodes4 = (int)wn4.size();
 
+    // boxes a ray must pass to reach an emitter (mis_ray_may_reach_emitter, wavefront.cuh): the BVH leaves and, for a small
+    // scene, the primitive groups that hold a triangle with a light index — the union, so the list is valid whichever
+    // traversal kernel the context ends up using
+    std::vector<float4> emit;
+    auto add_emit_box = [&](const float* mn, const float* mx) {
+        const float4 q0 = make_float4(mn[0], mn[1], mn[2], mx[0]), q1 = make_float4(mx[1], mx[2], 0.f, 0.f);
+        for (size_t i = 0; i + 1 < emit.size(); i += 2)
+            if (!std::memcmp(&emit[i], &q0, 16) && !std::memcmp(&emit[i + 1], &q1, 8)) return;
+        emit.push_back(q0); emit.push_back(q1);
+    };
+    for (int i = 0; i < v->n_nodes; ++i) {
+        if (!nodes[i].is_leaf) continue;
+        bool has = false;
+        for (int k = nodes[i].start; k <= nodes[i].end && k < v->n_prims; ++k) has = has || ws[k].lightIdx >= 0;
+        if (has) add_emit_box(nodes[i].fmin, nodes[i].fmax);
+    }
     // primitive groups for k_trace_small (<= 256 primitives): greedy agglomeration of tight primitive boxes under the
     // cost model  cost(group) = C_BOX + P(ray hits box) * C_PRIM * |group|,  P ~ surface area of the box / root's
     if (v->n_prims <= 256) {
@@ -356,6 +372,11 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
                 float f0, f1; std::memcpy(&f0, &u0, 4); std::memcpy(&f1, &u1, 4);
                 wl.push_back(make_float4(G.mn[0], G.mn[1], G.mn[2], G.mx[0]));
                 wl.push_back(make_float4(G.mx[1], G.mx[2], f0, f1));
+            }
+            for (const Grp& G : g) {
+                bool has = false;
+                for (int k = 0; k < G.n; ++k) has = has || ws[G.p[k]].lightIdx >= 0;
+                if (has) add_emit_box(G.mn, G.mx);
             }
             c->n_leaves = (int)g.size();
             int rc2 = dev_upload(c, &c->leaves, wl.data(), wl.size());
@@ -423,6 +444,16 @@ static int build_scene(b200pt_ctx* c, const b200pt_scene_view* v) {
     int n_types = 0;
     for (uint32_t m = c->mats_used; m; m &= m - 1u) ++n_types;
     c->bin_materials = n_types >= 3;
+    {   // MIS-ray culling: needs at least one emitter, no environment light (a ray that escapes then carries radiance), a short list
+        bool on = !emit.empty() && (int)emit.size() / 2 <= kMaxEmitBoxes && !(v->infinite && ((const RefInfinite*)v->infinite)->isvalid);
+        if (const char* env = getenv("B200PT_CULL_MIS")) on = on && atoi(env) != 0;
+        sc.emit_boxes = nullptr; sc.n_emit_boxes = 0;
+        if (on) {
+            float4* d_emit;
+            if ((rc = dev_upload(c, &d_emit, emit.data(), emit.size()))) return rc;
+            sc.emit_boxes = d_emit; sc.n_emit_boxes = (int)emit.size() / 2;
+        }
+    }
     if (const char* env = getenv("B200PT_BIN_MATERIALS")) c->bin_materials = atoi(env) != 0;
     std::vector<WMedium> wm(std::max(v->n_mediums, 1));
     std::memset(wm.data(), 0, wm.size() * sizeof(WMedium));
@@ -747,6 +778,7 @@ extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_val
     else if (n == "lambert_only") *out_value = c->lambert_only ? 1 : 0;
     else if (n == "fused") *out_value = c->fused ? 1 : 0;
     else if (n == "bin_materials") *out_value = c->bin_materials ? 1 : 0;
+    else if (n == "emit_boxes") *out_value = c->sc.n_emit_boxes;
     else if (n == "wide") *out_value = c->wide ? 1 : 0;
     else if (n == "nodes4") *out_value = c->n_nodes4;
     else if (n == "wave_blocks") *out_value = c->wave_blocks;

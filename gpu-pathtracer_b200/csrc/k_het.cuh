@@ -498,7 +498,7 @@ __device__ __forceinline__ void het_slot(const ShadeArgs& a, const Pool& pool, c
                 float s0 = rng_next(rng), s1 = rng_next(rng), s2 = rng_next(rng);
                 f3 out, fr; float pdf;
                 sample_bsdf_m<MATS>(mat, material_albedo(sc, mat, h.uv), -d, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
-                if (is_black(fr) || pdf == 0) { g = G_MIS + 100; }                               // no light ray: straight to the accumulation
+                if (is_black(fr) || pdf == 0 || !mis_ray_may_reach_emitter(sc, h.pos, out)) { g = G_MIS + 100; }   // no light ray: straight to the accumulation
                 else {
                     st_rec<FUSED>(pool.misf + slot, make_float4(fr.x, fr.y, fr.z, pdf));
                     st_rec<FUSED>(pool.beta_old + slot, make_float4(Ld.x, Ld.y, Ld.z, 0.f));

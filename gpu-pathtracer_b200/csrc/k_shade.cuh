@@ -513,7 +513,7 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const Pool& pool,
                         sample_bsdf_m<MATS>(mat, albedo, wo, h.nor, h.dpdu, mk3(s0, s1, s2), out, fr, pdf);
                         PT_PROBE("M out %a %a %a fr %a %a %a pdf %a\n", PT_P3(out), PT_P3(fr), (double)pdf);
                         float denom = ls.pdf * choicePdf;
-                        if (!(is_black(fr) || pdf == 0)) {
+                        if (!(is_black(fr) || pdf == 0) && mis_ray_may_reach_emitter(sc, h.pos, out)) {
                             nf |= F_MIS;
                             mis_absdot = fabsf(dot(out, h.nor));
                             st_rec<FUSED>(pool.misd + slot, make_float4(out.x, out.y, out.z, pdf));

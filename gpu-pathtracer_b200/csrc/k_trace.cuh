@@ -16,25 +16,6 @@
 namespace pt {
 
 
-// ---- the reference's slab test, BBox::Intersect (src/bbox.h:77-96), on one child box ---------------------
-// inv = 1/d is hoisted out of the node loop (the reference recomputes the same value per node).
-__device__ __forceinline__ bool slab(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
-                                     f3 o, f3 inv, float ray_tmax, float& tnear) {
-    float t1 = (bminx - o.x) * inv.x;
-    float t2 = (bmaxx - o.x) * inv.x;
-    float t3 = (bminy - o.y) * inv.y;
-    float t4 = (bmaxy - o.y) * inv.y;
-    float t5 = (bminz - o.z) * inv.z;
-    float t6 = (bmaxz - o.z) * inv.z;
-    float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
-    float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
-    tnear = tmin;
-    if (tmax <= 0.00001f) return false;
-    if (tmin > tmax) return false;
-    if (tmin > ray_tmax) return false;
-    return true;
-}
-
 struct Hit { float t; int prim; float b1, b2; };
 
 // Triangle::Intersect (src/mesh.h:45-66) / Sphere::Intersect (src/sphere.h:26-72) on a WPrim record.

@@ -86,9 +86,48 @@ struct SceneDev {
     int32_t root_leaf_count;        // > 0 when the whole scene is a single leaf (no inner node)
     int32_t integrator, max_depth;
     float eps;
+    const float4* emit_boxes;       // boxes (group record layout: min.xyz, max.x | max.yz, -, -) a ray must pass to reach an emitter
+    int32_t n_emit_boxes;           // 0: no culling of MIS rays (environment light, too many boxes, or switched off)
     const unsigned char* prim_key;  // per primitive: shade-stage sort key (material type, +8 for an emitter; 7 = no material)
     const WHetero* het;             // non-null when some medium is heterogeneous (then k_volpath_seq renders the scene)
 };
+
+// ---- the reference's slab test, BBox::Intersect (src/bbox.h:77-96), on one child box ---------------------
+// inv = 1/d is hoisted out of the node loop (the reference recomputes the same value per node).
+__device__ __forceinline__ bool slab(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                                     f3 o, f3 inv, float ray_tmax, float& tnear) {
+    float t1 = (bminx - o.x) * inv.x;
+    float t2 = (bmaxx - o.x) * inv.x;
+    float t3 = (bminy - o.y) * inv.y;
+    float t4 = (bmaxy - o.y) * inv.y;
+    float t5 = (bminz - o.z) * inv.z;
+    float t6 = (bmaxz - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    tnear = tmin;
+    if (tmax <= 0.00001f) return false;
+    if (tmin > tmax) return false;
+    if (tmin > ray_tmax) return false;
+    return true;
+}
+
+// A BSDF-sampled light ray (the MIS ray of a bounce) adds radiance only if its CLOSEST hit is an emitter (or, with an
+// environment light, if it escapes).  The traversal tests a primitive only after the ray passed the slab test of the box
+// it sits in — its primitive group (small scenes) or its BVH leaf (tree kernel) — so a ray that fails that test for every
+// box holding an emitter can never report an emitter: it is not traced at all.  Same test, same operands, same
+// decision as the traversal would make; no random number is involved.  The host lists the boxes (SceneDev::emit_boxes,
+// at most kMaxEmitBoxes; none when the scene has an environment light).  Cornell box: one box, 9 of 10 MIS rays dropped.
+constexpr int kMaxEmitBoxes = 16;
+__device__ __forceinline__ bool mis_ray_may_reach_emitter(const SceneDev& sc, const f3 o, const f3 d) {
+    if (sc.n_emit_boxes <= 0) return true;
+    const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    for (int i = 0; i < sc.n_emit_boxes; ++i) {
+        const float4 q0 = sc.emit_boxes[2 * i], q1 = sc.emit_boxes[2 * i + 1];
+        float tn;
+        if (slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, INFINITY, tn)) return true;
+    }
+    return false;
+}
 
 // ---- path pool -------------------------------------------------------------------------------------------
 // flags word

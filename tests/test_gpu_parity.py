@@ -319,25 +319,28 @@ def test_full_config_c4_one_million_triangles_matches_reference_cuda():
 @pytest.mark.parametrize("name,mk,spp,variants", [
     # CTA-local vs global wavefront; material binning on / off (six BSDFs, pt and vpt)
     ("material_zoo_pt", lambda: pt.scenes.cornell_material_zoo(256, 256, 8, "pt"), 16,
-     [{}, {"B200PT_FUSED": "0"}, {"B200PT_BIN_MATERIALS": "0"}, {"B200PT_FUSED": "0", "B200PT_BIN_MATERIALS": "0"}]),
+     [{}, {"B200PT_FUSED": "0"}, {"B200PT_BIN_MATERIALS": "0"}, {"B200PT_FUSED": "0", "B200PT_BIN_MATERIALS": "0"}, {"B200PT_CULL_MIS": "0"}]),
     ("material_zoo_vpt", lambda: pt.scenes.cornell_material_zoo(256, 256, 12, "vpt"), 16,
      [{}, {"B200PT_BIN_MATERIALS": "0"}, {"B200PT_FUSED": "0"}]),
     # tree kernel: two-child vs four-child records; binning in the HBM-pool shade kernel
-    ("veach_c3", lambda: pt.scenes.veach_standin(256, 192, 17), 16, [{}, {"B200PT_WIDE": "1"}, {"B200PT_BIN_MATERIALS": "0"}]),
+    ("veach_c3", lambda: pt.scenes.veach_standin(256, 192, 17), 16, [{}, {"B200PT_WIDE": "1"}, {"B200PT_BIN_MATERIALS": "0"}, {"B200PT_CULL_MIS": "0"}]),
     ("random_tris", lambda: pt.scenes.random_triangles(50000, 256, 256, 8), 8, [{}, {"B200PT_WIDE": "1"}, {"B200PT_LANES": "3"}]),
     ("textured_hair", lambda: pt.scenes.cornell_textured_hair(256, 256, 6), 16, [{}, {"B200PT_WIDE": "1"}]),
     # heterogeneous media: CTA-local coroutine vs the same coroutine over the HBM pool
-    ("smoke_shipped", lambda: pt.scenes.cornell_shipped_smoke(128, 128, 17), 8, [{}, {"B200PT_FUSED": "0"}]),
+    ("smoke_shipped", lambda: pt.scenes.cornell_shipped_smoke(128, 128, 17), 8, [{}, {"B200PT_FUSED": "0"}, {"B200PT_CULL_MIS": "0"}]),
+    ("cornell_c2", lambda: pt.scenes.cornell_pt(512, 512, 8), 16, [{}, {"B200PT_CULL_MIS": "0"}, {"B200PT_FUSED": "0"}]),
+    ("vol_caustic_c5", lambda: pt.scenes.cornell_vol_caustic(256, 256, 17), 16, [{}, {"B200PT_CULL_MIS": "0"}, {"B200PT_FUSED": "0"}]),
 ])
 def test_scheduling_options_do_not_change_a_bit(name, mk, spp, variants, monkeypatch):
     """Which kernel runs a slot, in which order, next to which other slots — CTA-local or HBM-pool wavefront, slots
-    sorted by BSDF class, medium walks in the trace phase, two- or four-child BVH records, number of lanes — is scheduling:
+    sorted by BSDF class, medium walks in the trace phase, two- or four-child BVH records, number of lanes, MIS rays that
+    cannot reach an emitter dropped — is scheduling:
     every sample has its own random-number stream and `Output` replays the iterations in order, so the accumulation image
     must be bit-identical under every option."""
     s = mk()
     images = []
     for env in variants:
-        for k in ("B200PT_FUSED", "B200PT_BIN_MATERIALS", "B200PT_WIDE", "B200PT_LANES"):
+        for k in ("B200PT_FUSED", "B200PT_BIN_MATERIALS", "B200PT_WIDE", "B200PT_LANES", "B200PT_CULL_MIS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

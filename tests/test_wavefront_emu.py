@@ -281,6 +281,27 @@ def test_material_binning_does_not_change_the_image(name, emu, oracle, monkeypat
             assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
 
 
+@pytest.mark.parametrize("name", ["cornell", "veach", "vol_caustic", "material_zoo_vpt", "textured_hair", "shipped_smoke", "random_tris"])
+def test_mis_rays_that_cannot_reach_an_emitter_are_not_traced(name, emu, oracle, monkeypatch):
+    """A BSDF-sampled light ray that fails the slab test of every box holding an emitter can never report one, so it is
+    dropped at emission — fewer rays, same bits as the oracle (which traces all of them).  Off when the scene has an
+    environment light (random_tris): a ray that escapes then carries radiance."""
+    s = SCENES[name]()
+    ref_acc, _ = oracle.render(s, 1, 3)
+    rays = []
+    for on in (0, 1):
+        monkeypatch.setenv("B200PT_CULL_MIS", str(on))
+        with pt.PathTracer(s) as r:
+            assert (r.info("emit_boxes") > 0) == bool(on and name != "random_tris")
+            r.render(1, reset=True, spp=3)
+            assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+            rays.append(r.stats()["rays"])
+    if name == "random_tris":
+        assert abs(rays[1] - rays[0]) <= 0.01 * rays[0]
+    else:
+        assert rays[1] < 0.95 * rays[0]
+
+
 @pytest.mark.parametrize("name", ["veach", "random_tris", "textured_hair"])
 def test_four_child_nodes_give_the_same_bits(name, emu, oracle, monkeypatch):
     """B200PT_WIDE=1: the tree kernel walks four-child records (every other level of the reference's tree collapsed).  The
