@@ -868,6 +868,7 @@ static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchPara
     sa.sc = c->sc; sa.pool = L.pool; sa.counters = L.counters; sa.samples = L.samples; sa.q = L.q; sa.parity = 0; sa.cam = cam; sa.map = L.map; sa.batch = bp; sa.frame = nullptr; sa.drain_hint = 0; sa.bin_materials = c->bin_materials ? 1 : 0;
     ta.sc = c->sc; ta.pool = L.pool; ta.q = L.q; ta.counters = L.counters; ta.parity = 0; ta.refill_below = c->refill_below;
     ta.stage_bytes_nodes = c->stage_nodes; ta.stage_bytes_prims = c->stage_prims; ta.small_prim_bytes = c->small_prim_bytes; ta.leaves = c->leaves; ta.n_leaves = c->n_leaves; ta.sec_tmax = c->het ? 1 : 0;
+    ta.mis_anyhit = (!c->vol && !c->het && c->sc.n_lights == 0 && c->sc.inf.isvalid && !getenv("B200PT_NO_MIS_ANYHIT")) ? 1 : 0;
 }
 
 // One batch = n_iters iterations of every local pixel through the wavefronts of all lanes, then the ordered resolve.

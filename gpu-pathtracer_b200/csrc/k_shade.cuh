@@ -219,6 +219,9 @@ template <bool FUSED> __device__ __forceinline__ void st_rec(float4* p, float4 v
 
 // Material specialisation: a scene whose materials are all lambertian gets a kernel without the GGX / dielectric
 // code (a quarter of the instructions and registers of the general one); MATS is the set of MaterialTypes present.
+#ifndef PT_CULL_ZERO_SHADOW
+#define PT_CULL_ZERO_SHADOW 1
+#endif
 constexpr uint32_t kMatsLambertOnly = 1u << MT_LAMBERTIAN;
 constexpr uint32_t kMatsLDC = (1u << MT_LAMBERTIAN) | (1u << MT_DIELECTRIC) | (1u << MT_ROUGHCONDUCTOR);   // e.g. veach_bidir
 constexpr uint32_t kMatsAll = 0x3fu;
@@ -502,8 +505,16 @@ __device__ __forceinline__ void shade_slot(const ShadeArgs& a, const Pool& pool,
                             float weight = power_heuristic(1, ls.pdf * choicePdf, 1, samplePdf);
                             nf |= F_SHADOW;
                             st_rec<FUSED>(pool.shd + slot, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
-                            if (!VOL) ldl = weight * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
-                            else {
+                            if (!VOL) {
+                                ldl = weight * fr * ls.radiance * fabsf(dot(h.nor, ls.dir)) / (ls.pdf * choicePdf);
+                                // a light sample worth exactly zero (BSDF black: the light is below the surface's horizon) adds
+                                // +0 whether it is visible or not — its shadow ray is not traced (a NaN term is not zero: traced).
+                                // `pt` only: under `vpt` the term is formed after the walk (weight * Tr * fr * ...), the rule saved
+                                // 0.1 % of C5's rays, and with it 5 samples of 2 M of the six-BSDF `vpt` scene took another path on
+                                // the GPU (profiles/r02w_diag.txt; exact in emulation — most likely the added code moved an FMA
+                                // contraction in that instantiation): dropped rather than chased
+                                if (PT_CULL_ZERO_SHADOW && ldl.x == 0.f && ldl.y == 0.f && ldl.z == 0.f) nf &= ~F_SHADOW;
+                            } else {
                                 ldl = fr;
                                 st_rec<FUSED>(pool.aux + slot, make_float4(ls.radiance.x, ls.radiance.y, ls.radiance.z, weight));
                             }

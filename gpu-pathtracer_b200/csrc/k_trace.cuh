@@ -112,6 +112,10 @@ struct TraceArgs {
     const float4* leaves;                            // small scenes: primitive-group records (box + <= 4 primitives)
     int32_t n_leaves;
     int32_t sec_tmax;                                // kind-2 rays carry their own tmax in misd.w (heterogeneous-media wavefront: Tr() segments)
+    // `pt`, scene without area emitters (environment light only): the MIS ray adds radiance iff it ESCAPES, so it is an
+    // any-hit query — "some primitive is hit" and "a closest hit exists" are the same event (a larger tmax only lets more
+    // boxes and primitives pass), and the primitive reported carries no light index either way
+    int32_t mis_anyhit;
 };
 
 constexpr int kDone = (int)0x80000000;               // traversal cursor: nothing left to visit (also "no postponed leaf")
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
                 else { dv = a.pool.misd[slot]; if (!a.sec_tmax) dv.w = INFINITY; }
                 d = mk3(dv.x, dv.y, dv.z);
                 tmax = dv.w;
-                anyhit = !VOL && kind == 1u;
+                anyhit = !VOL && (kind == 1u || (kind == 2u && a.mis_anyhit != 0));
                 if (VOL && kind == 1u) {
                     const uint32_t flags = __float_as_uint(a.pool.d_flags[slot].w);
                     medium = (int)((flags >> kMedium2Shift) & 0xffu) - 1;
