@@ -55,9 +55,19 @@ struct WaveArgs {
 // Shared-memory footprint of one CTA: scene (primitive records + group boxes) + path planes + ray queue.
 template <bool VOL> struct WavePlanes { static constexpr int value = VOL ? 15 : 14; };
 // ... + the per-ray box results of the sorted trace phase: hit-group mask (8 B), order (2 B) and nearest group (1 B) per queue entry
+// PT_WAVE_SORT = 1: the trace phase of the CTA-local wavefront runs in two passes — the box pass of every queued ray (the
+// same work for every ray: full SIMT width), a counting sort of the rays by (kind of query, number of hit groups) in shared
+// memory, and the primitive pass in that order: every ray needs a different number of Moeller-Trumbore tests, and in queue
+// order the primitive loop ran at 5-10 of 32 lanes (profiles/r02d_wave_c2_lines.txt).  It was worth +3.4 % on C2 while a
+// sample cost 10.2 rays; with the pruned ray set (6.4 rays per sample, wavefront.cuh) the three extra barriers per step cost
+// more than the fuller warps return — single pass: C2 1422 -> 1508 Msamples/s, C1 1651 -> 1768 (profiles/r02z_sort_again.txt).
+#ifndef PT_WAVE_SORT
+#define PT_WAVE_SORT 0
+#endif
 template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_leaves, int threads) {
     return (size_t)((prim_bytes + (uint32_t)n_leaves * 32u + 127u) & ~127u) + (size_t)WavePlanes<VOL>::value * threads * sizeof(float4) +
-           (size_t)3 * threads * sizeof(uint32_t) + (size_t)3 * threads * (sizeof(unsigned long long) + sizeof(uint16_t) + 2);
+           (size_t)3 * threads * sizeof(uint32_t) +
+           ((PT_WAVE_SORT != 0 && !VOL) ? (size_t)3 * threads * (sizeof(unsigned long long) + sizeof(uint16_t) + 2) : (size_t)0);   // sort arrays of the two-pass trace phase
 }
 
 #ifndef B200PT_EMULATE
@@ -69,13 +79,6 @@ template <bool VOL> inline size_t wave_smem_bytes(uint32_t prim_bytes, int n_lea
 #define PT_WAVE_SYNC() do { } while (0)
 #endif
 
-// The trace phase of the CTA-local wavefront runs in two passes (PT_WAVE_SORT): the box pass of every queued ray (the same
-// work for every ray: full SIMT width), a counting sort of the rays by (kind of query, number of hit groups) in shared
-// memory, and the primitive pass in that order — every ray needs a different number of Moeller-Trumbore tests, and in queue
-// order the primitive loop ran at 5-10 of 32 lanes (profiles/r02d_wave_c2_lines.txt).
-#ifndef PT_WAVE_SORT
-#define PT_WAVE_SORT 1
-#endif
 template <bool VOL> __device__ __forceinline__ uint32_t wave_sort_key(uint32_t entry, unsigned long long mask) {
     const uint32_t kind = entry >> kKindShift;
     const uint32_t n = (uint32_t)__popc((uint32_t)mask) + (uint32_t)__popc((uint32_t)(mask >> 32));
@@ -111,7 +114,7 @@ constexpr uint32_t kWaveShadeKeys = 36u;
 
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
-__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? PT_WAVE_MATS_CTAS : 3) * (256 / kWaveThreads)) k_wave_small(const WaveArgs a) {
+__global__ void __launch_bounds__(WaveThreads<HET>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? PT_WAVE_MATS_CTAS : 3) * (kWaveThreads <= 128 ? 256 / kWaveThreads : 1)) k_wave_small(const WaveArgs a) {
     constexpr int kT = WaveThreads<HET>::value;
     const ShadeArgs& sa = a.sa;
     const TraceArgs& ta = a.ta;
