@@ -112,11 +112,17 @@ int b200pt_trace_primary(b200pt_ctx* ctx, const void* camera, uint32_t iter, flo
 int b200pt_stats(b200pt_ctx* ctx, double* out5);
 
 /* Read-only facts about a context: "lanes" (independent wavefronts), "pool_per_lane" (path slots of one lane),
- * "groups" (primitive groups of the small-scene kernel, 0 if the tree kernel is used), "small_kernel", "lambert_only". */
+ * "groups" (primitive groups of the small-scene kernel, 0 if the tree kernel is used), "small_kernel", "lambert_only",
+ * "fused" (CTA-local wavefront in use), "wave_blocks", "bin_materials" (shade stage sorts its slots by BSDF class),
+ * "emit_boxes" (boxes a MIS ray must pass to reach an emitter; 0 = such rays are not culled), "wide" / "nodes4". */
 int b200pt_get_info(b200pt_ctx* ctx, const char* name, int64_t* out_value);
 
 /* Tunables (pool = number of path slots in flight; 0 keeps default).  "reserve_iters" = n pre-sizes the sample planes
- * for batches of up to n iterations, so that no later b200pt_render allocates inside the call. */
+ * for batches of up to n iterations, so that no later b200pt_render allocates inside the call.  Scheduling switches —
+ * none of them changes a bit of the image: "fused", "bin_materials", "wave_ctas_per_sm", "trace_ctas_per_sm",
+ * "refill_below", "graph", "steps_per_poll", "max_batch_bytes", "stage_smem".  Read at b200pt_create from the environment
+ * (A/B measurements): B200PT_FUSED, B200PT_BIN_MATERIALS, B200PT_CULL_MIS, B200PT_WIDE, B200PT_LANES, B200PT_WAVE_CTAS,
+ * B200PT_STAGE_BYTES. */
 int b200pt_set_option(b200pt_ctx* ctx, const char* name, int64_t value);
 
 /* Replaces EndRender (src/pathtracer.cu:2697); frees ALL device memory of the context. */
