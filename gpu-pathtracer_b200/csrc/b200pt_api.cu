@@ -45,6 +45,7 @@ struct Lane {
     Counters* h_counters = nullptr;       // pinned, 2 polling slots
     float4* samples = nullptr; size_t samples_cap = 0;   // in float4
     unsigned long long* h_init = nullptr; // pinned: initial {next_sample, done_samples} of a batch
+    uint16_t* sort_keys = nullptr; uint32_t *sort_hist = nullptr, *sort_offs = nullptr, *sort_out = nullptr;   // ray sorting (tree kernel)
     std::vector<void*> pool_allocs;       // cudaMalloc'ed pool/queue planes (re-allocated by the "pool" option)
     ShadeArgs sa; TraceArgs ta;
     int chunk = 0; bool done = false, exact_pending = false, nearly_done = false;
@@ -68,6 +69,7 @@ struct b200pt_ctx {
     uint32_t mats_used = 0;                // MaterialTypes referenced by primitives (picks the k_shade instantiation)
     float4* leaves = nullptr; int n_leaves = 0;   // primitive groups (scenes with <= 256 primitives)
     bool wide = false;                     // tree kernel walks four-child nodes (WNode4)
+    bool sort_rays = false;                // the tree kernel's queue is sorted by origin cell / direction octant before each trace step
     bool bin_materials = false;            // k_shade sorts its tile's records by material (scenes with more than one BSDF)
     int n_nodes4 = 0;
     bool small_scene = false;              // use k_trace_small
@@ -583,6 +585,7 @@ static void free_pool(Lane& L) {
     for (void* p : L.pool_allocs) cudaFree(p);
     L.pool_allocs.clear();
     L.pool = Pool{}; L.q.entries = nullptr;
+    L.sort_keys = nullptr; L.sort_hist = L.sort_offs = L.sort_out = nullptr;
 }
 static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
     free_pool(L);
@@ -598,7 +601,12 @@ static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
     };
     for (auto a : arrs) { int rc = grab((void**)a, (size_t)n * sizeof(float4)); if (rc) return rc; }
     p.n = n;
-    return grab((void**)&L.q.entries, (size_t)3 * n * sizeof(uint32_t));     // at most three rays per slot and step
+    int rc = grab((void**)&L.q.entries, (size_t)3 * n * sizeof(uint32_t));     // at most three rays per slot and step
+    if (rc || !c->sort_rays) return rc;
+    if ((rc = grab((void**)&L.sort_keys, (size_t)3 * n * sizeof(uint16_t)))) return rc;
+    if ((rc = grab((void**)&L.sort_out, (size_t)3 * n * sizeof(uint32_t)))) return rc;
+    if ((rc = grab((void**)&L.sort_hist, (size_t)kRaySortBins * sizeof(uint32_t)))) return rc;
+    return grab((void**)&L.sort_offs, (size_t)kRaySortBins * sizeof(uint32_t));
 }
 // Pool slots per lane: the context total split evenly, never more than 4 slots per pixel of the lane.
 static int lane_pool_size(const b200pt_ctx* c, const Lane& L) {
@@ -692,6 +700,9 @@ extern "C" int b200pt_create(const b200pt_scene_view* scene, uint32_t width, uin
     // scenes whose primitives fit in shared memory run the CTA-local wavefront (k_wave.cuh); B200PT_FUSED=0 keeps the
     // global wavefront (k_shade + k_trace_small over the HBM pool) for A/B runs
     c->fused = c->small_scene;
+    // ray sorting before the tree kernel (k_trace.cuh): opt-in, measured slower (profiles/r03c_sort_rays.txt)
+    c->sort_rays = false;
+    if (const char* env = getenv("B200PT_SORT_RAYS")) c->sort_rays = !c->small_scene && atoi(env) != 0;
     if (const char* env = getenv("B200PT_FUSED")) c->fused = c->fused && atoi(env) != 0;
     int n_lanes = c->fused ? 1 : (c->small_scene ? 3 : 2);
     if (const char* env = getenv("B200PT_LANES")) n_lanes = std::max(1, std::min(8, atoi(env)));
@@ -779,6 +790,7 @@ extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_val
     else if (n == "fused") *out_value = c->fused ? 1 : 0;
     else if (n == "bin_materials") *out_value = c->bin_materials ? 1 : 0;
     else if (n == "emit_boxes") *out_value = c->sc.n_emit_boxes;
+    else if (n == "sort_rays") *out_value = c->sort_rays ? 1 : 0;
     else if (n == "wide") *out_value = c->wide ? 1 : 0;
     else if (n == "nodes4") *out_value = c->n_nodes4;
     else if (n == "wave_blocks") *out_value = c->wave_blocks;
@@ -861,6 +873,18 @@ static void launch_trace(b200pt_ctx* c, const Lane& L, const TraceArgs& ta) {
         return;
     }
     const size_t smem = (size_t)c->stage_nodes + c->stage_prims + kTraceStackBytes;
+    if (c->sort_rays && L.sort_out) {
+        RaySortArgs sa;
+        sa.sc = c->sc; sa.pool = L.pool; sa.q = L.q; sa.parity = ta.parity; sa.sec_tmax = ta.sec_tmax;
+        sa.keys = L.sort_keys; sa.hist = L.sort_hist; sa.offs = L.sort_offs; sa.sorted = L.sort_out;
+        PT_LAUNCH(k_ray_hist, c->num_sms * 8, 256, 0, L.stream, sa);
+        PT_LAUNCH(k_ray_scan, 1, 1024, 0, L.stream, sa);
+        PT_LAUNCH(k_ray_scatter, c->num_sms * 8, 256, 0, L.stream, sa);
+        TraceArgs t2 = ta;
+        t2.q.entries = L.sort_out;
+        with_trace_kernel(c, [&](auto kernel) { PT_LAUNCH(kernel, c->trace_blocks, kTraceThreads, smem, L.stream, t2); });
+        return;
+    }
     with_trace_kernel(c, [&](auto kernel) { PT_LAUNCH(kernel, c->trace_blocks, kTraceThreads, smem, L.stream, ta); });
 }
 static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchParams& bp) {
@@ -940,7 +964,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
                 launch_trace(c, L, L.ta); L.ta.parity ^= 1u;
                 L.sa.parity ^= 1u; launch_shade(c, L, L.sa);
             }
-            *launches += 2.0 * n_steps; *steps += n_steps;
+            *launches += (c->sort_rays && L.sort_out && !c->small_scene ? 5.0 : 2.0) * n_steps; *steps += n_steps;
             const int slot = L.chunk & 1;
             CK(cudaMemcpyAsync(&L.h_counters[slot], L.counters, sizeof(Counters), cudaMemcpyDeviceToHost, L.stream));
             if (capture) { L.done = true; ++L.chunk; continue; }      // verdict is read by the caller after the graph has run

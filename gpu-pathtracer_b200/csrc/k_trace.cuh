@@ -397,6 +397,75 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const TraceArgs a) {
 #undef STK_PUSH
 #undef STK_POP
 
+// ---- ray sorting for the tree kernel ------------------------------------------------------------------------------------------
+// After the first bounce the 32 rays a warp pulls from the queue have nothing in common: they start anywhere in the scene
+// and point anywhere, every lane walks its own part of the tree, and the node loop runs at a third of the SIMT width (C4:
+// 11.7 of 32 lanes).  Before k_trace, the step's queue is therefore counting-sorted by
+//     key = any-hit query | Morton code of the origin's cell (16^3 cells over the root box) | octant of the direction,
+// so that the rays of a warp enter the tree through the same top nodes and tend to stay together.  Three small kernels on
+// the lane's stream (histogram, one-CTA scan, scatter); the queue itself is not touched — k_trace reads the sorted copy.
+// Pure scheduling: which lane traces a ray changes, nothing about the ray does.
+// MEASURED AND LEFT OFF (B200PT_SORT_RAYS=1 switches it on; profiles/r03c_sort_rays.txt): the node loop of C4 goes from 11.7
+// to 12.3 of 32 lanes only — rays that start in the same cell and octant still part ways within a few levels of a
+// 20-level tree over a triangle soup, the divergence is in trip counts, not in entry points — and the three extra
+// kernels cost more than that returns: C4 126 -> 106 Msamples/s, C3 460 -> 220 (its steps are 0.3 ms long), hair 464 -> 240.
+constexpr int kRaySortBins = 1 << 16;
+struct RaySortArgs {
+    SceneDev sc; Pool pool; RayQueue q; uint32_t parity; int32_t sec_tmax;
+    uint16_t* keys; uint32_t* hist; uint32_t* offs; uint32_t* sorted;
+};
+__device__ __forceinline__ uint32_t morton3_4bit(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t m = 0u;
+    for (int b = 0; b < 4; ++b) m |= (((x >> b) & 1u) << (3 * b)) | (((y >> b) & 1u) << (3 * b + 1)) | (((z >> b) & 1u) << (3 * b + 2));
+    return m;
+}
+__global__ void __launch_bounds__(256) k_ray_hist(const RaySortArgs a) {
+    const uint32_t tail = a.q.ctl->tail[a.parity & 1u];
+    const float sx = 16.f / fmaxf(a.sc.root_max[0] - a.sc.root_min[0], 1e-30f), sy = 16.f / fmaxf(a.sc.root_max[1] - a.sc.root_min[1], 1e-30f),
+                sz = 16.f / fmaxf(a.sc.root_max[2] - a.sc.root_min[2], 1e-30f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tail; i += gridDim.x * blockDim.x) {
+        const uint32_t entry = a.q.entries[i];
+        const uint32_t slot = entry & kSlotMask, kind = entry >> kKindShift;
+        const float4 o = kind == 0u ? a.pool.o_rng[slot] : a.pool.pend_o[slot];
+        const float4 d = kind == 0u ? a.pool.d_flags[slot] : (kind == 1u ? a.pool.shd[slot] : a.pool.misd[slot]);
+        const float fx = fminf(fmaxf((o.x - a.sc.root_min[0]) * sx, 0.f), 15.f), fy = fminf(fmaxf((o.y - a.sc.root_min[1]) * sy, 0.f), 15.f),
+                    fz = fminf(fmaxf((o.z - a.sc.root_min[2]) * sz, 0.f), 15.f);
+        const int cx = (int)fx, cy = (int)fy, cz = (int)fz;           // (a NaN origin lands in cell 0: fmaxf drops it)
+        const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+        const uint32_t key = (kind == 1u ? 0x8000u : 0u) | (morton3_4bit((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3) | oct;
+        a.keys[i] = (uint16_t)key;
+        atomicAdd(&a.hist[key], 1u);
+    }
+}
+// one CTA: counts -> exclusive start offsets (into `offs`), counts cleared for the next step
+__global__ void __launch_bounds__(1024) k_ray_scan(const RaySortArgs a) {
+    constexpr int kPer = kRaySortBins / 1024;
+    __shared__ uint32_t s_part[1024];
+    const uint32_t t = threadIdx.x;
+    uint32_t sum = 0u;
+    for (int k = 0; k < kPer; ++k) sum += a.hist[t * kPer + k];
+    s_part[t] = sum;
+    __syncthreads();
+#ifndef B200PT_EMULATE
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {            // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = t >= off ? s_part[t - off] : 0u;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[t] - sum;
+#else
+    uint32_t run = 0u;
+    for (uint32_t k = 0; k < t; ++k) run += s_part[k];
+#endif
+    for (int k = 0; k < kPer; ++k) { const uint32_t c = a.hist[t * kPer + k]; a.offs[t * kPer + k] = run; run += c; a.hist[t * kPer + k] = 0u; }
+}
+__global__ void __launch_bounds__(256) k_ray_scatter(const RaySortArgs a) {
+    const uint32_t tail = a.q.ctl->tail[a.parity & 1u];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tail; i += gridDim.x * blockDim.x)
+        a.sorted[atomicAdd(&a.offs[a.keys[i]], 1u)] = a.q.entries[i];
+}
+
 // All group boxes of a small scene against one ray, warp-uniform: the hit groups as a 64-bit mask and the group the ray
 // enters first.
 __device__ __forceinline__ void small_ray_boxes(const TraceArgs& a, const float4* __restrict__ leaves, const f3 o, const f3 inv, const float tmax,

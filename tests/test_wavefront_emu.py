@@ -303,6 +303,24 @@ def test_mis_rays_that_cannot_reach_an_emitter_are_not_traced(name, emu, oracle,
 
 
 @pytest.mark.parametrize("name", ["veach", "random_tris", "textured_hair"])
+def test_sorting_the_ray_queue_does_not_change_the_image(name, emu, oracle, monkeypatch):
+    """Tree kernel: the step's ray queue is counting-sorted by (any-hit, origin cell, direction octant) before k_trace, so
+    that the rays of a warp enter the tree together.  Which lane traces a ray is scheduling: same bits as the oracle."""
+    s = SCENES[name]()
+    ref_acc, _ = oracle.render(s, 1, 3)
+    monkeypatch.setenv("B200PT_FUSED", "0")
+    monkeypatch.setenv("B200PT_STAGE_BYTES", "0")
+    for on in (0, 1):
+        monkeypatch.setenv("B200PT_SORT_RAYS", str(on))
+        with pt.PathTracer(s, pool=2048) as r:
+            r.set_option("small_kernel", 0)
+            assert r.info("sort_rays") == on or r.info("small_kernel") == 1
+            r.render(1, reset=True, spp=3)
+            assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+            assert r.stats()["launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["veach", "random_tris", "textured_hair"])
 def test_four_child_nodes_give_the_same_bits(name, emu, oracle, monkeypatch):
     """B200PT_WIDE=1: the tree kernel walks four-child records (every other level of the reference's tree collapsed).  The
     slab test is monotone in the box, so the same primitives reach the exact primitive test: same bits."""
