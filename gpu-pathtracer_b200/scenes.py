@@ -444,6 +444,40 @@ def veach_standin(width=768, height=576, max_depth=17, prep=None):
                     L.cat(prims, L.Primitive), L.cat(lights, L.Area), prep=prep)
 
 
+def room_with_lights(n_lights=6, width=128, height=96, max_depth=6, sky=False, prep=None):
+    """A closed room with `n_lights` small ceiling emitters and two blocks (and optionally the analytic sky as an
+    environment light): exercises the emitter-box list of the MIS-ray pruning — short list, list over the limit (> 16
+    boxes: pruning off), environment light present (pruning off)."""
+    mats = L.cat([make_material("lambertian", diffuse=(0.7, 0.7, 0.7)), make_material("lambertian", diffuse=(0.6, 0.3, 0.2)),
+                  make_material("roughconduct", alphaU=0.3, alphaV=0.3, eta=(2.8, 2.1, 1.9), k=(3.0, 2.0, 1.6))], L.Material)
+    prims = [triangles_to_prims(*_box_tris((-2.0, -2.0, 0.0), (2.0, 2.0, 2.5), inward=True), 0),
+             triangles_to_prims(*_box_tris((-1.2, -0.6, 0.0), (-0.4, 0.2, 0.9)), 1),
+             triangles_to_prims(*_box_tris((0.3, -0.2, 0.0), (1.1, 0.6, 1.4)), 2)]
+    lights = []
+    cols = max(1, int(np.ceil(np.sqrt(n_lights))))
+    for i in range(n_lights):
+        cx = -1.6 + 3.2 * ((i % cols) + 0.5) / cols
+        cy = -1.6 + 3.2 * ((i // cols) + 0.5) / cols
+        p0 = np.asarray((cx - 0.08, cy - 0.08, 2.49), F)
+        q = [p0, p0 + np.asarray((0.16, 0, 0), F), p0 + np.asarray((0.16, 0.16, 0), F), p0 + np.asarray((0, 0.16, 0), F)]
+        tv = np.asarray([[q[0], q[2], q[1]], [q[0], q[3], q[2]]], F)
+        tn = np.tile(np.asarray((0, 0, -1), F), (2, 3, 1))
+        tuv = np.zeros((2, 3, 2), F)
+        p = triangles_to_prims(tv, tn, tuv, 0, -1, -1, light_base=2 * i)
+        a = np.zeros(2, L.Area)
+        a["radiance"] = np.asarray((30.0, 28.0, 24.0), F) * (1.0 + 0.1 * i); a["triangle"] = p["triangle"]; a["medium"] = -1
+        prims.append(p); lights.append(a)
+    cam = {"position": [0.0, -1.9, 1.2], "lookat": [0.0, 0.0, 0.9], "up": [0.0, 0.0, 1.0], "fov": 60.0, "medium": -1}
+    infinite = texels = None
+    if sky:
+        texels = sky_texels(64, 32)
+        infinite = np.zeros(1, L.Infinite)
+        infinite["data"] = texels.ctypes.data; infinite["width"] = texels.shape[1]; infinite["height"] = texels.shape[0]
+        infinite["u"] = (1, 0, 0); infinite["v"] = (0, 1, 0); infinite["w"] = (0, 0, 1); infinite["isvalid"] = 1
+    return assemble(f"room_{n_lights}_lights" + ("_sky" if sky else ""), width, height, 0.001, "pt", max_depth, cam, mats, np.zeros(0, L.Medium),
+                    L.cat(prims, L.Primitive), L.cat(lights, L.Area) if lights else np.zeros(0, L.Area), infinite=infinite, infinite_texels=texels, prep=prep)
+
+
 def sky_texels(w=512, h=256):
     """Analytic HDRI for C4: vertical sky gradient + Gaussian sun (no .exr is shipped)."""
     v = (np.arange(h, dtype=np.float64) + 0.5) / h           # 0 = +v pole (zenith)

@@ -87,6 +87,9 @@ def main():
         "material_zoo_pt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 8, "pt", prep=prep),
         "material_zoo_vpt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 12, "vpt", prep=prep),
         "environment_camera_128x64": lambda: pt.scenes.cornell_environment_camera(128, 64, 6, prep=prep),
+        # several area lights (emitter-box list of the MIS-ray pruning), alone and next to an environment light
+        "room_6_lights_64x48": lambda: pt.scenes.room_with_lights(6, 64, 48, 6, prep=prep),
+        "room_4_lights_sky_64x48": lambda: pt.scenes.room_with_lights(4, 64, 48, 6, sky=True, prep=prep),
     }
     only = [a for a in sys.argv[1:] if not a.startswith("-")]          # optional: regenerate just these fixtures
     for name, mk in scenes.items():

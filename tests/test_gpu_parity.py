@@ -31,6 +31,10 @@ SCENES = {
     "material_zoo_pt": (lambda: pt.scenes.cornell_material_zoo(256, 256, 8, "pt"), 32),
     "material_zoo_vpt": (lambda: pt.scenes.cornell_material_zoo(256, 256, 12, "vpt"), 32),
     "environment_camera": (lambda: pt.scenes.cornell_environment_camera(256, 128, 6), 32),
+    # several area lights (short emitter-box list: MIS rays pruned), many (list over the limit: not pruned), area + environment light
+    "room_6_lights": (lambda: pt.scenes.room_with_lights(6, 256, 192, 6), 32),
+    "room_40_lights": (lambda: pt.scenes.room_with_lights(40, 256, 192, 6), 32),
+    "room_4_lights_sky": (lambda: pt.scenes.room_with_lights(4, 256, 192, 6, sky=True), 32),
 }
 
 

@@ -25,6 +25,8 @@ SCENES = {
     "material_zoo_pt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 8, "pt"),
     "material_zoo_vpt_64": lambda: pt.scenes.cornell_material_zoo(64, 64, 12, "vpt"),
     "environment_camera_128x64": lambda: pt.scenes.cornell_environment_camera(128, 64, 6),
+    "room_6_lights_64x48": lambda: pt.scenes.room_with_lights(6, 64, 48, 6),               # several emitters (MIS-ray pruning)
+    "room_4_lights_sky_64x48": lambda: pt.scenes.room_with_lights(4, 64, 48, 6, sky=True),  # area + environment light
 }
 
 

@@ -35,6 +35,8 @@ SCENES = {
     "material_zoo_pt": lambda: pt.scenes.cornell_material_zoo(64, 64, 8, "pt"),     # all six BSDFs, thin lens, gamma tone map
     "material_zoo_vpt": lambda: pt.scenes.cornell_material_zoo(64, 64, 12, "vpt"),  # + Henyey-Greenstein media, g = 0.6 / 5e-4 / -0.4
     "environment_camera": lambda: pt.scenes.cornell_environment_camera(128, 64, 6),  # lat-long camera
+    "room_6_lights": lambda: pt.scenes.room_with_lights(6, 64, 48, 6),               # several emitters
+    "room_4_lights_sky": lambda: pt.scenes.room_with_lights(4, 64, 48, 6, sky=True), # area lights + environment light
 }
 
 
@@ -300,6 +302,18 @@ def test_mis_rays_that_cannot_reach_an_emitter_are_not_traced(name, emu, oracle,
         assert abs(rays[1] - rays[0]) <= 0.01 * rays[0]
     else:
         assert rays[1] < 0.95 * rays[0]
+
+
+@pytest.mark.parametrize("n_lights,sky,expect_boxes", [(1, False, True), (6, False, True), (30, False, True), (40, False, False), (4, True, False), (0, True, False)])
+def test_emitter_box_list_limits(n_lights, sky, expect_boxes, emu, oracle):
+    """MIS-ray pruning is on only when the emitter boxes (BVH leaves + primitive groups holding a light) make a short
+    list (<= 16) and the scene has no environment light; on or off, fused or not, the image is the oracle's."""
+    s = pt.scenes.room_with_lights(n_lights, 64, 48, 6, sky=sky)
+    ref_acc, _ = oracle.render(s, 1, 3)
+    with pt.PathTracer(s) as r:
+        assert (r.info("emit_boxes") > 0) == expect_boxes, r.info("emit_boxes")
+        r.render(1, reset=True, spp=3)
+        assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
 
 
 @pytest.mark.parametrize("name", ["veach", "random_tris", "textured_hair"])
