@@ -45,6 +45,7 @@ struct Lane {
     Counters* h_counters = nullptr;       // pinned, 2 polling slots
     float4* samples = nullptr; size_t samples_cap = 0;   // in float4
     unsigned long long* h_init = nullptr; // pinned: initial {next_sample, done_samples} of a batch
+    int pool_cap = 0;                     // slots allocated; pool.n = slots the current batch uses (<= pool_cap)
     uint16_t* sort_keys = nullptr; uint32_t *sort_hist = nullptr, *sort_offs = nullptr, *sort_out = nullptr;   // ray sorting (tree kernel)
     std::vector<void*> pool_allocs;       // cudaMalloc'ed pool/queue planes (re-allocated by the "pool" option)
     ShadeArgs sa; TraceArgs ta;
@@ -78,7 +79,8 @@ struct b200pt_ctx {
     uint32_t small_prim_bytes = 0;
     size_t max_batch_bytes = (size_t)2 << 30;
     int steps_per_poll = 8;
-    int pool_total = 1 << 21;              // path slots over all lanes (2^21 against 2^20: C3 +3.8 %, hair +3.3 %, C4 +4.4 %; 2^22 adds nothing: profiles/r02t_pool2m.txt)
+    int pool_total = 1 << 22;              // path slots ALLOCATED over all lanes; a batch uses as many as pay for it (batch_pool_slots)
+    bool pool_explicit = false;            // set by the "pool" option: every batch uses exactly that many
     double stats[5] = {0, 0, 0, 0, 0};
     double total_ms = 0;
     bool vol = false;
@@ -584,7 +586,7 @@ static size_t wave_smem(const b200pt_ctx* c) {
 static void free_pool(Lane& L) {
     for (void* p : L.pool_allocs) cudaFree(p);
     L.pool_allocs.clear();
-    L.pool = Pool{}; L.q.entries = nullptr;
+    L.pool = Pool{}; L.q.entries = nullptr; L.pool_cap = 0;
     L.sort_keys = nullptr; L.sort_hist = L.sort_offs = L.sort_out = nullptr;
 }
 static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
@@ -600,7 +602,7 @@ static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
         return 0;
     };
     for (auto a : arrs) { int rc = grab((void**)a, (size_t)n * sizeof(float4)); if (rc) return rc; }
-    p.n = n;
+    p.n = n; L.pool_cap = n;
     int rc = grab((void**)&L.q.entries, (size_t)3 * n * sizeof(uint32_t));     // at most three rays per slot and step
     if (rc || !c->sort_rays) return rc;
     if ((rc = grab((void**)&L.sort_keys, (size_t)3 * n * sizeof(uint16_t)))) return rc;
@@ -608,12 +610,12 @@ static int alloc_pool(b200pt_ctx* c, Lane& L, int n) {
     if ((rc = grab((void**)&L.sort_hist, (size_t)kRaySortBins * sizeof(uint32_t)))) return rc;
     return grab((void**)&L.sort_offs, (size_t)kRaySortBins * sizeof(uint32_t));
 }
-// Pool slots per lane: the context total split evenly, never more than 4 slots per pixel of the lane.
+// Pool slots per lane: the context total split evenly, never more than 8 slots per pixel of the lane.
 static int lane_pool_size(const b200pt_ctx* c, const Lane& L) {
     int pool = std::max(1024, c->pool_total / (int)c->lanes.size());
     // a lane whose pixels almost fit gets one slot per pixel: a 1-spp Render call then runs in exact-step mode
     if (L.map.n_local_pixels > pool && (double)L.map.n_local_pixels <= 1.1 * pool) pool = L.map.n_local_pixels;
-    if ((size_t)pool > (size_t)L.map.n_local_pixels * 4) pool = std::max(1024, L.map.n_local_pixels * 4);
+    if ((size_t)pool > (size_t)L.map.n_local_pixels * 8) pool = std::max(1024, L.map.n_local_pixels * 8);
     return pool;
 }
 
@@ -783,7 +785,7 @@ extern "C" int b200pt_get_info(b200pt_ctx* c, const char* name, int64_t* out_val
     if (!c || !name || !out_value) return fail(B200PT_EINVAL, "null argument");
     const std::string n(name);
     if (n == "lanes") *out_value = (int64_t)c->lanes.size();
-    else if (n == "pool_per_lane") *out_value = c->lanes.empty() ? 0 : (int64_t)c->lanes[0].pool.n;
+    else if (n == "pool_per_lane") *out_value = c->lanes.empty() ? 0 : (int64_t)c->lanes[0].pool_cap;
     else if (n == "groups") *out_value = c->small_scene ? c->n_leaves : 0;
     else if (n == "small_kernel") *out_value = c->small_scene ? 1 : 0;
     else if (n == "lambert_only") *out_value = c->lambert_only ? 1 : 0;
@@ -809,7 +811,7 @@ extern "C" int b200pt_set_option(b200pt_ctx* c, const char* name, int64_t value)
         if (value < 256 || value > (1 << 26)) return fail(B200PT_EINVAL, "pool must be in [256, 2^26]");
         CK(cudaSetDevice(c->device));
         CK(cudaDeviceSynchronize());
-        c->pool_total = (int)value;
+        c->pool_total = (int)value; c->pool_explicit = true;
         for (Lane& L : c->lanes) {
             int rc = alloc_pool(c, L, std::max(256, (int)value / (int)c->lanes.size()));
             if (rc) return rc;
@@ -895,6 +897,22 @@ static void fill_args(b200pt_ctx* c, Lane& L, const Camera& cam, const BatchPara
     ta.mis_anyhit = (!c->vol && !c->het && c->sc.n_lights == 0 && c->sc.inf.isvalid && !getenv("B200PT_NO_MIS_ANYHIT")) ? 1 : 0;
 }
 
+// How many of a lane's slots a batch of `need` samples uses.  Every wavefront step has a fixed cost (two launches, and a
+// kernel cannot end before its longest ray has), so more slots = fewer, fuller steps — until the batch has too few samples
+// per slot to keep them regenerating and the ramp / drain steps take over.  Measured (profiles/r03f_pool_sweep.txt,
+// r03f_pool_adaptive.txt): C3 at 64 spp (28 M samples) with 0.26 / 0.5 / 1 / 2 / 4 / 8 / 16 M slots -> 402 / 448 / 469 / 486 /
+// 501 / 493 / 476 Msamples/s; hair at 32 spp best at 4 samples per slot, C4 at 8 spp flat from 4 to 8 — so a batch uses
+// need / 5 slots, at least 2^19 per lane.  All samples in flight at once (one pass, max_depth + 1 steps, no regeneration) is
+// kept for the one-Render-per-frame usage, where it is the only choice: at 8 spp it loses 6 % against two passes.
+static int batch_pool_slots(const b200pt_ctx* c, const Lane& L, size_t need) {
+    if (c->pool_explicit) return L.pool_cap;
+    size_t n;
+    if (need <= (size_t)L.map.n_local_pixels + (size_t)L.map.n_local_pixels / 8) n = need;          // one iteration: exact-step frame
+    else n = std::max<size_t>(need / 5, (size_t)1 << 19);
+    n = (std::min<size_t>(n, need) + 255) & ~(size_t)255;
+    return (int)std::min<size_t>(n, (size_t)L.pool_cap);
+}
+
 // One batch = n_iters iterations of every local pixel through the wavefronts of all lanes, then the ordered resolve.
 // Lane streams are forked from / joined into lane 0's stream with events, so the caller sees one ordered stream.
 // `capture`: the call is being recorded into a CUDA graph (exact-step mode only: no allocation, no host polling, and
@@ -930,6 +948,7 @@ static int run_batch(b200pt_ctx* c, const Camera& cam, uint32_t first_iter, uint
             L.done = true;
             continue;
         }
+        L.pool.n = batch_pool_slots(c, L, need);
         bp.k_static = (uint32_t)((need - need / 4) / (unsigned long long)L.pool.n);      // ~3/4 of the batch by static assignment
         // next_sample starts behind the statically assigned range; done_samples at 0 (rays keeps counting)
         L.h_init[0] = (unsigned long long)bp.k_static * (unsigned long long)L.pool.n; L.h_init[1] = 0ull;
@@ -1037,7 +1056,7 @@ extern "C" int b200pt_render(b200pt_ctx* c, const void* camera, uint32_t first_i
     // one Render per frame (`pt`, 1 spp, every lane single-pass): the whole frame — uploads, shade / trace steps of all
     // lanes, resolves — is ONE captured CUDA graph, replayed with the per-call inputs refreshed through c->d_frame
     bool graph_frame = c->use_graph && !c->vol && spp == 1;
-    if (!c->fused) for (Lane& L : c->lanes) if (L.map.n_local_pixels > L.pool.n) graph_frame = false;
+    if (!c->fused) for (Lane& L : c->lanes) if (L.map.n_local_pixels > L.pool_cap) graph_frame = false;
     if (graph_frame) {
         for (Lane& L : c->lanes) {
             int rc2 = ensure_samples(c, L, (size_t)L.map.n_local_pixels);
@@ -1133,6 +1152,7 @@ extern "C" int b200pt_trace_primary(b200pt_ctx* c, const void* camera, uint32_t 
     L.map = c->map;
     const uint32_t npix = c->width * c->height;
     std::vector<float4> hits(npix);
+    L.pool.n = L.pool_cap;
     const uint32_t P = (uint32_t)L.pool.n;
     int rc = 0;
     if ((rc = ensure_samples(c, L, npix))) { L.map = saved_map; return rc; }
