@@ -579,7 +579,11 @@ template <class F> static void with_wave_kernel(const b200pt_ctx* c, F&& f) {
         else f(k_wave_small<false, kMatsAll, false>, false);
     }
 }
-static int wave_threads(const b200pt_ctx* c) { return c->het ? WaveThreads<true>::value : WaveThreads<false>::value; }
+static int wave_threads(const b200pt_ctx* c) {
+    if (c->het) return WaveThreads<true>::value;
+    const bool all_mats = !c->lambert_only && (c->mats_used & ~kMatsLDC) != 0u;       // the instantiation with_wave_kernel picks
+    return all_mats ? WaveThreads<false, kMatsAll>::value : WaveThreads<false>::value;
+}
 static size_t wave_smem(const b200pt_ctx* c) {
     return c->vol ? wave_smem_bytes<true>(c->small_prim_bytes, c->n_leaves, wave_threads(c)) : wave_smem_bytes<false>(c->small_prim_bytes, c->n_leaves, wave_threads(c));
 }
