@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(WaveThreads<HET, MATS>::value, HET ? PT_WAVE_H
             if (t < 32u) s_hist[t] = 0u;
             if (bin && t < kWaveShadeKeys) { s_mcnt[t] = 0u; s_mpos[t] = 0u; }
         }
-        // (measured, profiles/r02i_sort_ab.txt: sorted passes +3.4 % on C2, +2.4 % on C1, +5 % on the material zoo; -5 % on C5,
-        // whose shadow queries are multi-leg transmittance walks — `vpt` keeps the single pass)
+        // (two-pass trace phase, compiled out by default — see PT_WAVE_SORT above; never used for `vpt`, whose shadow queries are
+        // multi-leg transmittance walks: -5 % on C5, profiles/r02i_sort_ab.txt)
         constexpr bool kSort = (PT_WAVE_SORT != 0) && !VOL;
         if (kSort) {
             PT_WAVE_SYNC();
