@@ -1,20 +1,23 @@
 """Scene front-end: the data formats on the caller side of the hot path.
 
-Reads the reference's scene JSON (src/parsescene.cpp:45-590) and Wavefront OBJ meshes, and generates the
-synthetic benchmark scenes of BASELINE.json (C3 stand-in geometry, C4 random triangles + analytic HDRI).
+Reads the reference's scene JSON (src/parsescene.cpp:45-590) with Wavefront OBJ / Stanford PLY meshes (meshio.py) and an
+OpenEXR environment map (exr.py), and generates the synthetic benchmark scenes of BASELINE.json (C3 stand-in geometry, C4 random triangles + analytic HDRI).
 Output is a `SceneArrays` holding numpy arrays in the reference's struct layouts (layouts.py) — exactly what
 `b200pt_scene_view` (include/b200pt.h) points at.  BVH, light CDF and camera go through the host-side C ABI
 (`b200pt_bvh_build`, `b200pt_light_distribution`, `b200pt_camera_init`) unless a `prep` override is given
 (the tests pass the reference's own Scene::Init from oracle/_ref to pin them).
 
 Mesh import caveat: the reference imports through Assimp, which is not available; meshes with
-explicit normals and triangle faces (all config geometry) are unambiguous, anything else is rejected loudly.
+explicit normals (all config geometry) are unambiguous — polygons are triangulated by Assimp's documented rule — and
+normals generated for meshes without them follow Assimp's rule but are not pinned against it (meshio.py says what is).
 """
 import json
 import os
 from dataclasses import dataclass, field
 
 import numpy as np
+
+from . import exr, meshio
 
 from . import layouts as L
 
@@ -46,45 +49,14 @@ class SceneArrays:
 
 # ------------------------------------------------------------------------------------------------ OBJ / meshes
 def load_obj(path):
-    """Triangles of an OBJ file as (n_tri, 3) records of (v, n, uv). Requires explicit vn; fan-triangulates
-    polygons in file order (Assimp's Triangulate does the same for convex quads)."""
-    vs, vns, vts, faces = [], [], [], []
-    with open(path) as f:
-        for line in f:
-            p = line.split()
-            if not p:
-                continue
-            if p[0] == "v":
-                vs.append([float(x) for x in p[1:4]])
-            elif p[0] == "vn":
-                vns.append([float(x) for x in p[1:4]])
-            elif p[0] == "vt":
-                vts.append([float(x) for x in p[1:3]])
-            elif p[0] == "f":
-                corners = []
-                for c in p[1:]:
-                    idx = c.split("/")
-                    vi = int(idx[0])
-                    ti = int(idx[1]) if len(idx) > 1 and idx[1] else 0
-                    ni = int(idx[2]) if len(idx) > 2 and idx[2] else 0
-                    if ni == 0:
-                        raise ValueError(f"{path}: face without normals; smooth-normal generation (Assimp) is not reproduced")
-                    corners.append((vi, ti, ni))
-                for k in range(1, len(corners) - 1):
-                    faces.append((corners[0], corners[k], corners[k + 1]))
-    vs = np.asarray(vs, F).reshape(-1, 3)
-    vns = np.asarray(vns, F).reshape(-1, 3)
-    vts = np.asarray(vts, F).reshape(-1, 2)
-    tri_v = np.zeros((len(faces), 3, 3), F)
-    tri_n = np.zeros((len(faces), 3, 3), F)
-    tri_uv = np.zeros((len(faces), 3, 2), F)
-    for i, fc in enumerate(faces):
-        for k, (vi, ti, ni) in enumerate(fc):
-            tri_v[i, k] = vs[vi - 1 if vi > 0 else vi]
-            tri_n[i, k] = vns[ni - 1 if ni > 0 else ni]
-            if ti:
-                tri_uv[i, k] = vts[ti - 1 if ti > 0 else ti]
-    return tri_v, tri_n, tri_uv
+    """Triangles of an OBJ file as (n_tri, 3) arrays of (v, n, uv): meshio.load_obj (polygons triangulated by assimp's rule,
+    missing normals generated)."""
+    return meshio.load_obj(path)
+
+
+def load_mesh(path):
+    """.obj or .ply (the veach_bidir assets the reference does not ship are .ply): meshio.load_mesh."""
+    return meshio.load_mesh(path)
 
 
 def _trs(scale, translate, rotate_deg):
@@ -235,7 +207,8 @@ def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials
 
 def load_scene_json(path, prep=None, overrides=None):
     """The subset of LoadScene (src/parsescene.cpp:45) the hot path's configs use: homogeneous and heterogeneous media, constant
-    colour materials, OBJ meshes with TRS, spheres, mesh area lights.  Raises on anything else."""
+    colour materials, OBJ / PLY meshes with TRS (polygons triangulated, missing normals generated: meshio.py), spheres, mesh
+    area lights, an .exr infinite light (exr.py).  Raises on anything else."""
     with open(path) as f:
         doc = json.load(f)
     if overrides:
@@ -306,7 +279,7 @@ def load_scene_json(path, prep=None, overrides=None):
         if mat_name != "" or not (mi != -1 or mo != -1):
             midx = mat_idx(mat_name)
         if "mesh" in u:
-            tv, tn, tuv = load_obj(os.path.join(base, u["mesh"]))
+            tv, tn, tuv = load_mesh(os.path.join(base, u["mesh"]))
             trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
             tv, tn = _transform_mesh(tv, tn, trs)
             prims.append(triangles_to_prims(tv, tn, tuv, midx, mi, mo))
@@ -316,10 +289,24 @@ def load_scene_json(path, prep=None, overrides=None):
             raise ValueError("line primitives are a 'next' row (SURVEY §8(f).2)")
     lights = []
     n_lights = 0
+    infinite = infinite_texels = None
     for u in doc.get("light", []):
+        if "infinite" in u:
+            # src/parsescene.cpp:544-580: texels through ImageIO::LoadExr (RGB of tinyexr's RGBA, rows in file order), frame
+            # u / v / w = the columns of Rx * Ry * Rz ("rotate", degrees).  The reference leaves the frame UNINITIALISED when
+            # neither "rotate" nor "matrix" is given, and "matrix" goes through glm::inverse — both are rejected here.
+            if "matrix" in u or "rotate" not in u:
+                raise ValueError("infinite light: give \"rotate\" (the reference leaves the frame uninitialised without it; \"matrix\" is not reproduced)")
+            infinite_texels = np.ascontiguousarray(exr.load_exr(os.path.join(base, u["infinite"]))[..., :3], F)
+            R = _trs([1, 1, 1], [0, 0, 0], u["rotate"])
+            infinite = np.zeros(1, L.Infinite)
+            infinite["data"] = infinite_texels.ctypes.data
+            infinite["width"] = infinite_texels.shape[1]; infinite["height"] = infinite_texels.shape[0]
+            infinite["u"] = R[:3, 0]; infinite["v"] = R[:3, 1]; infinite["w"] = R[:3, 2]; infinite["isvalid"] = 1
+            continue
         if "mesh" not in u:
-            raise ValueError("infinite lights load from .exr, which is not shipped; use the generators")
-        tv, tn, tuv = load_obj(os.path.join(base, u["mesh"]))
+            raise ValueError("only mesh area lights and .exr infinite lights exist (src/parsescene.cpp:583)")
+        tv, tn, tuv = load_mesh(os.path.join(base, u["mesh"]))
         trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
         tv, tn = _transform_mesh(tv, tn, trs)
         # light triangles: mediumInside/Outside are left untouched by the reference (src/parsescene.cpp:531-541);
@@ -333,9 +320,9 @@ def load_scene_json(path, prep=None, overrides=None):
         lights.append(a)
         n_lights += len(p)
     prims = L.cat(prims, L.Primitive)
-    lights = L.cat(lights, L.Area)
+    lights = L.cat(lights, L.Area) if lights else np.zeros(0, L.Area)
     return assemble(os.path.basename(path), width, height, epsilon, integrator, max_depth, cam, materials, mediums,
-                    prims, lights, prep=prep, meta={"json": path}, densities=densities)
+                    prims, lights, infinite=infinite, infinite_texels=infinite_texels, prep=prep, meta={"json": path}, densities=densities)
 
 
 # ------------------------------------------------------------------------------------------------ configs

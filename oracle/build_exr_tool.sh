@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE — compiles oracle/refbuild/exr_tool.cpp against the reference's vendored EXR code where it lies
+# (REF/src/tinyexr.h); only the binary lands in oracle/_ref/ (git-ignored).  Needs /root/reference: this container only.
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+mkdir -p "$HERE/_ref"
+g++ -O2 -w -std=c++11 -I"$REF/src" "$HERE/refbuild/exr_tool.cpp" -o "$HERE/_ref/exr_tool"
+echo "built $HERE/_ref/exr_tool"

@@ -1,0 +1,192 @@
+"""SURVEY 8(f).4, the part that can be pinned in this image: EXR texels for the `Infinite` light (gpu-pathtracer_b200/exr.py
+against the EXR code the reference links — fixtures made by oracle/make_exr_fixtures.py from its vendored tinyexr), PLY
+import, assimp's Triangulate rule on the reference's shipped quad mesh, smooth-normal generation on analytic meshes, and
+a scene.json that uses all of it, rendered in emulation against the CPU oracle.  CPU only."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gpu_pathtracer_b200 as pt
+from gpu_pathtracer_b200 import _lib, exr, meshio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "exr")
+TOOL = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "exr_tool")
+GEOM = os.path.join(pt.scenes.data_dir(), "scenes", "cornell_box", "geometry")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _image():
+    rng = np.random.default_rng(20261017)
+    img = (rng.random((21, 37, 3)).astype(np.float32) * np.float32(30.0)) ** 2
+    img[0, 0] = (0.0, 1e-8, 65504.0); img[20, 36] = (1.0, 0.5, 0.25)
+    return img
+
+
+# ------------------------------------------------------------------------------------------------ EXR
+@pytest.mark.parametrize("comp", ["none", "rle", "zips", "zip"])
+@pytest.mark.parametrize("ptype", ["float", "half"])
+def test_exr_reader_equals_the_references_reader_on_files_of_the_references_writer(comp, ptype):
+    got = exr.load_exr(os.path.join(GOLD, f"ref_{comp}_{ptype}.exr"))
+    want = np.load(os.path.join(GOLD, f"ref_{comp}_{ptype}.npy"))
+    assert got.shape == want.shape == (21, 37, 4)
+    assert np.array_equal(_bits(got), _bits(want))
+    assert np.all(got[..., 3] == 1.0)                                   # no A channel in the file: alpha 1
+    if ptype == "float":
+        assert np.array_equal(_bits(got[..., :3]), _bits(_image()))      # and it is the image that was written
+
+
+@pytest.mark.parametrize("comp", ["none", "zips", "zip"])
+@pytest.mark.parametrize("half", [False, True])
+def test_exr_writer_is_read_by_the_references_reader(comp, half, tmp_path):
+    p = str(tmp_path / "x.exr")
+    exr.save_exr(p, _image(), {"none": exr.NONE, "zips": exr.ZIPS, "zip": exr.ZIP}[comp], half)
+    want = np.load(os.path.join(GOLD, f"mine_{comp}_{'half' if half else 'float'}.npy"))     # LoadEXR of the same bytes
+    assert np.array_equal(_bits(exr.load_exr(p)), _bits(want))
+    if os.path.exists(TOOL):                                            # live, where the reference tool is built
+        out = str(tmp_path / "x.bin")
+        subprocess.run([TOOL, "load", p, out], check=True)
+        live = np.frombuffer(open(out, "rb").read(), np.float32, offset=8).reshape(21, 37, 4)
+        assert np.array_equal(_bits(live), _bits(want))
+
+
+def test_exr_rejects_what_it_does_not_read(tmp_path):
+    with pytest.raises(exr.ExrError, match="PIZ"):
+        exr.load_exr(os.path.join(GOLD, "ref_piz_float.exr"))
+    p = tmp_path / "bad.exr"
+    p.write_bytes(b"not an exr file at all")
+    with pytest.raises(exr.ExrError):
+        exr.load_exr(str(p))
+
+
+# ------------------------------------------------------------------------------------------------ meshes
+def test_quads_of_the_shipped_mesh_are_fanned_from_corner_zero():
+    """density_render.obj (the medium boundary of the reference's scene.json) is six quads: assimp's Triangulate gives
+    (0,1,2), (0,2,3) for a convex quad — the primitives the pinned `shipped_smoke` fixture holds."""
+    tv, tn, tuv = meshio.load_obj(os.path.join(GEOM, "density_render.obj"))
+    assert tv.shape == (12, 3, 3)
+    quads = []
+    vs = []
+    for line in open(os.path.join(GEOM, "density_render.obj")):
+        t = line.split()
+        if t and t[0] == "v":
+            vs.append([float(x) for x in t[1:4]])
+        if t and t[0] == "f":
+            quads.append([int(c.split("/")[0]) - 1 for c in t[1:]])
+    vs = np.asarray(vs, np.float32)
+    for q, (a, b) in zip(quads, tv.reshape(6, 2, 3, 3)):
+        assert np.array_equal(a, vs[[q[0], q[1], q[2]]]) and np.array_equal(b, vs[[q[0], q[2], q[3]]])
+
+
+def test_triangulate_rules():
+    sq = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)]
+    assert meshio.triangulate([0, 1, 2, 3], sq) == [(0, 1, 2), (0, 2, 3)]
+    dart = [(0, 0, 0), (2, 0, 0), (0.5, 0.5, 0), (0, 2, 0)]                   # corner 2 is concave: the fan starts there
+    assert meshio.triangulate([0, 1, 2, 3], dart) == [(2, 3, 0), (2, 0, 1)]
+    penta = [(np.cos(a), np.sin(a), 0.0) for a in np.linspace(0, 2 * np.pi, 6)[:-1]]
+    assert meshio.triangulate(list(range(5)), penta) == [(0, 1, 2), (0, 2, 3), (0, 3, 4)]
+    concave5 = [(0, 0, 0), (2, 0, 0), (2, 2, 0), (1, 0.5, 0), (0, 2, 0)]
+    with pytest.raises(meshio.MeshError, match="concave"):
+        meshio.triangulate(list(range(5)), concave5)
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+@pytest.mark.parametrize("name", ["short.obj", "floor.obj", "light.obj", "density_render.obj"])
+def test_ply_loads_to_the_same_triangles_as_obj(name, fmt, tmp_path):
+    tv, tn, tuv = meshio.load_obj(os.path.join(GEOM, name))
+    p = str(tmp_path / "m.ply")
+    meshio.save_ply(p, tv, tn, tuv, fmt)
+    v2, n2, uv2 = meshio.load_mesh(p)
+    assert np.array_equal(_bits(v2), _bits(tv)) and np.array_equal(_bits(n2), _bits(tn)) and np.array_equal(_bits(uv2), _bits(tuv))
+
+
+def test_ply_with_shared_vertices_quads_and_extra_elements(tmp_path):
+    p = tmp_path / "q.ply"
+    p.write_text("ply\nformat ascii 1.0\ncomment a quad and a triangle over shared vertices\nelement vertex 5\n"
+                 "property float x\nproperty float y\nproperty float z\nproperty uchar red\n"
+                 "element face 2\nproperty list uchar int vertex_index\nelement edge 1\nproperty int a\nproperty int b\nend_header\n"
+                 "0 0 0 9\n1 0 0 9\n1 1 0 9\n0 1 0 9\n0.5 2 0 9\n4 0 1 2 3\n3 3 2 4\n0 1\n")
+    tv, tn, tuv = meshio.load_ply(str(p))
+    assert tv.shape == (3, 3, 3)
+    assert np.array_equal(tv[0], np.asarray([[0, 0, 0], [1, 0, 0], [1, 1, 0]], np.float32))
+    assert np.array_equal(tv[1], np.asarray([[0, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32))
+    assert np.allclose(tn, [0, 0, 1])                                        # generated: a flat patch
+
+
+def _uv_sphere(nu=48, nv=24):
+    tris = []
+    P = lambda i, j: (np.sin(np.pi * j / nv) * np.cos(2 * np.pi * i / nu), np.cos(np.pi * j / nv), np.sin(np.pi * j / nv) * np.sin(2 * np.pi * i / nu))
+    for j in range(nv):
+        for i in range(nu):
+            a, b, c, d = P(i, j), P(i + 1, j), P(i + 1, j + 1), P(i, j + 1)
+            if j > 0:
+                tris.append((a, c, b))
+            if j < nv - 1:
+                tris.append((a, d, c))
+    return np.asarray(tris, np.float32)
+
+
+def test_generated_normals_on_analytic_meshes():
+    tv = _uv_sphere()
+    for weighting in ("area", "uniform"):
+        tn = meshio.gen_smooth_normals(tv, weighting)
+        assert np.allclose(np.linalg.norm(tn, axis=-1), 1.0, atol=1e-5)
+        cosang = np.abs((tn * tv).sum(-1))                                    # unit sphere: the analytic normal is the position
+        assert cosang.min() > 0.995, cosang.min()
+    # a cube without normals: every corner's normal is the normalised sum of the face normals of the corners that meet there
+    # (area-weighted: one or two triangles per face touch a corner) — checked against a brute-force sum
+    cube = meshio.load_obj(os.path.join(GEOM, "short.obj"))[0]
+    tn = meshio.gen_smooth_normals(cube)
+    fn = np.cross(cube[:, 1].astype(np.float64) - cube[:, 0], cube[:, 2].astype(np.float64) - cube[:, 0])
+    for t in range(len(cube)):
+        for k in range(3):
+            same = np.all(np.abs(cube - cube[t, k]) < 1e-6, axis=-1)            # (n_tri, 3) corners at this position
+            s = (fn[:, None, :] * same[..., None]).sum((0, 1))
+            assert np.allclose(tn[t, k], s / np.linalg.norm(s), atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ a scene that uses all of it
+def test_scene_json_with_ply_meshes_and_an_exr_environment_renders_like_the_oracle(tmp_path, oracle):
+    geo = tmp_path / "geometry"
+    geo.mkdir()
+    for name, keep_normals in (("floor", True), ("short", False), ("tall", True)):
+        tv, tn, tuv = meshio.load_obj(os.path.join(GEOM, ("short" if name == "tall" else name) + ".obj"))
+        if name == "tall":
+            tv = tv * np.float32(0.5) + np.asarray([0.6, 0.0, 0.2], np.float32)
+        meshio.save_ply(str(geo / (name + ".ply")), tv, tn if keep_normals else None, None, "binary_little_endian")
+    sky = pt.scenes.sky_texels(32, 16)
+    exr.save_exr(str(tmp_path / "sky.exr"), sky, exr.ZIP, half=False)
+    doc = {"screen_width": 64, "screen_height": 32, "integrator": "pt", "maxDepth": 5,
+           "camera": {"position": [0, 1, 4.5], "lookat": [0, 0.8, 0], "up": [0, 1, 0], "fov": 40},
+           "material": [{"name": "grey", "bsdf": "lambertian", "diffuse": [0.6, 0.6, 0.6]},
+                        {"name": "metal", "bsdf": "roughconduct", "alpha": 0.2, "eta": [2.8, 2.1, 1.9], "k": [3.0, 2.0, 1.6]}],
+           "scene": [{"mesh": "geometry/floor.ply", "material": "grey"}, {"mesh": "geometry/short.ply", "material": "metal"},
+                     {"mesh": "geometry/tall.ply", "material": "grey", "rotate": [0, 20, 0]}],
+           "light": [{"infinite": "sky.exr", "rotate": [0, 30, 0]}]}
+    (tmp_path / "scene.json").write_text(json.dumps(doc))
+    s = pt.scenes.load_scene_json(str(tmp_path / "scene.json"))
+    assert s.infinite is not None and int(s.infinite["isvalid"][0]) == 1 and s.infinite_texels.shape == (16, 32, 3)
+    assert np.array_equal(_bits(s.infinite_texels), _bits(sky))
+    c, sn = np.float32(np.cos(np.float32(np.radians(np.float32(30.0))))), np.float32(np.sin(np.float32(np.radians(np.float32(30.0)))))
+    assert np.allclose(s.infinite["u"][0], [c, 0, -sn], atol=1e-6) and np.allclose(s.infinite["w"][0], [sn, 0, c], atol=1e-6)
+    assert len(s.prims) == 2 + 12 + 12 and len(s.lights) == 0
+    ref_acc, _ = oracle.render(s, 1, 2)
+    assert ref_acc.mean() > 1e-3
+    saved = _lib._lib
+    _lib.load(os.path.join(HERE, "emu", "libb200pt_emu.so"))
+    try:
+        with pt.PathTracer(s) as r:
+            r.render(1, reset=True, spp=2)
+            assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+    finally:
+        _lib._lib = saved
+    with pytest.raises(ValueError, match="rotate"):
+        doc["light"] = [{"infinite": "sky.exr"}]
+        (tmp_path / "scene2.json").write_text(json.dumps(doc))
+        pt.scenes.load_scene_json(str(tmp_path / "scene2.json"))
