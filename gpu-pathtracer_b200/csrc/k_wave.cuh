@@ -32,8 +32,9 @@ namespace pt {
 #endif
 constexpr int kWaveThreads = PT_WAVE_THREADS;     // slots (= threads) per CTA of the surface / homogeneous-medium wavefront
 #ifndef PT_WAVE_HET_THREADS
-#define PT_WAVE_HET_THREADS 256                   // heterogeneous media (128-thread CTAs measured slower: smoke 113 vs 146 Msamples/s)
-#endif
+#define PT_WAVE_HET_THREADS 320                   // heterogeneous media: 2 CTAs x 10 warps at 96 registers (~200 B of spills) against 2 x 8 at 123:
+#endif                                            // more slots per sort, more warps per SM — smoke 175 -> 203 Msamples/s, shipped scene 131 -> 137 at
+                                                  // 1024^2 (288: 205 / 130, 352: 197 / 129, 384: 177 / 128, 128: 113; profiles/r06_het_cta.txt)
 #ifndef PT_WAVE_ALLMATS_THREADS
 #define PT_WAVE_ALLMATS_THREADS 288               // all-BSDF instantiations: the larger sort domain of the material binning is worth more than
 #endif                                            // the registers (27 warps per SM, 72 registers): six-BSDF scene +10 % `pt`, +12 % `vpt`;
