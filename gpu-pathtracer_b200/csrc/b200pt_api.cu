@@ -582,6 +582,7 @@ template <class F> static void with_wave_kernel(const b200pt_ctx* c, F&& f) {
 static int wave_threads(const b200pt_ctx* c) {
     if (c->het) return WaveThreads<true>::value;
     const bool all_mats = !c->lambert_only && (c->mats_used & ~kMatsLDC) != 0u;       // the instantiation with_wave_kernel picks
+    if (c->lambert_only && !c->vol) return WaveThreads<false, kMatsLambertOnly, false>::value;
     return all_mats ? WaveThreads<false, kMatsAll>::value : WaveThreads<false>::value;
 }
 static size_t wave_smem(const b200pt_ctx* c) {

@@ -39,9 +39,17 @@ constexpr int kWaveThreads = PT_WAVE_THREADS;     // slots (= threads) per CTA o
 #define PT_WAVE_ALLMATS_THREADS 288               // all-BSDF instantiations: the larger sort domain of the material binning is worth more than
 #endif                                            // the registers (27 warps per SM, 72 registers): six-BSDF scene +10 % `pt`, +12 % `vpt`;
                                                   // C2 +0.5 %, C5 -5 % stay at 256 (profiles/r03b_t288.txt)
-template <bool HET, uint32_t MATS = 0u> struct WaveThreads {
-    static constexpr int value = HET ? PT_WAVE_HET_THREADS : (MATS == 0x3fu ? PT_WAVE_ALLMATS_THREADS : kWaveThreads);
+#ifndef PT_WAVE_LAMBERT_THREADS
+#define PT_WAVE_LAMBERT_THREADS 448               // lambertian `pt` (C1 / C2): 2 CTAs x 14 warps instead of 3 x 8 — what shared memory allows once the
+#endif                                            // sort arrays of the two-pass trace phase are gone: C2 1513 -> 1552 Msamples/s, C1 1773 -> 1846
+                                                  // (2 x 384: +1 %, 2 x 416: -2.5 %, 3 x 288: +0.5 %; profiles/r07_lambert_cta.txt)
+template <bool HET, uint32_t MATS = 0u, bool VOL = true> struct WaveThreads {
+    static constexpr int value = HET ? PT_WAVE_HET_THREADS
+                                     : (MATS == 0x3fu ? PT_WAVE_ALLMATS_THREADS : ((MATS == 1u && !VOL) ? PT_WAVE_LAMBERT_THREADS : kWaveThreads));
 };
+#ifndef PT_WAVE_LAMBERT_CTAS
+#define PT_WAVE_LAMBERT_CTAS 2      // resident CTAs per SM the lambertian `pt` instantiation is compiled for
+#endif
 #ifndef PT_WAVE_MATS_CTAS
 #define PT_WAVE_MATS_CTAS 3         // resident CTAs per SM the `vpt` / several-BSDF instantiations are compiled for: 80 registers and
                                     // ~100 B of spills against 96-99 at 2 — C5 662 -> 706 Msamples/s, six-BSDF scenes unchanged (profiles/r02s_ctas3.txt)
@@ -121,8 +129,8 @@ constexpr uint32_t kWaveShadeKeys = 36u;
 
 // HET: the slots run the heterogeneous-media coroutine (k_het.cuh) instead of the surface / homogeneous shade stage.
 template <bool VOL, uint32_t MATS, bool HET>
-__global__ void __launch_bounds__(WaveThreads<HET, MATS>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? PT_WAVE_MATS_CTAS : 3) * (kWaveThreads <= 128 ? 256 / kWaveThreads : 1)) k_wave_small(const WaveArgs a) {
-    constexpr int kT = WaveThreads<HET, MATS>::value;
+__global__ void __launch_bounds__(WaveThreads<HET, MATS, VOL>::value, HET ? PT_WAVE_HET_CTAS : ((VOL || MATS != kMatsLambertOnly) ? PT_WAVE_MATS_CTAS : PT_WAVE_LAMBERT_CTAS) * (kWaveThreads <= 128 ? 256 / kWaveThreads : 1)) k_wave_small(const WaveArgs a) {
+    constexpr int kT = WaveThreads<HET, MATS, VOL>::value;
     const ShadeArgs& sa = a.sa;
     const TraceArgs& ta = a.ta;
 #ifndef B200PT_EMULATE
