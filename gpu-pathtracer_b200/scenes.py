@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import exr, meshio
+from . import exr, meshio, textures as texio
 
 from . import layouts as L
 
@@ -207,7 +207,7 @@ def assemble(name, width, height, epsilon, integrator, max_depth, cam, materials
 
 def load_scene_json(path, prep=None, overrides=None):
     """The subset of LoadScene (src/parsescene.cpp:45) the hot path's configs use: homogeneous and heterogeneous media, constant
-    colour materials, OBJ / PLY meshes with TRS (polygons triangulated, missing normals generated: meshio.py), spheres, mesh
+    colour or image-textured (textures.py) materials, OBJ / PLY meshes with TRS (polygons triangulated, missing normals generated: meshio.py), spheres, mesh
     area lights, an .exr infinite light (exr.py).  Raises on anything else."""
     with open(path) as f:
         doc = json.load(f)
@@ -251,20 +251,32 @@ def load_scene_json(path, prep=None, overrides=None):
     max_depth = doc.get("maxDepth", 5)
 
     mat_names, mats = [], []
+    tex_files, tex_list = [], []                  # src/parsescene.cpp:299-310: one Texture per distinct file string, in order of first use
     for m in doc.get("material", []):
         if "bssrdf" in m:
             raise ValueError("bssrdf materials are unreachable on the device path")
+        tex_idx = -1
         if isinstance(m.get("diffuse"), str):
-            raise ValueError("textured materials are a 'next' row (SURVEY §8(f).2)")
-        if m.get("remap", False):
-            raise ValueError("roughness remap not supported by this front-end")
+            if m["diffuse"] not in tex_files:
+                tex_files.append(m["diffuse"])
+                tex_list.append(texio.load_texture(os.path.join(base, m["diffuse"])))
+            tex_idx = tex_files.index(m["diffuse"])
+            m = dict(m); m["diffuse"] = [1, 1, 1]          # the constant stays at its default next to a texture
         if "alpha" in m:
             au = av = m["alpha"]
         else:
             au, av = m.get("alphaU", 0.01), m.get("alphaV", 0.01)
+        if m.get("remap", False):                  # src/parsescene.cpp:281-291, float arithmetic left to right (logf of the host's libm)
+            def remap(r):
+                r = max(F(r), F(1e-3))
+                x = F(np.log(r))
+                return float(F(F(F(F(F(1.62142) + F(F(0.819955) * x)) + F(F(F(0.1734) * x) * x)) + F(F(F(F(0.0171201) * x) * x) * x)) +
+                               F(F(F(F(F(0.000640711) * x) * x) * x) * x)))
+            au, av = remap(au), remap(av)
         mats.append(make_material(m["bsdf"], m.get("diffuse", [1, 1, 1]), m.get("specular", [1, 1, 1]), au, av,
                                   m.get("insideIOR", 1.0), m.get("outsideIOR", 1.0), m.get("k", [0, 0, 0]),
                                   m.get("eta", [0, 0, 0])))
+        mats[-1]["textureIdx"] = tex_idx
         mat_names.append(m["name"])
     materials = L.cat(mats, L.Material)
 
@@ -322,7 +334,8 @@ def load_scene_json(path, prep=None, overrides=None):
     prims = L.cat(prims, L.Primitive)
     lights = L.cat(lights, L.Area) if lights else np.zeros(0, L.Area)
     return assemble(os.path.basename(path), width, height, epsilon, integrator, max_depth, cam, materials, mediums,
-                    prims, lights, infinite=infinite, infinite_texels=infinite_texels, prep=prep, meta={"json": path}, densities=densities)
+                    prims, lights, infinite=infinite, infinite_texels=infinite_texels, prep=prep, meta={"json": path}, densities=densities,
+                    textures=tex_list)
 
 
 # ------------------------------------------------------------------------------------------------ configs

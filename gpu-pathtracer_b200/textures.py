@@ -1,0 +1,51 @@
+"""Image textures for `Material.textureIdx`: what `Texture::Texture(file)` holds after `ImageIO::LoadTexture(file, w, h, true)`
+(src/texture.h:14-27, src/imageio.cpp:11-58) — the image flipped vertically, 8-bit channels scaled by 1.f / 255.f, r g b
+through powf(x, 2.2f) (sRGB to linear), and everything truncated back to uchar4 by (unsigned char)(v * 255).
+
+Decoding goes through Pillow (a library; this is scene loading, not the hot path).  PNG is lossless, so the texels equal the
+ones the reference's stb_image produces — pinned by tests/test_frontend_io.py against oracle/_ref/tex_tool, which runs the
+reference's vendored stb_image.h.  A JPEG is decoded by a different IDCT than stb's: texels may differ by a few steps of
+255 (measured on the reference's WoodFloor.jpg: see the test), which is stated, not hidden — `strict=True` rejects JPEG."""
+import numpy as np
+
+F = np.float32
+
+
+class TextureError(ValueError):
+    pass
+
+
+def texels_from_bytes(img):
+    """(h, w) or (h, w, 1 | 3 | 4) uint8, rows top to bottom as decoded -> (h, w, 4) uint8 texels as the reference stores them."""
+    img = np.asarray(img)
+    if img.dtype != np.uint8:
+        raise TextureError("8-bit images only (stb_image hands the reference 8-bit channels)")
+    if img.ndim == 2:
+        img = img[..., None]
+    h, w, c = img.shape
+    if c not in (1, 3, 4):
+        raise TextureError(f"{c} components: the reference's LoadTexture handles 1, 3 or 4")
+    img = img[::-1]                                                           # stbi_set_flip_vertically_on_load(true)
+    t = img.astype(F) * F(1.0 / 255.0)
+    rgba = np.ones((h, w, 4), F)
+    rgba[..., :3] = t[..., :1] if c == 1 else t[..., :3]
+    if c == 4:
+        rgba[..., 3] = t[..., 3]
+    rgba[..., :3] = np.power(rgba[..., :3], F(2.2), dtype=F)                   # powf(x, 2.2f)
+    return np.ascontiguousarray((rgba * F(255.0)).astype(np.uint8))          # (unsigned char)(v * 255): truncation
+
+
+def load_texture(path, strict=False):
+    from PIL import Image
+    im = Image.open(path)
+    if im.format == "JPEG" and strict:
+        raise TextureError(f"{path}: JPEG texels depend on the decoder's IDCT and are not pinned against the reference's")
+    if im.mode in ("P", "PA"):
+        im = im.convert("RGBA" if "transparency" in im.info or im.mode == "PA" else "RGB")
+    elif im.mode in ("I;16", "I;16B", "I", "F"):
+        raise TextureError(f"{path}: {im.mode} images are not read")
+    elif im.mode == "LA":
+        raise TextureError(f"{path}: two components (grey + alpha) — the reference leaves such texels uninitialised")
+    elif im.mode not in ("L", "RGB", "RGBA"):
+        im = im.convert("RGB")
+    return texels_from_bytes(np.asarray(im))

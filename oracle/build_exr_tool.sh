@@ -6,4 +6,6 @@ REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 mkdir -p "$HERE/_ref"
 g++ -O2 -w -std=c++11 -I"$REF/src" "$HERE/refbuild/exr_tool.cpp" -o "$HERE/_ref/exr_tool"
-echo "built $HERE/_ref/exr_tool"
+# ... and the image decoder it links (REF/include/stb/stb_image.h): texels as Texture::Texture would hold them
+g++ -O2 -w -std=c++11 -ffp-contract=off -I"$REF/include" "$HERE/refbuild/tex_tool.cpp" -o "$HERE/_ref/tex_tool"
+echo "built $HERE/_ref/exr_tool $HERE/_ref/tex_tool"

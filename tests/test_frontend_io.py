@@ -190,3 +190,71 @@ def test_scene_json_with_ply_meshes_and_an_exr_environment_renders_like_the_orac
         doc["light"] = [{"infinite": "sky.exr"}]
         (tmp_path / "scene2.json").write_text(json.dumps(doc))
         pt.scenes.load_scene_json(str(tmp_path / "scene2.json"))
+
+
+# ------------------------------------------------------------------------------------------------ image textures
+from gpu_pathtracer_b200 import textures as texio  # noqa: E402
+
+TEX = os.path.join(HERE, "golden", "tex")
+
+
+@pytest.mark.parametrize("name", ["rgb.png", "rgba.png", "grey.png", "palette.png", "uvgrid.png"])
+def test_png_texels_equal_the_references_decoder_path(name):
+    """PNG is lossless: the texels are the ones the reference's stb_image + LoadTexture(srgb) + Texture ctor produce
+    (fixtures: oracle/make_tex_fixtures.py through oracle/_ref/tex_tool)."""
+    want = np.load(os.path.join(TEX, "ref_texels.npz"))[name]
+    path = os.path.join(TEX, name) if name != "uvgrid.png" else os.path.join(pt.scenes.data_dir(), "scenes", "cornell_box", "textures", name)
+    got = texio.load_texture(path, strict=True)
+    assert got.dtype == np.uint8 and got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_jpeg_texels_are_close_and_flagged():
+    want = np.load(os.path.join(TEX, "ref_texels.npz"))["rgb.jpg"]
+    got = texio.load_texture(os.path.join(TEX, "rgb.jpg"))
+    assert got.shape == want.shape
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 8          # another IDCT than stb's: a few steps of 255, never pinned
+    with pytest.raises(texio.TextureError, match="JPEG"):
+        texio.load_texture(os.path.join(TEX, "rgb.jpg"), strict=True)
+
+
+def test_texture_conversion_rule():
+    img = np.asarray([[[0, 128, 255]], [[255, 0, 64]]], np.uint8)           # 2 rows, 1 column
+    t = texio.texels_from_bytes(img)
+    assert t.shape == (2, 1, 4) and np.array_equal(t[..., 3], [[255], [255]])
+    assert np.array_equal(t[0, 0, :3], [255, 0, int(np.float32(np.float32(64 * np.float32(1 / 255)) ** np.float32(2.2)) * np.float32(255))])   # flipped
+    assert t[1, 0, 1] == int(np.power(np.float32(128) * np.float32(1.0 / 255.0), np.float32(2.2), dtype=np.float32) * np.float32(255.0))
+    with pytest.raises(texio.TextureError):
+        texio.texels_from_bytes(np.zeros((2, 2, 2), np.uint8))
+
+
+def test_scene_json_with_an_image_texture_renders_like_the_oracle(tmp_path, oracle):
+    import shutil
+    src = os.path.join(pt.scenes.data_dir(), "scenes", "cornell_box")
+    shutil.copytree(os.path.join(src, "geometry"), tmp_path / "geometry")
+    (tmp_path / "textures").mkdir()
+    shutil.copy(os.path.join(src, "textures", "uvgrid.png"), tmp_path / "textures" / "uvgrid.png")
+    doc = json.load(open(os.path.join(src, "cornell_pt.json")))
+    doc["screen_width"], doc["screen_height"] = 64, 64
+    doc["material"].append({"name": "grid", "bsdf": "lambertian", "diffuse": "textures/uvgrid.png"})
+    doc["material"].append({"name": "grid2", "bsdf": "roughconduct", "alpha": 0.3, "remap": True, "diffuse": "textures/uvgrid.png",
+                            "eta": [2.8, 2.1, 1.9], "k": [3.0, 2.0, 1.6]})
+    for u in doc["scene"]:
+        if "floor" in u.get("mesh", ""):
+            u["material"] = "grid"
+        if "short" in u.get("mesh", ""):
+            u["material"] = "grid2"
+    (tmp_path / "scene.json").write_text(json.dumps(doc))
+    s = pt.scenes.load_scene_json(str(tmp_path / "scene.json"))
+    assert len(s.textures) == 1 and s.textures[0].shape == (512, 512, 4)        # one Texture per distinct file
+    idx = [int(m["textureIdx"]) for m in s.materials]
+    assert idx[-2:] == [0, 0] and all(i == -1 for i in idx[:-2])
+    ref_acc, _ = oracle.render(s, 1, 2)
+    saved = _lib._lib
+    _lib.load(os.path.join(HERE, "emu", "libb200pt_emu.so"))
+    try:
+        with pt.PathTracer(s) as r:
+            r.render(1, reset=True, spp=2)
+            assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
+    finally:
+        _lib._lib = saved
