@@ -297,8 +297,14 @@ def load_scene_json(path, prep=None, overrides=None):
             prims.append(triangles_to_prims(tv, tn, tuv, midx, mi, mo))
         elif "sphere" in u:
             prims.append(sphere_prim(u.get("center", [0, 0, 0]), u.get("radius", 1.0), midx, mi, mo))
+        elif "line" in u:                               # src/parsescene.cpp:393-424: end points through t * r * s, radii as given
+            trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
+            ends = np.asarray([u.get("p0", [0, 0, 0]), u.get("p1", [1, 1, 1])], F)
+            if not np.array_equal(trs, np.eye(4, dtype=F)):
+                ends = (ends @ trs[:3, :3].T + trs[:3, 3]).astype(F)
+            prims.append(line_prims(ends[:1], ends[1:], [u.get("width0", 0.025)], [u.get("width1", 0.025)], mat_idx(u.get("material", "matte"))))
         else:
-            raise ValueError("line primitives are a 'next' row (SURVEY §8(f).2)")
+            raise ValueError("scene unit is neither a mesh, a sphere nor a line")
     lights = []
     n_lights = 0
     infinite = infinite_texels = None
@@ -557,6 +563,30 @@ def cornell_textured_hair(width=256, height=256, max_depth=6, n_hair=400, seed=1
     return assemble("cornell_textured_hair", width, height, base.epsilon, "pt", max_depth, cam, mats, base.mediums,
                     L.cat([prims, hair], L.Primitive), base.lights, prep=prep,
                     textures=[checker_texture(64, 32, 7), checker_texture(16, 48, 8)])
+
+
+def load_line_fragment(path):
+    """The reference's scenes/cornell_box/fur.json: not a scene but a comma-separated run of {"line": true, p0, p1, width0,
+    width1, material} units meant to be pasted into a scene's "scene" array.  Returns (p0, p1, width0, width1) arrays."""
+    import gzip
+    raw = (gzip.open(path, "rt") if path.endswith(".gz") else open(path)).read().strip()
+    units = json.loads("[" + raw.rstrip(",") + "]")
+    p0 = np.asarray([u["p0"] for u in units], F); p1 = np.asarray([u["p1"] for u in units], F)
+    return p0, p1, np.asarray([u["width0"] for u in units], F), np.asarray([u["width1"] for u in units], F)
+
+
+def cornell_fur(width=512, height=512, max_depth=6, n_hair=None, prep=None):
+    """SURVEY 8(f).2's named asset: the Cornell box with the reference's shipped fur.json — 10 000 `Line` segments (src/line.h)
+    fanning out of one point — under `pt`.  10 036 primitives: the tree kernel with hair at scale."""
+    base = cornell_pt(width, height, max_depth, prep=prep)
+    mats = np.concatenate([base.materials, make_material("lambertian", diffuse=(0.45, 0.3, 0.15))])
+    p0, p1, w0, w1 = load_line_fragment(os.path.join(data_dir(), "scenes", "cornell_box", "fur.json.gz"))
+    if n_hair is not None:
+        p0, p1, w0, w1 = p0[:n_hair], p1[:n_hair], w0[:n_hair], w1[:n_hair]
+    hair = line_prims(p0, p1, w0, w1, len(base.materials))
+    cam = {"position": [0, 1.0, 6.8], "lookat": [0, 1.0, 0], "up": [0, 1, 0], "fov": 19.5}
+    return assemble("cornell_fur", width, height, base.epsilon, "pt", max_depth, cam, mats, base.mediums,
+                    L.cat([base.prims.copy(), hair], L.Primitive), base.lights, prep=prep)
 
 
 def smoke_grid(nx=20, ny=24, nz=12, seed=3):

@@ -90,6 +90,8 @@ def main():
         # several area lights (emitter-box list of the MIS-ray pruning), alone and next to an environment light
         "room_6_lights_64x48": lambda: pt.scenes.room_with_lights(6, 64, 48, 6, prep=prep),
         "room_4_lights_sky_64x48": lambda: pt.scenes.room_with_lights(4, 64, 48, 6, sky=True, prep=prep),
+        # the reference's shipped fur.json (10 000 Line segments) in the Cornell box
+        "cornell_fur_64": lambda: pt.scenes.cornell_fur(64, 64, 6, prep=prep),
     }
     only = [a for a in sys.argv[1:] if not a.startswith("-")]          # optional: regenerate just these fixtures
     for name, mk in scenes.items():
@@ -98,7 +100,7 @@ def main():
         s = mk()
         out = {"camera": s.camera.view(np.uint8), "nodes": s.nodes.view(np.uint8), "prims_order_hash": prim_hash(s.prims),
                "light_distribution": s.light_distribution, "root_box": s.root_box}
-        if name != "random_tris_20k_64":
+        if name not in ("random_tris_20k_64", "cornell_fur_64"):
             out["prims"] = s.prims.view(np.uint8)
         spp = 4
         acc, tone = ref.render(s, 1, spp)

@@ -32,6 +32,8 @@ def make(name, size):
         return pt.scenes.cornell_material_zoo(size, size, 8, "pt")
     if name == "zoovpt":
         return pt.scenes.cornell_material_zoo(size, size, 12, "vpt")
+    if name == "fur":                                 # the reference's shipped fur.json: 10 000 Line segments in the Cornell box
+        return pt.scenes.cornell_fur(size, size, 6)
     if name == "hair":                                # textures + Line primitives
         return pt.scenes.cornell_textured_hair(size, size, 6)
     if name.startswith("tris"):

@@ -258,3 +258,25 @@ def test_scene_json_with_an_image_texture_renders_like_the_oracle(tmp_path, orac
             assert np.array_equal(_bits(r.accum()), _bits(ref_acc))
     finally:
         _lib._lib = saved
+
+
+def test_line_units_and_the_shipped_fur_fragment(tmp_path):
+    """`"line": true` scene units (src/parsescene.cpp:393-424) and the reference's fur.json fragment."""
+    p0, p1, w0, w1 = pt.scenes.load_line_fragment(os.path.join(pt.scenes.data_dir(), "scenes", "cornell_box", "fur.json.gz"))
+    assert p0.shape == p1.shape == (10000, 3) and np.all(p0 == np.float32([0, 1, -1])) and np.all(w0 == np.float32(0.001))
+    assert np.array_equal(p1[0], np.float32([0.426392, 1.072053, -0.749006]))
+    src = os.path.join(pt.scenes.data_dir(), "scenes", "cornell_box")
+    import shutil
+    shutil.copytree(os.path.join(src, "geometry"), tmp_path / "geometry")
+    doc = json.load(open(os.path.join(src, "cornell_pt.json")))
+    doc["screen_width"], doc["screen_height"] = 64, 64
+    doc["material"].append({"name": "fur", "bsdf": "lambertian", "diffuse": [0.4, 0.3, 0.2]})
+    doc["scene"].append({"line": True, "p0": [0, 1, -1], "p1": [0.4, 1.1, -0.7], "width0": 0.002, "width1": 0.001, "material": "fur"})
+    doc["scene"].append({"line": True, "p0": [0, 0, 0], "p1": [1, 0, 0], "material": "fur", "translate": [0, 1, 0], "scale": [0.5, 1, 1]})
+    (tmp_path / "scene.json").write_text(json.dumps(doc))
+    s = pt.scenes.load_scene_json(str(tmp_path / "scene.json"))
+    lines = s.prims[s.prims["type"] == pt.layouts.GT_LINES].view(pt.layouts.PrimitiveLine)["line"]
+    assert len(lines) == 2
+    ends = sorted((tuple(np.round(l["p0"], 6)), tuple(np.round(l["p1"], 6)), float(l["width0"]), float(l["width1"])) for l in lines)
+    assert ends[0] == ((0.0, 1.0, -1.0), (0.4, 1.1, -0.7), np.float32(0.002), np.float32(0.001))
+    assert ends[1] == ((0.0, 1.0, 0.0), (0.5, 1.0, 0.0), np.float32(0.025), np.float32(0.025))

@@ -27,6 +27,7 @@ SCENES = {
     "environment_camera_128x64": lambda: pt.scenes.cornell_environment_camera(128, 64, 6),
     "room_6_lights_64x48": lambda: pt.scenes.room_with_lights(6, 64, 48, 6),               # several emitters (MIS-ray pruning)
     "room_4_lights_sky_64x48": lambda: pt.scenes.room_with_lights(4, 64, 48, 6, sky=True),  # area + environment light
+    "cornell_fur_64": lambda: pt.scenes.cornell_fur(64, 64, 6),                            # the reference's fur.json: 10 000 Line segments
 }
 
 

@@ -37,6 +37,7 @@ SCENES = {
     "environment_camera": lambda: pt.scenes.cornell_environment_camera(128, 64, 6),  # lat-long camera
     "room_6_lights": lambda: pt.scenes.room_with_lights(6, 64, 48, 6),               # several emitters
     "room_4_lights_sky": lambda: pt.scenes.room_with_lights(4, 64, 48, 6, sky=True), # area lights + environment light
+    "cornell_fur": lambda: pt.scenes.cornell_fur(64, 64, 6),                         # the reference's fur.json: 10 000 Line segments
 }
 
 
