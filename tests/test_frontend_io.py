@@ -2,8 +2,10 @@
 against the EXR code the reference links — fixtures made by oracle/make_exr_fixtures.py from its vendored tinyexr), PLY
 import, assimp's Triangulate rule on the reference's shipped quad mesh, smooth-normal generation on analytic meshes, and
 a scene.json that uses all of it, rendered in emulation against the CPU oracle.  CPU only."""
+import hashlib
 import json
 import os
+import struct
 import subprocess
 
 import numpy as np
@@ -30,9 +32,9 @@ def _image():
 
 
 # ------------------------------------------------------------------------------------------------ EXR
-@pytest.mark.parametrize("comp", ["none", "rle", "zips", "zip"])
-@pytest.mark.parametrize("ptype", ["float", "half"])
+@pytest.mark.parametrize("comp,ptype", [(c, t) for c in ["none", "rle", "zips", "zip"] for t in ["float", "half"]] + [("piz", "float")])
 def test_exr_reader_equals_the_references_reader_on_files_of_the_references_writer(comp, ptype):
+    # (piz_float: the random test image does not compress, tinyexr stores it raw inside the PIZ chunk — src/tinyexr.h:9374)
     got = exr.load_exr(os.path.join(GOLD, f"ref_{comp}_{ptype}.exr"))
     want = np.load(os.path.join(GOLD, f"ref_{comp}_{ptype}.npy"))
     assert got.shape == want.shape == (21, 37, 4)
@@ -56,9 +58,79 @@ def test_exr_writer_is_read_by_the_references_reader(comp, half, tmp_path):
         assert np.array_equal(_bits(live), _bits(want))
 
 
+with open(os.path.join(GOLD, "piz_expected.json")) as _f:
+    PIZ_EXPECTED = json.load(_f)
+
+
+@pytest.mark.parametrize("case", sorted(PIZ_EXPECTED))
+def test_exr_piz_reader_equals_the_references_reader(case, tmp_path, monkeypatch):
+    """PIZ files written by the reference's vendored tinyexr (SaveEXRImageToFile, src/tinyexr.h:9250) from compressible
+    images: load_exr returns the bits tinyexr's LoadEXR / DecompressPiz (src/tinyexr.h:9370-9485) returns — as recorded
+    by oracle/make_exr_fixtures.py, and live where the reference tool is built."""
+    seen = {"w14": 0, "w16": 0, "maxlen": 0, "run": 0}
+    wavelet, huffman = exr._wavelet_decode, exr._huf_decode
+
+    def spy_wavelet(plane, max_value):
+        seen["w14" if max_value < (1 << 14) else "w16"] += 1
+        return wavelet(plane, max_value)
+
+    def spy_huffman(buf, pos, n_bits, lengths, run_symbol, expect):
+        seen["maxlen"] = max(seen["maxlen"], int(lengths.max()))
+        seen["run"] += int(lengths[run_symbol] > 0)
+        return huffman(buf, pos, n_bits, lengths, run_symbol, expect)
+
+    monkeypatch.setattr(exr, "_wavelet_decode", spy_wavelet)
+    monkeypatch.setattr(exr, "_huf_decode", spy_huffman)
+    p = os.path.join(GOLD, f"piz_{case}.exr")
+    got = exr.load_exr(p)
+    want = PIZ_EXPECTED[case]
+    assert got.shape == (want["height"], want["width"], 4) and got.dtype == np.float32
+    assert hashlib.sha256(got.tobytes()).hexdigest() == want["sha256"]
+    assert seen["w14"] + seen["w16"] > 0                                # the chunk really went through the PIZ stages
+    if case == "wavy_float_224x34":
+        assert seen["w16"] > 0 and seen["maxlen"] > 14                  # 16-bit wavelet mode, codes past the fast table
+    if case == "const_half_33x40":
+        assert seen["run"] > 0                                          # run codes
+    if os.path.exists(TOOL):
+        out = str(tmp_path / "x.bin")
+        subprocess.run([TOOL, "load", p, out], check=True)
+        b = open(out, "rb").read()
+        assert struct.unpack("<ii", b[:8]) == (want["width"], want["height"])
+        assert b[8:] == got.tobytes()
+
+
+def test_exr_piz_corruption_is_an_error_not_garbage(tmp_path):
+    src = open(os.path.join(GOLD, "piz_blocks_half_50x70.exr"), "rb").read()
+    good = exr.load_exr(os.path.join(GOLD, "piz_blocks_half_50x70.exr"))
+    hits = 0
+    for cut in (len(src) - 7, len(src) - 200, len(src) // 2):           # truncated in the last / an inner chunk
+        p = tmp_path / f"cut{cut}.exr"
+        p.write_bytes(src[:cut])
+        with pytest.raises((exr.ExrError, struct.error, ValueError, IndexError)):
+            exr.load_exr(str(p))
+    rng = np.random.default_rng(5)
+    for k in range(40):                                                 # a flipped byte is either caught or decodes to a same-sized image
+        b = bytearray(src)
+        at = int(rng.integers(len(src) - 3000, len(src)))
+        b[at] ^= 0x5a
+        p = tmp_path / f"flip{k}.exr"
+        p.write_bytes(bytes(b))
+        try:
+            img = exr.load_exr(str(p))
+            assert img.shape == good.shape
+        except (exr.ExrError, struct.error, ValueError, IndexError, OverflowError):
+            hits += 1
+    assert hits > 0
+
+
 def test_exr_rejects_what_it_does_not_read(tmp_path):
-    with pytest.raises(exr.ExrError, match="PIZ"):
-        exr.load_exr(os.path.join(GOLD, "ref_piz_float.exr"))
+    src = bytearray(open(os.path.join(GOLD, "ref_zip_float.exr"), "rb").read())
+    at = src.index(b"compression\0compression\0") + len(b"compression\0compression\0") + 4
+    src[at] = 5                                                         # PXR24
+    p = tmp_path / "pxr24.exr"
+    p.write_bytes(bytes(src))
+    with pytest.raises(exr.ExrError, match="compression type 5"):
+        exr.load_exr(str(p))
     p = tmp_path / "bad.exr"
     p.write_bytes(b"not an exr file at all")
     with pytest.raises(exr.ExrError):
