@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import exr, meshio, textures as texio
+from . import exr, meshio, textures as texio, xform
 
 from . import layouts as L
 
@@ -60,33 +60,25 @@ def load_mesh(path):
 
 
 def _trs(scale, translate, rotate_deg):
-    """glm: trs = t * r * s with r = Rx * Ry * Rz (src/parsescene.cpp:349-355), float32."""
-    def rot(axis, deg):
-        a = F(np.radians(F(deg)))
-        c, s = F(np.cos(a)), F(np.sin(a))
-        m = np.eye(4, dtype=F)
-        i, j = [(1, 2), (2, 0), (0, 1)][axis]
-        m[i, i] = c; m[j, j] = c; m[i, j] = -s; m[j, i] = s
-        return m
-    S = np.diag(np.asarray(list(scale) + [1], F))
-    T = np.eye(4, dtype=F); T[:3, 3] = np.asarray(translate, F)
-    R = (rot(0, rotate_deg[0]) @ rot(1, rotate_deg[1]) @ rot(2, rotate_deg[2])).astype(F)
-    return (T @ R @ S).astype(F)
+    """trs = t * r * s with r = Rx * Ry * Rz (src/parsescene.cpp:349-355) in GLM's own float32 operation order (xform.py,
+    pinned bit for bit against the GLM the reference vendors).  Returned in row-major [row, col] form."""
+    return np.ascontiguousarray(xform.trs(scale, translate, rotate_deg).T)
 
 
 def _transform_mesh(tri_v, tri_n, trs):
-    """Mesh::processMesh (src/mesh.cpp:50-62): v' = trs*(v,1); n' = normalize(inverse-transpose * (n,0))."""
+    """Mesh::processMesh (src/mesh.cpp:50-62): v' = vec3(trs * (v, 1)); n' = normalize(vec3(transpose(inverse(trs)) * (n, 0))),
+    every product and sum in GLM's order (xform.transform_points_normals).  With the identity that arithmetic returns its
+    input (the normal: normalised), except that a component -0.0 comes out as +0.0 ((-0 * 1 + 0) + (0 + 0)); the identity
+    is passed through here without those products, so the scene arrays of the pinned fixtures (made before the GLM order
+    was restated) keep their bits — no comparison in the integrators tells the two zeros apart."""
+    tri_v = np.asarray(tri_v, F); tri_n = np.asarray(tri_n, F)
     if np.array_equal(trs, np.eye(4, dtype=F)):
-        v = tri_v.copy()
-        nn = tri_n
-    else:
-        v = (tri_v @ trs[:3, :3].T + trs[:3, 3]).astype(F)
-        invT = np.linalg.inv(trs.astype(np.float64)).T.astype(F)
-        nn = (tri_n @ invT[:3, :3].T).astype(F)
-    # glm::normalize = v * (1 / sqrt(dot(v, v))) in float32, dot = (x*x + y*y) + z*z
-    d = (nn[..., 0] * nn[..., 0] + nn[..., 1] * nn[..., 1]).astype(F) + (nn[..., 2] * nn[..., 2]).astype(F)
-    inv = (F(1.0) / np.sqrt(d.astype(F))).astype(F)
-    return v, (nn * inv[..., None]).astype(F)
+        # glm::normalize = v * (1 / sqrt(dot(v, v))) in float32, dot = (x*x + y*y) + z*z
+        with np.errstate(invalid="ignore", divide="ignore"):
+            d = (tri_n[..., 0] * tri_n[..., 0] + tri_n[..., 1] * tri_n[..., 1]).astype(F) + (tri_n[..., 2] * tri_n[..., 2]).astype(F)
+            inv = (F(1.0) / np.sqrt(d.astype(F))).astype(F)
+        return tri_v.copy(), (tri_n * inv[..., None]).astype(F)
+    return xform.transform_points_normals(np.ascontiguousarray(np.asarray(trs, F).T), tri_v, tri_n)
 
 
 def triangles_to_prims(tri_v, tri_n, tri_uv, mat_idx, medium_inside=-1, medium_outside=-1, light_base=None):
@@ -300,8 +292,9 @@ def load_scene_json(path, prep=None, overrides=None):
         elif "line" in u:                               # src/parsescene.cpp:393-424: end points through t * r * s, radii as given
             trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
             ends = np.asarray([u.get("p0", [0, 0, 0]), u.get("p1", [1, 1, 1])], F)
-            if not np.array_equal(trs, np.eye(4, dtype=F)):
-                ends = (ends @ trs[:3, :3].T + trs[:3, 3]).astype(F)
+            if not np.array_equal(trs, np.eye(4, dtype=F)):                       # vec3(trs * vec4(p, 1)), GLM's order
+                ex, ey, ez, _ = xform.mul_vec4(np.ascontiguousarray(trs.T), ends[:, 0], ends[:, 1], ends[:, 2], F(1.0))
+                ends = np.stack([ex, ey, ez], -1).astype(F)
             prims.append(line_prims(ends[:1], ends[1:], [u.get("width0", 0.025)], [u.get("width1", 0.025)], mat_idx(u.get("material", "matte"))))
         else:
             raise ValueError("scene unit is neither a mesh, a sphere nor a line")
@@ -311,16 +304,23 @@ def load_scene_json(path, prep=None, overrides=None):
     for u in doc.get("light", []):
         if "infinite" in u:
             # src/parsescene.cpp:544-580: texels through ImageIO::LoadExr (RGB of tinyexr's RGBA, rows in file order), frame
-            # u / v / w = the columns of Rx * Ry * Rz ("rotate", degrees).  The reference leaves the frame UNINITIALISED when
-            # neither "rotate" nor "matrix" is given, and "matrix" goes through glm::inverse — both are rejected here.
-            if "matrix" in u or "rotate" not in u:
-                raise ValueError("infinite light: give \"rotate\" (the reference leaves the frame uninitialised without it; \"matrix\" is not reproduced)")
+            # u / v / w = the columns of Rx * Ry * Rz ("rotate", degrees) or of glm::inverse("matrix") — "matrix" wins when
+            # both are given (it is applied second).  With neither the reference leaves the frame UNINITIALISED: rejected.
+            if "matrix" not in u and "rotate" not in u:
+                raise ValueError("infinite light: give \"rotate\" or \"matrix\" (the reference leaves the frame uninitialised without them)")
             infinite_texels = np.ascontiguousarray(exr.load_exr(os.path.join(base, u["infinite"]))[..., :3], F)
-            R = _trs([1, 1, 1], [0, 0, 0], u["rotate"])
+            if "matrix" in u:
+                if len(u["matrix"]) != 16:
+                    raise ValueError("infinite light: \"matrix\" takes 16 numbers (column by column)")
+                fu, fv, fw = xform.frame_from_matrix(u["matrix"])
+                if not np.all(np.isfinite([fu, fv, fw])):
+                    raise ValueError("infinite light: \"matrix\" is singular")
+            else:
+                fu, fv, fw = xform.frame_from_rotate(u["rotate"])
             infinite = np.zeros(1, L.Infinite)
             infinite["data"] = infinite_texels.ctypes.data
             infinite["width"] = infinite_texels.shape[1]; infinite["height"] = infinite_texels.shape[0]
-            infinite["u"] = R[:3, 0]; infinite["v"] = R[:3, 1]; infinite["w"] = R[:3, 2]; infinite["isvalid"] = 1
+            infinite["u"] = fu; infinite["v"] = fv; infinite["w"] = fw; infinite["isvalid"] = 1
             continue
         if "mesh" not in u:
             raise ValueError("only mesh area lights and .exr infinite lights exist (src/parsescene.cpp:583)")

@@ -352,3 +352,84 @@ def test_line_units_and_the_shipped_fur_fragment(tmp_path):
     ends = sorted((tuple(np.round(l["p0"], 6)), tuple(np.round(l["p1"], 6)), float(l["width0"]), float(l["width1"])) for l in lines)
     assert ends[0] == ((0.0, 1.0, -1.0), (0.4, 1.1, -0.7), np.float32(0.002), np.float32(0.001))
     assert ends[1] == ((0.0, 1.0, 0.0), (0.5, 1.0, 0.0), np.float32(0.025), np.float32(0.025))
+
+
+# ------------------------------------------------------------------------------------------------ transforms (GLM order)
+GLM = os.path.join(HERE, "golden", "glm")
+GLM_TOOL = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "glm_tool")
+
+
+def test_trs_and_vertex_transform_equal_the_references_glm_bit_for_bit():
+    """scale / translate / rotate -> trs = t * r * s (src/parsescene.cpp:349-355), transpose(inverse(trs)), and the moved
+    vertex / normal of Mesh::processMesh (src/mesh.cpp:50-62): 400 cases computed by the GLM the reference vendors
+    (oracle/refbuild/glm_tool.cpp, fixtures by oracle/make_glm_fixtures.py)."""
+    from gpu_pathtracer_b200 import xform
+    d = np.load(os.path.join(GLM, "trs.npz"))
+    inp = d["inputs"]
+    for i, r in enumerate(inp):
+        m = xform.trs(r[0:3], r[3:6], r[6:9])
+        assert np.array_equal(_bits(m.ravel()), _bits(d["trs"][i])), i
+        assert np.array_equal(_bits(xform.transpose(xform.inverse(m)).ravel()), _bits(d["inv_t"][i])), i
+        v, n = xform.transform_points_normals(m, r[None, 9:12], r[None, 12:15])
+        assert np.array_equal(_bits(v[0]), _bits(d["v"][i])) and np.array_equal(_bits(n[0]), _bits(d["n"][i])), i
+        # the loader's entry points (row-major trs, arrays of triangles) give the same bits — except for the identity,
+        # which is passed through (signed zeros kept, scenes._transform_mesh)
+        t = pt.scenes._trs(r[0:3], r[3:6], r[6:9])
+        tv, tn = pt.scenes._transform_mesh(np.tile(r[9:12], (2, 3, 1)), np.tile(r[12:15], (2, 3, 1)), t)
+        if not np.array_equal(t, np.eye(4, dtype=np.float32)):
+            assert np.array_equal(_bits(tv[1, 2]), _bits(d["v"][i])) and np.array_equal(_bits(tn[1, 2]), _bits(d["n"][i])), i
+
+
+def test_infinite_light_frames_equal_the_references_glm_bit_for_bit():
+    """"rotate" (three glm::rotate calls) and "matrix" (glm::inverse) frames of an infinite light, src/parsescene.cpp:551-568"""
+    from gpu_pathtracer_b200 import xform
+    f = np.load(os.path.join(GLM, "frames.npz"))
+    for r, want in zip(f["rotate"], f["rotate_frames"]):
+        assert np.array_equal(_bits(np.concatenate(xform.frame_from_rotate(r))), _bits(want))
+    for m, want in zip(f["matrix"], f["matrix_frames"]):
+        assert np.array_equal(_bits(np.concatenate(xform.frame_from_matrix(m))), _bits(want))
+
+
+@pytest.mark.skipif(not os.path.exists(GLM_TOOL), reason="the reference's GLM is only compiled in the build container")
+def test_transforms_live_against_the_references_glm():
+    from gpu_pathtracer_b200 import xform
+    rng = np.random.default_rng(99)
+    rows = np.concatenate([np.exp(rng.uniform(-2, 2, (64, 3))), rng.uniform(-9, 9, (64, 3)), rng.uniform(-720, 720, (64, 3)),
+                           rng.uniform(-5, 5, (64, 3)), rng.normal(size=(64, 3))], 1).astype(np.float32)
+    text = "".join("T " + " ".join(f"{w:08x}" for w in r.view(np.uint32)) + "\n" for r in rows)
+    out = subprocess.run([GLM_TOOL], input=text, capture_output=True, text=True, check=True).stdout.splitlines()
+    for r, line in zip(rows, out):
+        want = np.array([int(w, 16) for w in line.split()], np.uint32)
+        m = xform.trs(r[0:3], r[3:6], r[6:9])
+        v, n = xform.transform_points_normals(m, r[None, 9:12], r[None, 12:15])
+        got = np.concatenate([m.ravel(), xform.transpose(xform.inverse(m)).ravel(), v[0], n[0]])
+        assert np.array_equal(_bits(got), want)
+
+
+def test_scene_json_takes_a_matrix_frame_for_the_infinite_light(tmp_path):
+    """"matrix" overrides "rotate" (it is applied second, src/parsescene.cpp:563-568); a singular matrix is refused."""
+    from gpu_pathtracer_b200 import xform
+    img = np.ones((4, 8, 3), np.float32)
+    exr.save_exr(str(tmp_path / "sky.exr"), img)
+    geom = os.path.join(GEOM, "floor.obj")
+    a = np.radians(40.0)
+    mat = [float(x) for x in np.array([[np.cos(a), 0, -np.sin(a), 0], [0, 1, 0, 0], [np.sin(a), 0, np.cos(a), 0], [0.5, 0, 0, 1]], np.float32).ravel()]
+    doc = {"screen_width": 32, "screen_height": 32, "integrator": "pt", "maxDepth": 2,
+           "camera": {"position": [0, 1, 5], "lookat": [0, 1, 0], "up": [0, 1, 0], "fov": 40},
+           "material": [{"name": "m", "bsdf": "lambertian", "diffuse": [0.5, 0.5, 0.5]}],
+           "scene": [{"mesh": geom, "material": "m"}],
+           "light": [{"infinite": "sky.exr", "rotate": [10, 20, 30], "matrix": mat}]}
+    p = tmp_path / "scene.json"
+    p.write_text(json.dumps(doc))
+    sc = pt.scenes.load_scene_json(str(p))
+    fu, fv, fw = xform.frame_from_matrix(mat)
+    inf = sc.infinite[0]
+    assert np.array_equal(_bits(inf["u"]), _bits(fu)) and np.array_equal(_bits(inf["v"]), _bits(fv)) and np.array_equal(_bits(inf["w"]), _bits(fw))
+    doc["light"][0]["matrix"] = [0.0] * 16
+    p.write_text(json.dumps(doc))
+    with pytest.raises(ValueError, match="singular"):
+        pt.scenes.load_scene_json(str(p))
+    del doc["light"][0]["matrix"], doc["light"][0]["rotate"]
+    p.write_text(json.dumps(doc))
+    with pytest.raises(ValueError, match="uninitialised"):
+        pt.scenes.load_scene_json(str(p))
