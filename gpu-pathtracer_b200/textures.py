@@ -2,10 +2,12 @@
 (src/texture.h:14-27, src/imageio.cpp:11-58) — the image flipped vertically, 8-bit channels scaled by 1.f / 255.f, r g b
 through powf(x, 2.2f) (sRGB to linear), and everything truncated back to uchar4 by (unsigned char)(v * 255).
 
-Decoding goes through Pillow (a library; this is scene loading, not the hot path).  PNG is lossless, so the texels equal the
-ones the reference's stb_image produces — pinned by tests/test_frontend_io.py against oracle/_ref/tex_tool, which runs the
-reference's vendored stb_image.h.  A JPEG is decoded by a different IDCT than stb's: texels may differ by a few steps of
-255 (measured on the reference's WoodFloor.jpg: see the test), which is stated, not hidden — `strict=True` rejects JPEG."""
+PNG decoding goes through Pillow (a library; this is scene loading, not the hot path).  PNG is lossless, so the texels equal
+the ones the reference's stb_image produces — pinned by tests/test_frontend_io.py against oracle/_ref/tex_tool, which runs the
+reference's vendored stb_image.h.  A JPEG's pixels depend on the decoder (IDCT rounding, chroma interpolation, colour
+transform): baseline JPEGs are decoded by jpeg.py, which restates stb's arithmetic and is pinned bit for bit against it
+(Pillow's libjpeg differs from stb on 5.7 % of the texels of the reference's WoodFloor.jpg, by up to 4 / 255).  Kinds jpeg.py
+does not read (progressive, CMYK, ...) go through Pillow, flagged as unpinned: `strict=True` rejects them."""
 import numpy as np
 
 F = np.float32
@@ -37,9 +39,18 @@ def texels_from_bytes(img):
 
 def load_texture(path, strict=False):
     from PIL import Image
+    from . import jpeg
+    with open(path, "rb") as f:
+        head = f.read(2)
+    if head == b"\xff\xd8":
+        try:
+            return texels_from_bytes(jpeg.load(path))                          # stb_image's arithmetic, pinned
+        except jpeg.JpegUnsupported as e:
+            if strict:
+                raise TextureError(f"{path}: {e} — its texels would come from another decoder than the reference's and are not pinned")
+        except jpeg.JpegError as e:
+            raise TextureError(f"{path}: {e}")
     im = Image.open(path)
-    if im.format == "JPEG" and strict:
-        raise TextureError(f"{path}: JPEG texels depend on the decoder's IDCT and are not pinned against the reference's")
     if im.mode in ("P", "PA"):
         im = im.convert("RGBA" if "transparency" in im.info or im.mode == "PA" else "RGB")
     elif im.mode in ("I;16", "I;16B", "I", "F"):

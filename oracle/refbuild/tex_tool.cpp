@@ -3,6 +3,7 @@
 // ImageIO::LoadTexture(file, w, h, srgb = true) + Texture::Texture (src/imageio.cpp:11-58, src/texture.h:14-27) restated:
 // vertical flip on load, x / 255 as x * (1.f / 255.f), powf(x, 2.2f) on r g b, (unsigned char)(v * 255) — under g++ / glibc.
 //   tex_tool in.png out.bin      out.bin = int32 width, int32 height, int32 components, uchar4[width*height]
+//   tex_tool in.jpg out.bin raw  out.bin = int32 width, int32 height, int32 components, the bytes stbi_load returned (flipped)
 #define STB_IMAGE_IMPLEMENTATION
 #include "stb/stb_image.h"
 #include <cmath>
@@ -15,6 +16,12 @@ int main(int argc, char** argv) {
     stbi_set_flip_vertically_on_load(true);
     unsigned char* tex = stbi_load(argv[1], &w, &h, &comp, 0);
     if (!tex) { fprintf(stderr, "stbi_load failed\n"); return 2; }
+    if (argc >= 4 && argv[3][0] == 'r') {
+        FILE* f = fopen(argv[2], "wb");
+        fwrite(&w, 4, 1, f); fwrite(&h, 4, 1, f); fwrite(&comp, 4, 1, f); fwrite(tex, 1, (size_t)w * h * comp, f);
+        fclose(f);
+        return 0;
+    }
     std::vector<unsigned char> out((size_t)4 * w * h);
     const float inv = 1.f / 255.f;
     for (int i = 0; i < w * h; ++i) {

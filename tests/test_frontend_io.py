@@ -281,13 +281,58 @@ def test_png_texels_equal_the_references_decoder_path(name):
     assert np.array_equal(got, want)
 
 
-def test_jpeg_texels_are_close_and_flagged():
+JPEG_PIXELS = np.load(os.path.join(TEX, "ref_jpeg_pixels.npz"))
+REF_WOODFLOOR = "/root/reference/scenes/cornell_box/textures/WoodFloor.jpg"
+
+
+@pytest.mark.parametrize("case", sorted(k for k in JPEG_PIXELS.files if not k.startswith("WoodFloor")))
+def test_jpeg_decoder_equals_the_references_stb_image_bit_for_bit(case, tmp_path):
+    """Baseline JPEGs — Pillow-written 4:4:4 / 4:2:2 / 4:2:0 (odd sizes, 1 x 1, optimised tables, restart markers, quality 20..100,
+    grey) and hand-written flat-block files with the sampling factors Pillow cannot write (1x2, 4x1, 1x4, 3x3, mixed, luma
+    sub-sampled): jpeg.load returns the bytes stbi_load returns (oracle/_ref/tex_tool raw mode, recorded by
+    oracle/make_tex_fixtures.py; re-run live where the tool is built)."""
+    from gpu_pathtracer_b200 import jpeg
+    p = os.path.join(TEX, case + ".jpg")
+    got = jpeg.load(p)
+    want = JPEG_PIXELS[case]
+    assert got.dtype == np.uint8 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    tool = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tex_tool")
+    if os.path.exists(tool):
+        out = str(tmp_path / "x.bin")
+        subprocess.run([tool, p, out, "raw"], check=True)
+        b = open(out, "rb").read()
+        w, h, c = struct.unpack("<iii", b[:12])
+        live = np.frombuffer(b, np.uint8, offset=12).reshape(h, w, c)[::-1]
+        assert np.array_equal(got.reshape(h, w, c), live)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_WOODFLOOR), reason="the reference tree is only in the build container")
+def test_the_references_shipped_jpeg_decodes_to_stb_images_pixels():
+    import hashlib
+    from gpu_pathtracer_b200 import jpeg
+    got = jpeg.load(REF_WOODFLOOR)
+    assert list(got.shape) == list(JPEG_PIXELS["WoodFloor_shape"])
+    assert hashlib.sha256(got.tobytes()).digest() == JPEG_PIXELS["WoodFloor_sha256"].tobytes()
+
+
+def test_jpeg_texels_are_pinned_and_other_kinds_flagged(tmp_path):
     want = np.load(os.path.join(TEX, "ref_texels.npz"))["rgb.jpg"]
-    got = texio.load_texture(os.path.join(TEX, "rgb.jpg"))
-    assert got.shape == want.shape
-    assert np.abs(got.astype(int) - want.astype(int)).max() <= 8          # another IDCT than stb's: a few steps of 255, never pinned
-    with pytest.raises(texio.TextureError, match="JPEG"):
-        texio.load_texture(os.path.join(TEX, "rgb.jpg"), strict=True)
+    for strict in (False, True):
+        got = texio.load_texture(os.path.join(TEX, "rgb.jpg"), strict=strict)
+        assert np.array_equal(got, want)                                   # stb's arithmetic: the reference's texels, bit for bit
+    from PIL import Image
+    img = np.asarray(Image.open(os.path.join(TEX, "rgb.png")))
+    p = str(tmp_path / "prog.jpg")
+    Image.fromarray(img, "RGB").save(p, quality=90, progressive=True)
+    loose = texio.load_texture(p)                                          # another decoder (Pillow): loads, but is not pinned ...
+    assert loose.shape == want.shape
+    with pytest.raises(texio.TextureError, match="progressive"):
+        texio.load_texture(p, strict=True)                                 # ... so strict refuses it
+    bad = tmp_path / "cut.jpg"
+    bad.write_bytes(open(os.path.join(TEX, "rgb.jpg"), "rb").read()[:400])
+    with pytest.raises(texio.TextureError):
+        texio.load_texture(str(bad))
 
 
 def test_texture_conversion_rule():
