@@ -1,12 +1,13 @@
-"""Baseline JPEG -> the 8-bit pixels the reference's decoder produces.
+"""Baseline and progressive JPEG -> the 8-bit pixels the reference's decoder produces.
 
 `ImageIO::LoadTexture` (src/imageio.cpp:11-58) decodes through the stb_image v2.19 the reference vendors.  A JPEG's pixels
 depend on the decoder: the inverse DCT's fixed-point constants and rounding, how sub-sampled chroma is interpolated, and the
 YCbCr -> RGB arithmetic all differ between libjpeg (Pillow) and stb — on the reference's shipped WoodFloor.jpg 5.7 % of the
 texels come out different.  This module restates stb's choices, whole-image at a time with numpy instead of block by block:
 
-  * entropy decoding as the standard prescribes (stb's only deviation: ANY run/size byte with size 0 other than 0xF0 ends the
-    block), coefficients de-quantised and truncated to int16;
+  * entropy decoding as the standard prescribes (stb's only deviation: ANY run/size byte with size 0 other than 0xF0 ends a
+    baseline block), coefficients de-quantised and truncated to int16; progressive files: DC / AC first and refinement scans
+    with end-of-band runs, a DC first scan clears its block, de-quantisation after the last scan;
   * the 8 x 8 inverse DCT in 32-bit integers: constants round(x * 4096), first pass keeps 2 extra bits ((x + 512) >> 10), second
     pass removes 17 with the +128 level shift folded in ((x + 65536 + (128 << 17)) >> 17), clamped to 0..255 — both passes over
     all blocks of a component at once;
@@ -16,9 +17,10 @@ texels come out different.  This module restates stb's choices, whole-image at a
     anything else -> replication;
   * YCbCr -> RGB in 20-bit fixed point with constants int(x * 4096 + 0.5) << 8, the Cb term of green masked to its upper 16 bits.
 
-Not read (the caller falls back to Pillow unless strict): progressive and arithmetic-coded files, 12-bit samples, CMYK / YCCK,
+Not read (the caller falls back to Pillow unless strict): arithmetic-coded and lossless files, 12-bit samples, CMYK / YCCK,
 files whose three components are stored as RGB.  Pinned bit for bit against the reference's vendored stb_image
-(oracle/_ref/tex_tool) on its shipped JPEG and on synthetic files of every sub-sampling mode — tests/test_frontend_io.py."""
+(oracle/_ref/tex_tool) on its shipped JPEG and on synthetic files of every sub-sampling mode, baseline and progressive —
+tests/test_frontend_io.py."""
 import struct
 
 import numpy as np
@@ -196,7 +198,7 @@ def _segments(buf, pos):
 
 
 def decode(buf):
-    """bytes of a baseline JPEG file -> uint8 (height, width) for one component or (height, width, 3) RGB, rows top to bottom"""
+    """bytes of a baseline or progressive JPEG file -> uint8 (height, width) for one component or (height, width, 3) RGB, rows top to bottom"""
     try:
         return _decode(buf)
     except (IndexError, struct.error, KeyError) as e:
@@ -256,7 +258,7 @@ def _decode(buf):
             jfif = True
         elif m == 0xEE and body[:6] == b"Adobe\0" and len(body) >= 12:
             adobe_transform = body[11]
-        elif m in (0xC0, 0xC1):
+        elif m in (0xC0, 0xC1, 0xC2):
             if frame is not None:
                 raise JpegError("two frame headers")
             prec, h, w, nc = struct.unpack_from(">BHHB", body, 0)
@@ -278,9 +280,10 @@ def _decode(buf):
                 c["x"] = (w * c["h"] + hmax - 1) // hmax; c["y"] = (h * c["v"] + vmax - 1) // vmax
                 c["bw"] = mcux * c["h"]; c["bh"] = mcuy * c["v"]
                 c["coef"] = np.zeros((c["bh"], c["bw"], 64), np.int64)
-            frame = {"w": w, "h": h, "comps": comps, "hmax": hmax, "vmax": vmax, "mcux": mcux, "mcuy": mcuy}
-        elif m == 0xC2:
-            raise JpegUnsupported("progressive JPEG is left to the fallback decoder")
+            frame = {"w": w, "h": h, "comps": comps, "hmax": hmax, "vmax": vmax, "mcux": mcux, "mcuy": mcuy, "progressive": m == 0xC2}
+            if m == 0xC2:                                           # coefficients are built up over several scans: plain lists
+                for c in comps:
+                    c["blocks"] = [[[0] * 64 for _ in range(c["bw"])] for _ in range(c["bh"])]
         elif 0xC3 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
             raise JpegUnsupported("lossless / arithmetic-coded JPEG")
         elif m == 0xDA:
@@ -293,13 +296,22 @@ def _decode(buf):
                 c = next((c for c in frame["comps"] if c["id"] == cid), None)
                 if c is None:
                     raise JpegError("scan names an unknown component")
+                if frame["progressive"]:
+                    sel.append((c, huff.get((0, tt >> 4)), huff.get((1, tt & 15)), None))
+                    continue
                 if (0, tt >> 4) not in huff or (1, tt & 15) not in huff or c["tq"] not in quant:
                     raise JpegError("scan uses a table that was not defined")
                 sel.append((c, huff[(0, tt >> 4)], huff[(1, tt & 15)], quant[c["tq"]]))
+            ss, se, a = body[1 + 2 * ns], body[2 + 2 * ns], body[3 + 2 * ns]
             segs, pos = _segments(buf, pos + L)
             for c in frame["comps"]:
                 c["pred"] = 0
-            _decode_scan(frame, sel, segs, restart)
+            if frame["progressive"]:
+                if ss > 63 or se > 63 or ss > se or (a >> 4) > 13 or (a & 15) > 13:
+                    raise JpegError("bad SOS")
+                _decode_scan_progressive(frame, sel, segs, restart, ss, se, a >> 4, a & 15)
+            else:
+                _decode_scan(frame, sel, segs, restart)
             continue
         pos += L
     if frame is None:
@@ -307,6 +319,12 @@ def _decode(buf):
     comps = frame["comps"]
     planes = []
     for c in comps:
+        if frame["progressive"]:                                    # de-quantise at the end, product kept in 16 bits like stb
+            if c["tq"] not in quant:
+                raise JpegError("no quantisation table")
+            qnat = np.zeros(64, np.int64)
+            qnat[_ZIGZAG] = quant[c["tq"]]
+            c["coef"] = (np.array(c["blocks"], np.int64).astype(np.int16).astype(np.int64) * qnat)
         px = _idct(c["coef"].astype(np.int16).reshape(-1, 8, 8))    # (short) truncation of coefficient * quantiser
         planes.append(px.reshape(c["bh"], c["bw"], 8, 8).transpose(0, 2, 1, 3).reshape(c["bh"] * 8, c["bw"] * 8))
     w, h = frame["w"], frame["h"]
@@ -319,14 +337,162 @@ def _decode(buf):
     return _ycbcr_to_rgb(*full)
 
 
+def _units(frame, sel):
+    """the order in which a scan visits blocks: one component -> its own blocks in raster order (no MCU padding), several ->
+    MCU by MCU, h x v blocks of each component in turn; every entry = (selection, (block row, block column))"""
+    if len(sel) == 1:
+        c = sel[0][0]
+        return [[(sel[0], (by, bx))] for by in range((c["y"] + 7) >> 3) for bx in range((c["x"] + 7) >> 3)]
+    return [[(e, (my * e[0]["v"] + v, mx * e[0]["h"] + hh)) for e in sel for v in range(e[0]["v"]) for hh in range(e[0]["h"])]
+            for my in range(frame["mcuy"]) for mx in range(frame["mcux"])]
+
+
+def _decode_scan_progressive(frame, sel, segs, restart, ss, se, ah, al):
+    """one scan of a progressive file: DC first / DC refinement (any number of components), or AC first / AC refinement over
+    the band ss..se of ONE component with end-of-band runs; successive approximation by the bit position `al`"""
+    comps = frame["comps"]
+    if ss == 0 and se != 0:
+        raise JpegError("a scan cannot merge DC and AC")
+    if ss != 0 and len(sel) != 1:
+        raise JpegError("an AC scan takes one component")
+    units = _units(frame, sel)
+    per = restart if restart else len(units)
+    si = 0
+    bits = None
+    eob_run = 0
+    bit = 1 << al
+    for u, unit in enumerate(units):
+        if u % per == 0:
+            if si >= len(segs):
+                raise JpegError("entropy-coded data ends early")
+            bits = _Bits(segs[si]); si += 1
+            eob_run = 0
+            for c in comps:
+                c["pred"] = 0
+        win = bits.win
+        pos = bits.pos
+        for (c, hdc, hac, _q), (by, bx) in unit:
+            data = c["blocks"][by][bx]
+            if ss == 0:
+                if ah == 0:                                         # DC, first pass (also clears the block, as stb does)
+                    if hdc is None:
+                        raise JpegError("scan uses a table that was not defined")
+                    w = (win[pos >> 3] << (pos & 7)) & 0xFFFFFFFFFFFFFFFF
+                    idx = w >> 48
+                    l = hdc.length[idx]
+                    if l == 0:
+                        raise JpegError("bad huffman code")
+                    t = hdc.value[idx]
+                    pos += l
+                    diff = 0
+                    if t:
+                        diff = ((w << l) & 0xFFFFFFFFFFFFFFFF) >> (64 - t)
+                        if diff < (1 << (t - 1)):
+                            diff += (-1 << t) + 1
+                        pos += t
+                    c["pred"] += diff
+                    data[:] = [0] * 64
+                    data[0] = c["pred"] << al
+                else:                                               # DC refinement: one bit
+                    if (win[pos >> 3] >> (63 - (pos & 7))) & 1:
+                        data[0] += bit
+                    pos += 1
+                continue
+            if hac is None:
+                raise JpegError("scan uses a table that was not defined")
+            alen, aval = hac.length, hac.value
+            if ah == 0:                                             # AC band, first pass
+                if eob_run:
+                    eob_run -= 1
+                    continue
+                k = ss
+                while k <= se:
+                    w = (win[pos >> 3] << (pos & 7)) & 0xFFFFFFFFFFFFFFFF
+                    idx = w >> 48
+                    l = alen[idx]
+                    if l == 0:
+                        raise JpegError("bad huffman code")
+                    rs = aval[idx]
+                    pos += l
+                    s = rs & 15
+                    r = rs >> 4
+                    if s == 0:
+                        if r < 15:
+                            eob_run = 1 << r
+                            if r:
+                                eob_run += ((w << l) & 0xFFFFFFFFFFFFFFFF) >> (64 - r)
+                                pos += r
+                            eob_run -= 1
+                            break
+                        k += 16
+                        continue
+                    k += r
+                    if k > 63:
+                        raise JpegError("coefficient index past the block")
+                    v = ((w << l) & 0xFFFFFFFFFFFFFFFF) >> (64 - s)
+                    if v < (1 << (s - 1)):
+                        v += (-1 << s) + 1
+                    pos += s
+                    data[_ZZ[k]] = v << al
+                    k += 1
+                continue
+            # AC band, refinement
+            if eob_run:
+                eob_run -= 1
+                for k in range(ss, se + 1):
+                    z = _ZZ[k]
+                    p = data[z]
+                    if p != 0:
+                        if (win[pos >> 3] >> (63 - (pos & 7))) & 1:
+                            if (p & bit) == 0:
+                                data[z] = p + bit if p > 0 else p - bit
+                        pos += 1
+                continue
+            k = ss
+            while k <= se:
+                w = (win[pos >> 3] << (pos & 7)) & 0xFFFFFFFFFFFFFFFF
+                idx = w >> 48
+                l = alen[idx]
+                if l == 0:
+                    raise JpegError("bad huffman code")
+                rs = aval[idx]
+                pos += l
+                s = rs & 15
+                r = rs >> 4
+                if s == 0:
+                    if r < 15:
+                        eob_run = (1 << r) - 1
+                        if r:
+                            eob_run += ((w << l) & 0xFFFFFFFFFFFFFFFF) >> (64 - r)
+                            pos += r
+                        r = 64                                      # to the end of the band
+                else:
+                    if s != 1:
+                        raise JpegError("bad huffman code")
+                    s = bit if (win[pos >> 3] >> (63 - (pos & 7))) & 1 else -bit
+                    pos += 1
+                while k <= se:
+                    z = _ZZ[k]
+                    k += 1
+                    p = data[z]
+                    if p != 0:
+                        if (win[pos >> 3] >> (63 - (pos & 7))) & 1:
+                            if (p & bit) == 0:
+                                data[z] = p + bit if p > 0 else p - bit
+                        pos += 1
+                    else:
+                        if r == 0:
+                            data[z] = s
+                            break
+                        r -= 1
+        if pos > bits.limit:
+            raise JpegError("entropy-coded data ends early")
+        bits.pos = pos
+
+
 def _decode_scan(frame, sel, segs, restart):
     comps = frame["comps"]
-    if len(sel) == 1:                                               # one component: its own blocks in raster order, no MCU padding
-        c = sel[0][0]
-        units = [[sel[0] + ((by, bx),)] for by in range((c["y"] + 7) >> 3) for bx in range((c["x"] + 7) >> 3)]
-    else:
-        units = [[e + ((my * e[0]["v"] + v, mx * e[0]["h"] + hh),) for e in sel for v in range(e[0]["v"]) for hh in range(e[0]["h"])]
-                 for my in range(frame["mcuy"]) for mx in range(frame["mcux"])]
+    units = _units(frame, sel)
     per = restart if restart else len(units)
     si = 0
     bits = None
@@ -337,7 +503,7 @@ def _decode_scan(frame, sel, segs, restart):
             bits = _Bits(segs[si]); si += 1
             for c in comps:
                 c["pred"] = 0
-        for c, hdc, hac, q, (by, bx) in unit:
+        for (c, hdc, hac, q), (by, bx) in unit:
             c["coef"][by, bx], c["pred"] = _decode_block(bits, hdc, hac, q, c["pred"])
 
 

@@ -5,9 +5,9 @@ through powf(x, 2.2f) (sRGB to linear), and everything truncated back to uchar4 
 PNG decoding goes through Pillow (a library; this is scene loading, not the hot path).  PNG is lossless, so the texels equal
 the ones the reference's stb_image produces — pinned by tests/test_frontend_io.py against oracle/_ref/tex_tool, which runs the
 reference's vendored stb_image.h.  A JPEG's pixels depend on the decoder (IDCT rounding, chroma interpolation, colour
-transform): baseline JPEGs are decoded by jpeg.py, which restates stb's arithmetic and is pinned bit for bit against it
+transform): baseline and progressive JPEGs are decoded by jpeg.py, which restates stb's arithmetic and is pinned bit for bit against it
 (Pillow's libjpeg differs from stb on 5.7 % of the texels of the reference's WoodFloor.jpg, by up to 4 / 255).  Kinds jpeg.py
-does not read (progressive, CMYK, ...) go through Pillow, flagged as unpinned: `strict=True` rejects them."""
+does not read (CMYK, arithmetic-coded, ...) go through Pillow, flagged as unpinned: `strict=True` rejects them."""
 import numpy as np
 
 F = np.float32

@@ -34,7 +34,7 @@ def ref_raw(path):
 
 
 def jpeg_cases():
-    """baseline JPEGs of every kind gpu-pathtracer_b200/jpeg.py reads: name -> (image, Pillow save options)"""
+    """baseline and progressive JPEGs of every kind gpu-pathtracer_b200/jpeg.py reads: name -> (image, Pillow save options)"""
     rng = np.random.default_rng(20261018)
 
     def picture(w, h):
@@ -56,6 +56,11 @@ def jpeg_cases():
         "j420_50x35_rst": (picture(50, 35), dict(quality=80, subsampling=2, restart_marker_blocks=2)),
         "grey_29x13": (picture(29, 13)[..., 1], dict(quality=88)),
         "j444_40x24_q100": (picture(40, 24), dict(quality=100, subsampling=0)),
+        "p420_50x35": (picture(50, 35), dict(quality=80, subsampling=2, progressive=True)),            # progressive: 10 scans each
+        "p444_37x21_q95": (picture(37, 21), dict(quality=95, subsampling=0, progressive=True)),
+        "p422_64x64_q30_opt": (picture(64, 64), dict(quality=30, subsampling=1, progressive=True, optimize=True)),
+        "p420_70x50_rst": (picture(70, 50), dict(quality=75, subsampling=2, progressive=True, restart_marker_blocks=3)),
+        "pgrey_29x13": (picture(29, 13)[..., 0], dict(quality=85, progressive=True)),
     }
 
 

@@ -287,8 +287,8 @@ REF_WOODFLOOR = "/root/reference/scenes/cornell_box/textures/WoodFloor.jpg"
 
 @pytest.mark.parametrize("case", sorted(k for k in JPEG_PIXELS.files if not k.startswith("WoodFloor")))
 def test_jpeg_decoder_equals_the_references_stb_image_bit_for_bit(case, tmp_path):
-    """Baseline JPEGs — Pillow-written 4:4:4 / 4:2:2 / 4:2:0 (odd sizes, 1 x 1, optimised tables, restart markers, quality 20..100,
-    grey) and hand-written flat-block files with the sampling factors Pillow cannot write (1x2, 4x1, 1x4, 3x3, mixed, luma
+    """Pillow-written baseline and progressive JPEGs, 4:4:4 / 4:2:2 / 4:2:0 (odd sizes, 1 x 1, optimised tables, restart markers,
+    quality 20..100, grey) and hand-written flat-block files with the sampling factors Pillow cannot write (1x2, 4x1, 1x4, 3x3, mixed, luma
     sub-sampled): jpeg.load returns the bytes stbi_load returns (oracle/_ref/tex_tool raw mode, recorded by
     oracle/make_tex_fixtures.py; re-run live where the tool is built)."""
     from gpu_pathtracer_b200 import jpeg
@@ -323,11 +323,11 @@ def test_jpeg_texels_are_pinned_and_other_kinds_flagged(tmp_path):
         assert np.array_equal(got, want)                                   # stb's arithmetic: the reference's texels, bit for bit
     from PIL import Image
     img = np.asarray(Image.open(os.path.join(TEX, "rgb.png")))
-    p = str(tmp_path / "prog.jpg")
-    Image.fromarray(img, "RGB").save(p, quality=90, progressive=True)
+    p = str(tmp_path / "cmyk.jpg")
+    Image.fromarray(img, "RGB").convert("CMYK").save(p, quality=90)
     loose = texio.load_texture(p)                                          # another decoder (Pillow): loads, but is not pinned ...
     assert loose.shape == want.shape
-    with pytest.raises(texio.TextureError, match="progressive"):
+    with pytest.raises(texio.TextureError, match="CMYK"):
         texio.load_texture(p, strict=True)                                 # ... so strict refuses it
     bad = tmp_path / "cut.jpg"
     bad.write_bytes(open(os.path.join(TEX, "rgb.jpg"), "rb").read()[:400])
