@@ -53,7 +53,9 @@ def load_texture(path, strict=False):
     im = Image.open(path)
     if im.mode in ("P", "PA"):
         im = im.convert("RGBA" if "transparency" in im.info or im.mode == "PA" else "RGB")
-    elif im.mode in ("I;16", "I;16B", "I", "F"):
+    elif im.mode in ("I;16", "I;16B"):                                        # 16-bit grey: stb keeps the upper byte (stbi__convert_16_to_8)
+        return texels_from_bytes((np.asarray(im).astype(np.uint16) >> 8).astype(np.uint8))
+    elif im.mode in ("I", "F"):
         raise TextureError(f"{path}: {im.mode} images are not read")
     elif im.mode == "LA":
         raise TextureError(f"{path}: two components (grey + alpha) — the reference leaves such texels uninitialised")

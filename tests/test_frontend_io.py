@@ -335,6 +335,24 @@ def test_jpeg_texels_are_pinned_and_other_kinds_flagged(tmp_path):
         texio.load_texture(str(bad))
 
 
+def test_sixteen_bit_png_keeps_the_upper_byte_like_stb(tmp_path):
+    """stbi_load hands the reference 8-bit channels: a 16-bit PNG is reduced by `>> 8` (checked against oracle/_ref/tex_tool
+    for grey and RGB when this was written; live below where the tool is built)."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    g16 = rng.integers(0, 65536, (9, 14)).astype(np.uint16)
+    p = str(tmp_path / "g16.png")
+    Image.fromarray(g16).save(p)
+    got = texio.load_texture(p, strict=True)
+    assert np.array_equal(got, texio.texels_from_bytes((g16 >> 8).astype(np.uint8)))
+    tool = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tex_tool")
+    if os.path.exists(tool):
+        out = str(tmp_path / "x.bin")
+        subprocess.run([tool, p, out], check=True)
+        live = np.frombuffer(open(out, "rb").read(), np.uint8, offset=12).reshape(9, 14, 4)
+        assert np.array_equal(got, live)
+
+
 def test_texture_conversion_rule():
     img = np.asarray([[[0, 128, 255]], [[255, 0, 64]]], np.uint8)           # 2 rows, 1 column
     t = texio.texels_from_bytes(img)
