@@ -37,14 +37,15 @@ def texels_from_bytes(img):
     return np.ascontiguousarray((rgba * F(255.0)).astype(np.uint8))          # (unsigned char)(v * 255): truncation
 
 
-def load_texture(path, strict=False):
+def decode_image(path, strict=False):
+    """the 8-bit pixels stbi_load hands the reference: uint8 (h, w) or (h, w, 1 | 3 | 4), rows top to bottom"""
     from PIL import Image
     from . import jpeg
     with open(path, "rb") as f:
         head = f.read(2)
     if head == b"\xff\xd8":
         try:
-            return texels_from_bytes(jpeg.load(path))                          # stb_image's arithmetic, pinned
+            return jpeg.load(path)                                             # stb_image's arithmetic, pinned
         except jpeg.JpegUnsupported as e:
             if strict:
                 raise TextureError(f"{path}: {e} — its texels would come from another decoder than the reference's and are not pinned")
@@ -54,11 +55,15 @@ def load_texture(path, strict=False):
     if im.mode in ("P", "PA"):
         im = im.convert("RGBA" if "transparency" in im.info or im.mode == "PA" else "RGB")
     elif im.mode in ("I;16", "I;16B"):                                        # 16-bit grey: stb keeps the upper byte (stbi__convert_16_to_8)
-        return texels_from_bytes((np.asarray(im).astype(np.uint16) >> 8).astype(np.uint8))
+        return (np.asarray(im).astype(np.uint16) >> 8).astype(np.uint8)
     elif im.mode in ("I", "F"):
         raise TextureError(f"{path}: {im.mode} images are not read")
     elif im.mode == "LA":
         raise TextureError(f"{path}: two components (grey + alpha) — the reference leaves such texels uninitialised")
     elif im.mode not in ("L", "RGB", "RGBA"):
         im = im.convert("RGB")
-    return texels_from_bytes(np.asarray(im))
+    return np.asarray(im)
+
+
+def load_texture(path, strict=False):
+    return texels_from_bytes(decode_image(path, strict))

@@ -122,6 +122,46 @@ FLAT_CASES = {                                   # name: (width, height, (h, v) 
 }
 
 
+IMAGEIO_TOOL = os.path.join(ROOT, "oracle", "_ref", "imageio_tool")
+
+
+def imageio_image():
+    rng = np.random.default_rng(11)
+    img = rng.normal(0.5, 0.6, (19, 33, 3)).astype(np.float32)
+    img[0, 0] = (np.nan, np.inf, -np.inf); img[1, 1] = (1.0, 0.0, 0.999999); img[2, 2] = (1 / 255, 254.999 / 255, 0.5)
+    return img
+
+
+def imageio_fixtures():
+    """What the reference's OWN src/imageio.cpp + src/texture.h do (oracle/_ref/imageio_tool, oracle/build_imageio_tool.sh):
+    tests/golden/tex/ref_imageio.npz = the pixels of the PNG ImageIO::SavePng writes for imageio_image(); the file
+    ImageIO::SaveExr writes for |image| and what ImageIO::LoadExr returns for it; Texture::Texture texels of every fixture image."""
+    img = imageio_image()
+    h, w, _ = img.shape
+    tmp = os.path.join(OUT, "_io")
+    img.tofile(tmp + ".bin")
+    subprocess.run([IMAGEIO_TOOL, "savepng", tmp + ".bin", str(w), str(h), tmp + ".png"], check=True)
+    png = np.asarray(Image.open(tmp + ".png")).copy()
+    pos = np.abs(img); pos[~np.isfinite(pos)] = 3.0
+    pos.tofile(tmp + ".bin")
+    subprocess.run([IMAGEIO_TOOL, "saveexr", tmp + ".bin", str(w), str(h), os.path.join(OUT, "ref_saveexr.exr")], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([IMAGEIO_TOOL, "loadexr", os.path.join(OUT, "ref_saveexr.exr"), tmp + ".out"], check=True)
+    b = open(tmp + ".out", "rb").read()
+    loaded = np.frombuffer(b, np.float32, offset=8).reshape(h, w, 3).copy()
+    out = {"savepng_pixels": png, "loadexr_of_saveexr": loaded}
+    import glob
+    for p in sorted(glob.glob(os.path.join(OUT, "*.png")) + glob.glob(os.path.join(OUT, "*.jpg"))):
+        if os.path.basename(p).startswith("_"):
+            continue
+        subprocess.run([IMAGEIO_TOOL, "texture", p, tmp + ".out"], check=True)
+        b = open(tmp + ".out", "rb").read()
+        tw, th = struct.unpack("<ii", b[:8])
+        out["texture:" + os.path.basename(p)] = np.frombuffer(b, np.uint8, offset=8).reshape(th, tw, 4).copy()
+    for e in (".bin", ".png", ".out"):
+        os.remove(tmp + e)
+    np.savez_compressed(os.path.join(OUT, "ref_imageio.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     rng = np.random.default_rng(7)
@@ -153,6 +193,7 @@ def main():
     raw["WoodFloor_sha256"] = np.frombuffer(hashlib.sha256(wf.tobytes()).digest(), np.uint8)
     raw["WoodFloor_shape"] = np.array(wf.shape)
     np.savez_compressed(os.path.join(OUT, "ref_jpeg_pixels.npz"), **raw)
+    imageio_fixtures()
     print({k: v.shape for k, v in out.items()})
 
 

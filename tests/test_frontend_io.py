@@ -353,6 +353,66 @@ def test_sixteen_bit_png_keeps_the_upper_byte_like_stb(tmp_path):
         assert np.array_equal(got, live)
 
 
+# ------------------------------------------------------------------------------------------------ ImageIO, the reference's own
+REF_IO = np.load(os.path.join(TEX, "ref_imageio.npz"))
+IMAGEIO_TOOL = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "imageio_tool")
+
+
+def _imageio_image():
+    rng = np.random.default_rng(11)
+    img = rng.normal(0.5, 0.6, (19, 33, 3)).astype(np.float32)
+    img[0, 0] = (np.nan, np.inf, -np.inf); img[1, 1] = (1.0, 0.0, 0.999999); img[2, 2] = (1 / 255, 254.999 / 255, 0.5)
+    return img
+
+
+def test_savepng_writes_the_pixels_the_references_savepng_writes(tmp_path):
+    """ImageIO::SavePng (src/imageio.cpp:61-77, main.cpp's screenshot): vertical flip, fmaxf(0, fminf(x, 1)) * 255 truncated —
+    NaN and +inf become 255.  Expected pixels = the PNG the reference's own compiled imageio.cpp wrote (fixture), live too."""
+    from PIL import Image
+    from gpu_pathtracer_b200 import imageio
+    img = _imageio_image()
+    p = str(tmp_path / "shot.png")
+    assert imageio.SavePng(p, 33, 19, img)
+    got = np.asarray(Image.open(p))
+    assert np.array_equal(got, REF_IO["savepng_pixels"])
+    assert tuple(got[-1, 0]) == (255, 255, 0)                              # (nan, inf, -inf) of the renderer's row 0 = the file's last row
+    if os.path.exists(IMAGEIO_TOOL):
+        raw = str(tmp_path / "in.bin"); img.tofile(raw)
+        subprocess.run([IMAGEIO_TOOL, "savepng", raw, "33", "19", str(tmp_path / "ref.png")], check=True)
+        assert np.array_equal(got, np.asarray(Image.open(str(tmp_path / "ref.png"))))
+
+
+def test_saveexr_and_loadexr_equal_the_references(tmp_path):
+    """ImageIO::SaveExr writes B, G, R as HALF, uncompressed; ImageIO::LoadExr returns the RGB of tinyexr's RGBA."""
+    from gpu_pathtracer_b200 import imageio
+    pos = np.abs(_imageio_image()); pos[~np.isfinite(pos)] = 3.0
+    w, h, got = imageio.LoadExr(os.path.join(TEX, "ref_saveexr.exr"))      # the file the reference's SaveExr wrote
+    assert (w, h) == (33, 19) and np.array_equal(_bits(got), _bits(REF_IO["loadexr_of_saveexr"]))
+    p = str(tmp_path / "mine.exr")
+    assert imageio.SaveExr(p, 33, 19, pos)
+    mine, ref = open(p, "rb").read(), open(os.path.join(TEX, "ref_saveexr.exr"), "rb").read()
+    hm, hr = exr._parse_header(mine), exr._parse_header(ref)
+    assert hm[:4] == hr[:4]                                                # channels B G R as HALF, compression NONE, same window
+    assert np.array_equal(_bits(imageio.LoadExr(p)[2]), _bits(got))
+    if os.path.exists(IMAGEIO_TOOL):
+        out = str(tmp_path / "o.bin")
+        subprocess.run([IMAGEIO_TOOL, "loadexr", p, out], check=True)      # the reference reads the file this package wrote
+        live = np.frombuffer(open(out, "rb").read(), np.float32, offset=8).reshape(19, 33, 3)
+        assert np.array_equal(_bits(live), _bits(got))
+
+
+@pytest.mark.parametrize("name", sorted(k[8:] for k in REF_IO.files if k.startswith("texture:")))
+def test_texels_equal_what_the_references_texture_constructor_holds(name):
+    """Texture::Texture(file) of the reference's own compiled src/texture.h + src/imageio.cpp (not a restatement of it):
+    every PNG / JPEG fixture; LoadTexture's float4s reduce to the same texels."""
+    from gpu_pathtracer_b200 import imageio
+    want = REF_IO["texture:" + name]
+    got = texio.load_texture(os.path.join(TEX, name), strict=True)
+    assert np.array_equal(got, want)
+    w, h, rgba = imageio.LoadTexture(os.path.join(TEX, name))
+    assert (h, w) == want.shape[:2] and np.array_equal((rgba * np.float32(255.0)).astype(np.uint8), want)
+
+
 def test_texture_conversion_rule():
     img = np.asarray([[[0, 128, 255]], [[255, 0, 64]]], np.uint8)           # 2 rows, 1 column
     t = texio.texels_from_bytes(img)
