@@ -2,7 +2,11 @@
 BeginRender / Render / EndRender boundary (brickray/gpu-pathtracer, src/pathtracer.h:10-12).
 
     layouts   numpy dtypes of the reference's structs
-    scenes    scene JSON / OBJ front-end and the synthetic config scenes
+    scenes    scene JSON front-end (equal to the reference's LoadScene field by field) and the synthetic config scenes
+    meshio    OBJ / PLY import with assimp's Triangulate / GenSmoothNormals rules
+    xform     the parser's transform arithmetic in the float32 operation order of the reference's GLM
+    imageio   the reference's ImageIO under its own names: LoadTexture, SavePng, LoadExr, SaveExr
+    textures / jpeg / exr   texel conversion, stb_image-exact JPEG decoding, OpenEXR scan-line reader / writer
     _lib      ctypes binding of the C ABI (include/b200pt.h)
     renderer  PathTracer: Python mirror of BeginRender / Render / EndRender
 """
