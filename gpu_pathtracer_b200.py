@@ -10,3 +10,7 @@ _spec = importlib.util.spec_from_file_location("gpu_pathtracer_b200", os.path.jo
 _mod = importlib.util.module_from_spec(_spec)
 sys.modules["gpu_pathtracer_b200"] = _mod
 _spec.loader.exec_module(_mod)
+
+if __name__ == "__main__":                      # python gpu_pathtracer_b200.py scene.json --spp N --png out.png
+    from gpu_pathtracer_b200.cli import main
+    sys.exit(main())
