@@ -36,6 +36,7 @@ class JpegUnsupported(JpegError):
 
 _ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+_ZZ = _ZIGZAG.tolist()
 
 
 def _f2f(x):
@@ -170,8 +171,6 @@ def _decode_block(bits, hdc, hac, quant, pred):
     bits.pos = pos
     return out, pred
 
-
-_ZZ = _ZIGZAG.tolist()
 
 
 def _segments(buf, pos):
@@ -327,7 +326,6 @@ def _decode(buf):
             c["coef"] = (np.array(c["blocks"], np.int64).astype(np.int16).astype(np.int64) * qnat)
         px = _idct(c["coef"].astype(np.int16).reshape(-1, 8, 8))    # (short) truncation of coefficient * quantiser
         planes.append(px.reshape(c["bh"], c["bw"], 8, 8).transpose(0, 2, 1, 3).reshape(c["bh"] * 8, c["bw"] * 8))
-    w, h = frame["w"], frame["h"]
     full = [_upsample(planes[k], comps[k], frame) for k in range(len(comps))]
     if len(comps) == 1:
         return full[0]
