@@ -556,3 +556,63 @@ def test_scene_json_takes_a_matrix_frame_for_the_infinite_light(tmp_path):
     p.write_text(json.dumps(doc))
     with pytest.raises(ValueError, match="uninitialised"):
         pt.scenes.load_scene_json(str(p))
+
+
+# ------------------------------------------------------------------------------------------------ live fuzzing (build container)
+_TEX_TOOL = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tex_tool")
+
+
+@pytest.mark.skipif(not os.path.exists(_TEX_TOOL), reason="the reference's decoder is only compiled in the build container")
+def test_jpeg_decoder_fuzz_against_the_references_stb_image(tmp_path):
+    """40 random Pillow-written JPEGs (sizes 1..89, noise / pattern / flat, quality 5..100, baseline or progressive, every
+    sub-sampling, optimised tables, restart intervals, grey): jpeg.load == stbi_load, byte for byte.  (150 of these and 60 PIZ
+    files were run when the decoders were written: no difference.)"""
+    from PIL import Image
+    from gpu_pathtracer_b200 import jpeg
+    rng = np.random.default_rng(2026)
+    p = str(tmp_path / "f.jpg")
+    for k in range(40):
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        elif kind == 1:
+            y, x = np.mgrid[0:h, 0:w]
+            img = np.stack([(x * 5 + y * 3) % 256, (x * y) % 256, 255 - (x + y) % 256], -1).astype(np.uint8)
+        else:
+            img = np.full((h, w, 3), rng.integers(0, 256, 3), np.uint8)
+            img[h // 2:, :, 0] = 255
+        grey = rng.random() < 0.15
+        opts = dict(quality=int(rng.integers(5, 101)), progressive=bool(rng.random() < 0.4), optimize=bool(rng.random() < 0.5))
+        if not grey:
+            opts["subsampling"] = int(rng.integers(0, 3))
+        if rng.random() < 0.3:
+            opts["restart_marker_blocks"] = int(rng.integers(1, 6))
+        Image.fromarray(img[..., 0] if grey else img).save(p, **opts)
+        subprocess.run([_TEX_TOOL, p, p + ".bin", "raw"], check=True)
+        b = open(p + ".bin", "rb").read()
+        ww, hh, c = struct.unpack("<iii", b[:12])
+        want = np.frombuffer(b, np.uint8, offset=12).reshape(hh, ww, c)[::-1]
+        assert np.array_equal(jpeg.load(p).reshape(hh, ww, c), want), (k, w, h, opts)
+
+
+@pytest.mark.skipif(not os.path.exists(TOOL), reason="the reference's EXR code is only compiled in the build container")
+def test_piz_reader_fuzz_against_the_references_tinyexr(tmp_path):
+    rng = np.random.default_rng(77)
+    raw, p = str(tmp_path / "f.bin"), str(tmp_path / "f.exr")
+    for k in range(20):
+        w, h = int(rng.integers(1, 150)), int(rng.integers(1, 100))
+        y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            img = np.stack([np.sin(x * 0.1) + 1, y * 0.01, (x + y) * 0.001], -1).astype(np.float32)
+        elif kind == 1:
+            img = np.round(rng.random((h, w, 3)) * 4).astype(np.float32)
+        else:
+            img = np.full((h, w, 3), 0.5, np.float32)
+            img[:, : w // 2] = 7.0
+        img.tofile(raw)
+        subprocess.run([TOOL, "save", p, str(w), str(h), "4", str(int(rng.integers(0, 2))), raw], check=True)
+        subprocess.run([TOOL, "load", p, raw + ".out"], check=True)
+        want = np.frombuffer(open(raw + ".out", "rb").read(), np.float32, offset=8).reshape(h, w, 4)
+        assert np.array_equal(_bits(exr.load_exr(p)), _bits(want)), (k, w, h)
