@@ -67,17 +67,10 @@ def _trs(scale, translate, rotate_deg):
 
 def _transform_mesh(tri_v, tri_n, trs):
     """Mesh::processMesh (src/mesh.cpp:50-62): v' = vec3(trs * (v, 1)); n' = normalize(vec3(transpose(inverse(trs)) * (n, 0))),
-    every product and sum in GLM's order (xform.transform_points_normals).  With the identity that arithmetic returns its
-    input (the normal: normalised), except that a component -0.0 comes out as +0.0 ((-0 * 1 + 0) + (0 + 0)); the identity
-    is passed through here without those products, so the scene arrays of the pinned fixtures (made before the GLM order
-    was restated) keep their bits — no comparison in the integrators tells the two zeros apart."""
+    every product and sum in GLM's order (xform.transform_points_normals).  The identity goes through the same arithmetic, as
+    in the reference: it returns its input (the normal: normalised) except that a component -0.0 comes out as +0.0
+    ((-0 * 1 + 0) + (0 + 0)) — which is what the reference's parser hands to Scene::Init (tests/test_parser_vs_reference.py)."""
     tri_v = np.asarray(tri_v, F); tri_n = np.asarray(tri_n, F)
-    if np.array_equal(trs, np.eye(4, dtype=F)):
-        # glm::normalize = v * (1 / sqrt(dot(v, v))) in float32, dot = (x*x + y*y) + z*z
-        with np.errstate(invalid="ignore", divide="ignore"):
-            d = (tri_n[..., 0] * tri_n[..., 0] + tri_n[..., 1] * tri_n[..., 1]).astype(F) + (tri_n[..., 2] * tri_n[..., 2]).astype(F)
-            inv = (F(1.0) / np.sqrt(d.astype(F))).astype(F)
-        return tri_v.copy(), (tri_n * inv[..., None]).astype(F)
     return xform.transform_points_normals(np.ascontiguousarray(np.asarray(trs, F).T), tri_v, tri_n)
 
 
@@ -292,9 +285,8 @@ def load_scene_json(path, prep=None, overrides=None):
         elif "line" in u:                               # src/parsescene.cpp:393-424: end points through t * r * s, radii as given
             trs = _trs(u.get("scale", [1, 1, 1]), u.get("translate", [0, 0, 0]), u.get("rotate", [0, 0, 0]))
             ends = np.asarray([u.get("p0", [0, 0, 0]), u.get("p1", [1, 1, 1])], F)
-            if not np.array_equal(trs, np.eye(4, dtype=F)):                       # vec3(trs * vec4(p, 1)), GLM's order
-                ex, ey, ez, _ = xform.mul_vec4(np.ascontiguousarray(trs.T), ends[:, 0], ends[:, 1], ends[:, 2], F(1.0))
-                ends = np.stack([ex, ey, ez], -1).astype(F)
+            ex, ey, ez, _ = xform.mul_vec4(np.ascontiguousarray(trs.T), ends[:, 0], ends[:, 1], ends[:, 2], F(1.0))   # vec3(trs * vec4(p, 1)), GLM's order
+            ends = np.stack([ex, ey, ez], -1).astype(F)
             prims.append(line_prims(ends[:1], ends[1:], [u.get("width0", 0.025)], [u.get("width1", 0.025)], mat_idx(u.get("material", "matte"))))
         else:
             raise ValueError("scene unit is neither a mesh, a sphere nor a line")

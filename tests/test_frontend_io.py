@@ -495,12 +495,10 @@ def test_trs_and_vertex_transform_equal_the_references_glm_bit_for_bit():
         assert np.array_equal(_bits(xform.transpose(xform.inverse(m)).ravel()), _bits(d["inv_t"][i])), i
         v, n = xform.transform_points_normals(m, r[None, 9:12], r[None, 12:15])
         assert np.array_equal(_bits(v[0]), _bits(d["v"][i])) and np.array_equal(_bits(n[0]), _bits(d["n"][i])), i
-        # the loader's entry points (row-major trs, arrays of triangles) give the same bits — except for the identity,
-        # which is passed through (signed zeros kept, scenes._transform_mesh)
+        # the loader's entry points (row-major trs, arrays of triangles) give the same bits, the identity included
         t = pt.scenes._trs(r[0:3], r[3:6], r[6:9])
         tv, tn = pt.scenes._transform_mesh(np.tile(r[9:12], (2, 3, 1)), np.tile(r[12:15], (2, 3, 1)), t)
-        if not np.array_equal(t, np.eye(4, dtype=np.float32)):
-            assert np.array_equal(_bits(tv[1, 2]), _bits(d["v"][i])) and np.array_equal(_bits(tn[1, 2]), _bits(d["n"][i])), i
+        assert np.array_equal(_bits(tv[1, 2]), _bits(d["v"][i])) and np.array_equal(_bits(tn[1, 2]), _bits(d["n"][i])), i
 
 
 def test_infinite_light_frames_equal_the_references_glm_bit_for_bit():

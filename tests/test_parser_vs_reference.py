@@ -13,9 +13,7 @@ texture's texels, the Infinite light's frame / size / texels.  Not compared, wit
   * Vertex.t — tangents the reference accumulates in processMesh; no function reachable from Path / Volpath reads them
     (the loader leaves zeros);
   * mediumInside / mediumOutside of LIGHT triangles and the union members a Medium's type does not use: the reference
-    never writes them (uninitialised memory in its dump);
-  * signed zeros under an identity transform: the reference's trs * v turns -0 into +0, the loader passes the identity
-    through (scenes._transform_mesh explains why) — such meshes are compared by VALUE, all others by bits."""
+    never writes them (uninitialised memory in its dump)."""
 import gzip
 import os
 import subprocess
@@ -40,20 +38,17 @@ def staged(tmp_path_factory):
     return dst
 
 
-def _same(a, b, by_value=False):
-    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
-    if by_value:
-        return a.shape == b.shape and bool(np.all(a == b))
-    return a.tobytes() == b.tobytes()
+def _same(a, b):
+    return np.ascontiguousarray(a).tobytes() == np.ascontiguousarray(b).tobytes()
 
 
-def _check_vertices(ref_tri, mine_tri, what, by_value):
+def _check_vertices(ref_tri, mine_tri, what):
     for v in ("v1", "v2", "v3"):
         for f in ("v", "n", "uv"):
-            assert _same(ref_tri[v][f], mine_tri[v][f], by_value), f"{what}.{v}.{f}"
+            assert _same(ref_tri[v][f], mine_tri[v][f]), f"{what}.{v}.{f}"
 
 
-def _compare(ref, mine, identity_only):
+def _compare(ref, mine):
     assert (ref["width"], ref["height"]) == (mine["width"], mine["height"])
     assert ref["epsilon"] == np.float32(mine["epsilon"])
     assert ref["integrator"] == {"pt": L.IT_PT, "vpt": L.IT_VPT}[mine["integrator"]] and ref["max_depth"] == mine["max_depth"]
@@ -74,7 +69,7 @@ def _compare(ref, mine, identity_only):
     assert len(rp) == len(mp) and np.array_equal(rp["type"], mp["type"])
     tri = rp["type"] == L.GT_TRIANGLE
     rt, mt = rp["triangle"][tri], mp["triangle"][tri]
-    _check_vertices(rt, mt, "triangle", identity_only)
+    _check_vertices(rt, mt, "triangle")
     is_light = rt["lightIdx"] != -1
     for f in ("matIdx", "bssrdfIdx", "lightIdx"):
         assert _same(rt[f], mt[f]), f"triangle.{f}"
@@ -89,7 +84,7 @@ def _compare(ref, mine, identity_only):
     assert len(ref["lights"]) == len(mine["lights"])
     if len(ref["lights"]):
         assert _same(ref["lights"]["radiance"], mine["lights"]["radiance"]) and _same(ref["lights"]["medium"], mine["lights"]["medium"])
-        _check_vertices(ref["lights"]["triangle"], mine["lights"]["triangle"], "light.triangle", identity_only)
+        _check_vertices(ref["lights"]["triangle"], mine["lights"]["triangle"], "light.triangle")
         for f in ("matIdx", "bssrdfIdx", "lightIdx"):
             assert _same(ref["lights"]["triangle"][f], mine["lights"]["triangle"][f]), f"light.triangle.{f}"
     mtex = mine.get("textures") or []
@@ -114,7 +109,7 @@ def _compare(ref, mine, identity_only):
 def test_loader_equals_the_references_parser(name, staged):
     ref = pc.read_dump(gzip.open(os.path.join(GOLD, name + ".bin.gz"), "rb").read())
     mine = pc.loader_arrays(os.path.join(staged, name))
-    _compare(ref, mine, identity_only=not name.startswith("everything"))
+    _compare(ref, mine)
 
 
 @pytest.mark.skipif(not os.path.exists(TOOL), reason="the reference's parser is only compiled in the build container")
@@ -123,7 +118,7 @@ def test_loader_equals_the_references_parser_live(name, staged):
     out = os.path.join(staged, name + ".live.bin")
     subprocess.run([TOOL, os.path.join(staged, name), out], check=True, stdout=subprocess.DEVNULL)
     ref = pc.read_dump(open(out, "rb").read())
-    _compare(ref, pc.loader_arrays(os.path.join(staged, name)), identity_only=not name.startswith("everything"))
+    _compare(ref, pc.loader_arrays(os.path.join(staged, name)))
 
 
 REF_SCENES = "/root/reference/scenes/cornell_box"
@@ -151,7 +146,7 @@ def test_the_references_shipped_scene_files_load_as_its_parser_loads_them(name, 
             pc.write_sidecar(os.path.join(dst, m))
     out = os.path.join(dst, name + ".bin")
     subprocess.run([TOOL, os.path.join(dst, name), out], check=True, stdout=subprocess.DEVNULL)
-    _compare(pc.read_dump(open(out, "rb").read()), pc.loader_arrays(os.path.join(dst, name)), identity_only=True)
+    _compare(pc.read_dump(open(out, "rb").read()), pc.loader_arrays(os.path.join(dst, name)))
 
 
 def test_the_scene_with_everything_renders_bit_exactly_against_the_oracle(staged, oracle):
